@@ -1,0 +1,112 @@
+"""Contact-map readers (host side).  Only the text reader is implemented natively; `.hic` / `.cool` / `.mcool`
+inputs need the same third-party packages the reference needs (hicstraw, cooler) and are imported lazily, so the
+package imports cleanly on images that lack them (this one does).
+
+Restates mustache.py:199-297 (`get_sep`, `read_bias`, `read_pd`).  Out of scope for kernels.
+"""
+import numpy as np
+
+
+def strip_chr(name):
+    return str(name).replace("chr", "")
+
+
+def same_chromosome(a, b):
+    """mustache.py:191-196."""
+    return strip_chr(a) == strip_chr(b)
+
+
+def guess_separator(path):
+    """mustache.py:199-215: decided from the first line only."""
+    with open(path) as fh:
+        for line in fh:
+            if "\t" in line:
+                return "\t"
+            if " " in line.strip():
+                return " "
+            if "," in line:
+                return ","
+            if len(line.split(" ")) == 1:
+                return " "
+            break
+    raise FileNotFoundError(path)
+
+
+def read_bias(path, chromosome, res):
+    """mustache.py:218-251.  Returns {bin: bias}; bias < 0.2 or NaN becomes +inf (the contact is then dropped)."""
+    if not path:
+        return False
+    table = {}
+    sep = guess_separator(path)
+    with open(path) as fh:
+        for pos, line in enumerate(fh):
+            parts = line.strip().split(sep)
+            if len(parts) == 3:
+                if not same_chromosome(parts[0], chromosome):
+                    continue
+                key, val = float(parts[1]) // res, float(parts[2])
+            elif len(parts) == 1:
+                key, val = pos, float(parts[0])
+            else:
+                continue
+            table[key] = np.inf if (np.isnan(val) or val < 0.2) else val
+    return table
+
+
+def _bias_factors(table, bins):
+    uniq, inv = np.unique(np.asarray(bins), return_inverse=True)
+    vals = np.array([table.get(b, 1) for b in uniq.tolist()], dtype=np.float64)
+    return vals[inv]
+
+
+def read_text(path, distance_in_bp, bias_path, chromosome, res):
+    """mustache.py:254-297 (`read_pd`): 5-column (chr pos chr pos count) or 3-column (pos pos count) text.
+
+    Returns upper-triangular COO (x, y, value) in bin units: |pos1-pos2| <= (distance/res + 1)*res, divided by both
+    biases (in that order), non-positive values dropped.
+    """
+    import pandas as pd
+    sep = guess_separator(path)
+    df = pd.read_csv(path, sep=sep, header=None)
+    df = df.dropna()
+    limit = (distance_in_bp / res + 1) * res
+    if df.shape[1] == 5:
+        c1 = df[0].map(lambda s: same_chromosome(s, chromosome)).to_numpy(dtype=bool)
+        df = df[c1]
+        if df.shape[0] == 0:
+            print("Could't read any interaction for this chromosome!")
+            return None
+        c2 = df[2].map(lambda s: same_chromosome(s, chromosome)).to_numpy(dtype=bool)
+        df = df[c2]
+        a, b, val = df[1].to_numpy(), df[3].to_numpy(), df[4].to_numpy(dtype=np.float64)
+    elif df.shape[1] == 3:
+        a, b, val = df[0].to_numpy(), df[1].to_numpy(), df[2].to_numpy(dtype=np.float64)
+    else:
+        raise ValueError("expected a 3- or 5-column contact file, got %d columns" % df.shape[1])
+    near = np.abs(a - b) <= limit
+    a, b, val = a[near] // res, b[near] // res, val[near]
+    table = read_bias(bias_path, chromosome, res)
+    if table:
+        val = np.divide(val, _bias_factors(table, a))
+        val = np.divide(val, _bias_factors(table, b))
+    pos = val > 0
+    a, b, val = a[pos], b[pos], val[pos]
+    return np.minimum(a, b), np.maximum(a, b), np.array(val)
+
+
+def read_hic(path, norm_method, chrom_size, distance_in_bp, chr1, chr2, res):  # pragma: no cover - dependency absent
+    """mustache.py:300-396 needs `hicstraw`; not installed in this image."""
+    try:
+        import hicstraw  # noqa: F401
+    except ImportError as e:
+        raise ImportError(".hic input needs the `hicstraw` package (as the reference does)") from e
+    raise NotImplementedError(".hic reading is outside the accelerated path; see DESIGN.md (out of scope)")
+
+
+def read_cool(path, distance_in_bp, chr1, chr2, norm_method, res=None):  # pragma: no cover - dependency absent
+    """mustache.py:399-592 needs `cooler`; not installed in this image."""
+    try:
+        import cooler  # noqa: F401
+    except ImportError as e:
+        raise ImportError(".cool/.mcool input needs the `cooler` package (as the reference does)") from e
+    raise NotImplementedError(".cool reading is outside the accelerated path; see DESIGN.md (out of scope)")

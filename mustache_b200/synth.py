@@ -1,0 +1,102 @@
+"""Seeded synthetic contact tiles (BASELINE.json configs 2-5; definitions in SURVEY.md section 8(d)).
+
+Everything is generated in *band layout*  B[i, d - 4]  for diagonals d = j - i in [4, dpx + 1], which is the
+only part of a block the reference's text reader ever populates (mustache.py:264 keeps |j-i| <= dpx+1) and
+the only part the mask can select (mustache.py:699 needs j-i >= 4).  `band_to_dense` expands to the dense
+N x N tile `regulator()` builds at mustache.py:923-924.
+"""
+import numpy as np
+
+BAND_LO = 4  # first diagonal that can be in the mask (np.triu(c, 4), mustache.py:699)
+
+
+def band_width(dpx):
+    return dpx + 1 - BAND_LO + 1
+
+
+def dense_band_tile(n, dpx, seed=1001, blob_seed=1002, nblobs=200, missing=0.0, dtype=np.float64):
+    """Config 2: every cell with 5 <= j-i <= dpx ~ N(0,1); cells on diagonals 4 and dpx+1 non-zero;
+    `nblobs` planted blobs A*exp(-r^2/2s^2), A ~ U(6,15), s in {1.5,3,6,12}; optional fraction of missing cells."""
+    w = band_width(dpx)
+    rng = np.random.default_rng(seed)
+    band = rng.standard_normal((n, w)).astype(dtype, copy=False)
+    band[band == 0] = 1.0
+    if missing > 0:
+        band[rng.random((n, w)) < missing] = 0.0
+    brng = np.random.default_rng(blob_seed)
+    sig_choices = np.array([1.5, 3.0, 6.0, 12.0])
+    for _ in range(nblobs):
+        s = float(brng.choice(sig_choices))
+        amp = float(brng.uniform(6, 15))
+        d0 = int(brng.integers(10, max(11, dpx - 10)))
+        i0 = int(brng.integers(0, max(1, n - d0)))
+        j0 = i0 + d0
+        r = int(np.ceil(4 * s))
+        ii = np.arange(max(0, i0 - r), min(n, i0 + r + 1))
+        jj = np.arange(max(0, j0 - r), min(n, j0 + r + 1))
+        g = amp * np.exp(-((ii[:, None] - i0) ** 2 + (jj[None, :] - j0) ** 2) / (2 * s * s))
+        dd = jj[None, :] - ii[:, None]
+        ok = (dd >= BAND_LO) & (dd <= dpx + 1)
+        bi = np.broadcast_to(ii[:, None], dd.shape)[ok]
+        bd = dd[ok] - BAND_LO
+        keep = band[bi, bd] != 0
+        band[bi[keep], bd[keep]] += g[ok][keep]
+    # clip to the tile: (i, i+d) must have i+d < n
+    i = np.arange(n)[:, None]
+    d = np.arange(w)[None, :] + BAND_LO
+    band[(i + d) >= n] = 0.0
+    return band
+
+
+def band_to_dense(band, n=None):
+    n = band.shape[0] if n is None else n
+    w = band.shape[1]
+    c = np.zeros((n, n), dtype=band.dtype)
+    i = np.arange(band.shape[0])[:, None]
+    j = i + np.arange(w)[None, :] + BAND_LO
+    ok = j < n
+    c[np.broadcast_to(i, j.shape)[ok], j[ok]] = band[ok]
+    return c
+
+
+def band_to_coo(band, n=None):
+    n = band.shape[0] if n is None else n
+    i, k = np.nonzero(band)
+    j = i + k + BAND_LO
+    ok = j < n
+    return i[ok].astype(np.int32), j[ok].astype(np.int32), band[i[ok], k[ok]]
+
+
+def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed=None):
+    """Configs 3/4: raw counts ~ Poisson(lam(d)), lam(d) = lam_scale/(d+1) for d >= 1 (30 at d = 0), bias == 1,
+    planted loops adding Poisson(8) in a 3x3 patch.  Returns upper-triangular COO (x, y, count) with |y-x| <= dpx+1,
+    i.e. what read_pd() would return for a 3/5-column text file of these counts (mustache.py:254-297)."""
+    rng = np.random.default_rng(seed)
+    xs, ys, vs = [], [], []
+    for d in range(0, dpx + 2):
+        lam = 30.0 if d == 0 else lam_scale / (d + 1)
+        m = n - d
+        if m <= 0:
+            break
+        cnt = rng.poisson(lam, m)
+        nzi = np.nonzero(cnt)[0]
+        xs.append(nzi)
+        ys.append(nzi + d)
+        vs.append(cnt[nzi])
+    x = np.concatenate(xs).astype(np.int64)
+    y = np.concatenate(ys).astype(np.int64)
+    v = np.concatenate(vs).astype(np.float64)
+    if nloops:
+        lrng = np.random.default_rng(seed + 1 if loop_seed is None else loop_seed)
+        import scipy.sparse as sp
+        a = sp.coo_matrix((v, (x, y)), shape=(n, n)).tolil()
+        for _ in range(nloops):
+            d0 = int(lrng.integers(12, dpx - 4))
+            i0 = int(lrng.integers(2, n - d0 - 2))
+            for di in (-1, 0, 1):
+                for dj in (-1, 0, 1):
+                    a[i0 + di, i0 + d0 + dj] += lrng.poisson(8)
+        a = a.tocoo()
+        keep = a.data > 0
+        x, y, v = a.row[keep].astype(np.int64), a.col[keep].astype(np.int64), a.data[keep].astype(np.float64)
+    return x, y, v

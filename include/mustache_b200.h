@@ -1,0 +1,113 @@
+/* mustache_b200 -- C ABI of the B200 scale-space engine.
+ *
+ * Drop-in boundary for the hot path of ay-lab/mustache v1.3.3.  The reference has no plugin API; the seam is the body
+ * of `mustache()` between mustache/mustache.py:699 and :772 (and diff_mustache.py:262-425): given one dense N x N tile
+ * of normalised contacts it produces, for every mask pixel, the best DoG response, its scale and its p-value.
+ * Each entry point below cites the reference lines it replaces.  Plain C types only; every function returns 0 on
+ * success or a negative MB200_ERR_* code and never throws or aborts; mb200_last_error() gives the message.
+ *
+ * Usage (one engine per GPU per process; an engine is not thread-safe, distinct engines are independent):
+ *   mb200_create -> mb200_set_program -> mb200_configure -> mb200_upload_* (one per block) -> mb200_run
+ *   -> mb200_block_counts / mb200_fetch_records -> ... -> mb200_destroy
+ */
+#ifndef MUSTACHE_B200_H
+#define MUSTACHE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MB200_API __attribute__((visibility("default")))
+#else
+#define MB200_API
+#endif
+
+#define MB200_OK 0
+#define MB200_ERR_CUDA (-1)       /* a CUDA call failed */
+#define MB200_ERR_ARG (-2)        /* bad argument / call order */
+#define MB200_ERR_CAPACITY (-3)   /* more records than the configured capacity; raise record_fraction and rerun */
+#define MB200_ERR_NONFINITE (-4)  /* tile holds NaN/Inf (scipy.stats.expon.fit raises ValueError, mustache.py:755) */
+#define MB200_ERR_NOMEM (-5)      /* device memory */
+
+#define MB200_STEP_RESTART 1      /* chain cut before this Gaussian (first level of an octave that shares nothing) */
+#define MB200_STEP_SCORE 2        /* score the previous DoG once this step's DoG exists (mustache.py:760-768) */
+#define MB200_STEP_DIFFREF 4      /* this step's DoG is the octave's L_2 (diff_mustache.py:336, never rotated) */
+
+typedef struct mb200_engine mb200_engine;
+
+MB200_API int mb200_abi_version(void);
+MB200_API int mb200_device_count(int* count);
+
+/* One engine = one CUDA device + one stream + scratch.  Replaces the per-block multiprocessing.Process of
+ * mustache.py:926-934 (regulator) as the unit of execution. */
+MB200_API int mb200_create(int device, mb200_engine** out);
+MB200_API void mb200_destroy(mb200_engine* e);
+MB200_API const char* mb200_last_error(const mb200_engine* e);
+
+/* Scale table: the chain of Gaussians with strictly increasing sigma (mustache.py:714-752 evaluated on the host with
+ * numpy exactly as scipy does; see mustache_b200/ladder.py).  Per step: truncation radius, flags, and for scoring
+ * steps the id reported in records (octave*12 + i, i.e. the reference's scales[o][i]).
+ * half_taps: concatenated weights w[0..R] (centre first) of every step; tap_off[s] indexes into it. */
+MB200_API int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags, const int32_t* score_id,
+                      const int32_t* tap_off, const double* half_taps, int n_taps);
+
+/* Geometry of the next batch: nblocks tiles of side n (CHUNK_SIZE, mustache.py:896), distance_in_px (mustache.py:892),
+ * intra = chromosome == chromosome2 (mustache.py:705).  record_fraction: record capacity as a fraction of the band
+ * pixels (<= 0 selects the default 1/8). */
+MB200_API int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, double record_fraction);
+
+/* Tile inputs, the state of `cc` at mustache.py:923-924 (normalised, scattered, NOT yet 2-filled).
+ *  _coo_host   : block-local COO with unique coordinates (host pointers); entries off the band are ignored
+ *  _dense_host : row-major n x n host tile, leading dimension ld (only diagonals 4..dpx+1 are transferred)
+ *  _dense_dev  : same, device pointer (e.g. torch.Tensor.data_ptr())
+ *  _band_host  : band layout [n][wsrc], element (i, k) = tile[i][i+4+k]  (host pointer) */
+MB200_API int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const int32_t* cols, const double* vals,
+                          int64_t nnz);
+MB200_API int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int64_t ld);
+MB200_API int mb200_upload_dense_dev(mb200_engine* e, int block, const double* tile_dev, int64_t ld);
+MB200_API int mb200_upload_band_host(mb200_engine* e, int block, const double* band, int64_t wsrc);
+
+/* Runs the whole scale-space loop for all uploaded blocks: mask + fills (mustache.py:699-706), 12 Gaussians per octave
+ * (:719-751), DoG (:728,738,754), 3x3 maxima (:740-743,757), extremum test and running best (:760-768), exponential fit
+ * and p-value (:755-756).  Asynchronous on the engine's stream; mb200_sync / the fetch calls wait. */
+MB200_API int mb200_run(mb200_engine* e);
+MB200_API int mb200_sync(mb200_engine* e);
+
+/* nz_count = np.sum(nz) (mustache.py:701; guards at :701 and :775 stay with the caller), n_found = sum(pAll != 2). */
+MB200_API int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, int64_t* n_found);
+
+/* Records of every pixel with pAll != 2 (mustache.py:774), unordered: tile row, tile column, vAll, score id, raw p.
+ * Caller-allocated arrays of `capacity` elements; *n_out receives the number of records the block has (may exceed
+ * capacity, in which case only `capacity` are written). */
+MB200_API int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* rows, int32_t* cols, double* v,
+                        int32_t* score_id, double* p, int64_t* n_out);
+
+/* Exponential fit per scored step of a block (loc = min|L|, scale = mean|L| - loc, mustache.py:755): arrays of n_scored. */
+MB200_API int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored);
+
+/* Device time of the last mb200_run in milliseconds (CUDA events on the engine's stream):
+ * prep (mask count), axis-0 kernel, axis-1+extremum kernel, statistics+p-values, total. */
+MB200_API int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* fin_ms, float* total_ms);
+/* Kernel launches issued by the last mb200_run. */
+MB200_API int mb200_last_launches(mb200_engine* e, int* launches);
+
+/* Parity hooks: the Gaussian of chain step `step` and the DoG it completes, for block `block`, as dense n x n host
+ * arrays (valid on the diagonals 2..dhi+2 the detector reads; zero elsewhere).  Either pointer may be NULL. */
+MB200_API int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, double* dog_out);
+
+/* Pinned host memory for callers that want full-speed uploads. */
+MB200_API int mb200_host_alloc(void** ptr, int64_t bytes);
+MB200_API int mb200_host_free(void* ptr);
+
+/* One-call drop-in for the scale-space half of `mustache(c, ...)` (mustache.py:697-772) on a host tile. */
+MB200_API int mb200_scale_space_dense(mb200_engine* e, const double* tile, int n, int64_t ld, int dpx, int intra, int64_t capacity,
+                            int32_t* rows, int32_t* cols, double* v, int32_t* score_id, double* p, int64_t* nz_count,
+                            int64_t* n_found);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,576 @@
+// C-ABI host side of the scale-space engine (see include/mustache_b200.h for the contract and the reference
+// lines each entry point replaces).  Owns one CUDA stream and grow-only device scratch; no torch types anywhere.
+#include "../../include/mustache_b200.h"
+#include "mb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct mb200_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    MbProgram prog;
+    bool have_prog = false;
+    bool configured = false;
+    bool ran = false;
+    int n = 0, dpx = 0, intra = 1, dhi = 0, wc = 0, vlo = 0, wv = 0, nblocks = 0, pass_blocks = 0;
+    long long rec_cap = 0;
+    int ncta_h = 0;
+    DevBuf raw, V, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
+        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL;
+    std::vector<unsigned long long> h_nz, h_rec;
+    std::vector<int> h_nonfinite;
+    bool counts_valid = false;
+    cudaEvent_t ev_begin = nullptr, ev_prep = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_pass;   // 3 per pass: start, after kv, after kh
+    float t_prep = 0, t_kv = 0, t_kh = 0, t_fin = 0, t_total = 0;
+    int launches = 0;
+    size_t kv_smem_set = 0, kh_smem_set = 0;
+};
+
+namespace {
+
+int fail(mb200_engine* e, int code, const char* fmt, ...) {
+    if (e) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(e->err, sizeof(e->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(e, call)                                                                                           \
+    do {                                                                                                      \
+        cudaError_t _st = (call);                                                                             \
+        if (_st != cudaSuccess)                                                                               \
+            return fail((e), _st == cudaErrorMemoryAllocation ? MB200_ERR_NOMEM : MB200_ERR_CUDA, "%s: %s",   \
+                        #call, cudaGetErrorString(_st));                                                      \
+    } while (0)
+
+int ensure(mb200_engine* e, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return MB200_OK;
+    if (b.p) {
+        CU(e, cudaStreamSynchronize(e->stream));
+        CU(e, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    CU(e, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return MB200_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int use_device(mb200_engine* e) {
+    CU(e, cudaSetDevice(e->device));
+    return MB200_OK;
+}
+
+size_t v_bytes_per_block(const mb200_engine* e) {
+    return (size_t)e->prog.n_steps * e->n * e->wv * sizeof(double);
+}
+
+MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
+    MbGeom g;
+    g.n = e->n;
+    g.dpx = e->dpx;
+    g.intra = e->intra;
+    g.dhi = e->dhi;
+    g.wc = e->wc;
+    g.vlo = e->vlo;
+    g.wv = e->wv;
+    g.nblk = nblk;
+    g.ncta_h = e->ncta_h;
+    g.dbg_step = -1;
+    g.rec_cap = e->rec_cap;
+    const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
+    g.raw = (const double*)e->raw.p + (size_t)first_block * e->n * e->wc;
+    g.V = (double*)e->V.p;
+    g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
+    g.part_sum = (double*)e->part_sum.p + (size_t)first_block * ns * e->ncta_h;
+    g.rec_count = (unsigned long long*)e->rec_count.p + first_block;
+    g.rec_row = (int*)e->rec_row.p + (size_t)first_block * e->rec_cap;
+    g.rec_col = (int*)e->rec_col.p + (size_t)first_block * e->rec_cap;
+    g.rec_v = (double*)e->rec_v.p + (size_t)first_block * e->rec_cap;
+    g.rec_sidx = (int*)e->rec_sidx.p + (size_t)first_block * e->rec_cap;
+    g.dbgG = nullptr;
+    g.dbgL = nullptr;
+    return g;
+}
+
+dim3 kv_grid(const mb200_engine* e, int nblk) {
+    const int span = e->wv + KV_TH - 1;
+    return dim3((span + KV_TW - 1) / KV_TW, (e->n + KV_TH - 1) / KV_TH, nblk);
+}
+
+dim3 kh_grid(const mb200_engine* e, int nblk) {
+    const int span = (e->dhi - 4 + 1) + KH_SR - 1;
+    return dim3((span + KH_SC - 1) / KH_SC, (e->n + KH_SR - 1) / KH_SR, nblk);
+}
+
+int set_smem_limits(mb200_engine* e) {
+    const size_t kvb = kv_smem_bytes(e->prog.rmax), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
+    if (kvb > 227 * 1024 || khb > 227 * 1024)
+        return fail(e, MB200_ERR_ARG, "radius %d needs %zu / %zu bytes of shared memory (> 227 KB)", e->prog.rmax, kvb, khb);
+    if (kvb != e->kv_smem_set) {
+        CU(e, cudaFuncSetAttribute(kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        e->kv_smem_set = kvb;
+    }
+    if (khb != e->kh_smem_set) {
+        CU(e, cudaFuncSetAttribute(kh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        e->kh_smem_set = khb;
+    }
+    return MB200_OK;
+}
+
+int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cudaEvent_t after_kv) {
+    MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
+    const size_t kvb = kv_smem_bytes(e->prog.rmax), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
+    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(e->prog, g);
+    CU(e, cudaGetLastError());
+    if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
+    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(e->prog, g);
+    CU(e, cudaGetLastError());
+    e->launches += 2;
+    return MB200_OK;
+}
+
+int check_block(mb200_engine* e, int block) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured) return fail(e, MB200_ERR_ARG, "mb200_configure has not been called");
+    if (block < 0 || block >= e->nblocks) return fail(e, MB200_ERR_ARG, "block %d out of range [0,%d)", block, e->nblocks);
+    return MB200_OK;
+}
+
+int refresh_counts(mb200_engine* e) {
+    if (e->counts_valid) return MB200_OK;
+    if (!e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
+    e->h_nz.resize(e->nblocks);
+    e->h_rec.resize(e->nblocks);
+    e->h_nonfinite.resize(e->nblocks);
+    CU(e, cudaMemcpyAsync(e->h_nz.data(), e->nz_count.p, e->nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(e->h_rec.data(), e->rec_count.p, e->nblocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(e->h_nonfinite.data(), e->nonfinite.p, e->nblocks * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->counts_valid = true;
+    return MB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_abi_version(void) { return 1; }
+
+int mb200_device_count(int* count) {
+    if (!count) return MB200_ERR_ARG;
+    cudaError_t st = cudaGetDeviceCount(count);
+    if (st != cudaSuccess) {
+        *count = 0;
+        return MB200_ERR_CUDA;
+    }
+    return MB200_OK;
+}
+
+int mb200_create(int device, mb200_engine** out) {
+    if (!out) return MB200_ERR_ARG;
+    *out = nullptr;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return MB200_ERR_CUDA;
+    mb200_engine* e = new mb200_engine();
+    e->device = device;
+    memset(&e->prog, 0, sizeof(e->prog));
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_prep) != cudaSuccess ||
+        cudaEventCreate(&e->ev_end) != cudaSuccess) {
+        delete e;
+        return MB200_ERR_CUDA;
+    }
+    *out = e;
+    return MB200_OK;
+}
+
+void mb200_destroy(mb200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    DevBuf* all[] = {&e->raw, &e->V, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
+                     &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
+                     &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL};
+    for (DevBuf* b : all) release(*b);
+    for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_prep) cudaEventDestroy(e->ev_prep);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null engine"; }
+
+int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags, const int32_t* score_id,
+                      const int32_t* tap_off, const double* half_taps, int n_taps) {
+    if (!e || !radius || !flags || !score_id || !tap_off || !half_taps) return fail(e, MB200_ERR_ARG, "null argument");
+    if (n_steps < 1 || n_steps > MB_MAX_STEPS) return fail(e, MB200_ERR_ARG, "n_steps %d not in [1,%d]", n_steps, MB_MAX_STEPS);
+    if (n_taps < 1 || n_taps > MB_MAX_TAPS) return fail(e, MB200_ERR_ARG, "n_taps %d not in [1,%d]", n_taps, MB_MAX_TAPS);
+    MbProgram& p = e->prog;
+    memset(&p, 0, sizeof(p));
+    p.n_steps = n_steps;
+    int formed = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        if (radius[s] < 1 || tap_off[s] < 0 || tap_off[s] + radius[s] + 1 > n_taps)
+            return fail(e, MB200_ERR_ARG, "step %d: radius/tap_off out of range", s);
+        p.st[s].radius = radius[s];
+        p.st[s].tap_off = tap_off[s];
+        p.st[s].flags = flags[s];
+        p.st[s].score_idx = -1;
+        if (s == 0 && !(flags[s] & MB200_STEP_RESTART)) return fail(e, MB200_ERR_ARG, "step 0 must carry MB200_STEP_RESTART");
+        formed = (flags[s] & MB200_STEP_RESTART) ? 0 : formed + 1;
+        if (flags[s] & MB200_STEP_SCORE) {
+            if (formed < 3) return fail(e, MB200_ERR_ARG, "step %d scores before three DoGs of its chain exist", s);
+            if (score_id[s] < 1 || score_id[s] > 254) return fail(e, MB200_ERR_ARG, "step %d: score id %d not in [1,254]", s, score_id[s]);
+            p.st[s].score_idx = p.n_scored;
+            p.score_id[p.n_scored] = score_id[s];
+            ++p.n_scored;
+        }
+        p.rmax = std::max(p.rmax, radius[s]);
+    }
+    if (p.n_scored > 254) return fail(e, MB200_ERR_ARG, "too many scored steps");
+    memcpy(p.taps, half_taps, (size_t)n_taps * sizeof(double));
+    e->have_prog = true;
+    e->configured = false;
+    return MB200_OK;
+}
+
+int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, double record_fraction) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->have_prog) return fail(e, MB200_ERR_ARG, "mb200_set_program has not been called");
+    if (n < 8 || dpx < 1 || nblocks < 1) return fail(e, MB200_ERR_ARG, "bad geometry n=%d dpx=%d nblocks=%d", n, dpx, nblocks);
+    if (!intra) return fail(e, MB200_ERR_ARG, "inter-chromosomal tiles are not supported (the reference path is broken, mustache.py:939-942)");
+    if (n <= 2 * e->prog.rmax + 1) return fail(e, MB200_ERR_ARG, "tile side %d too small for radius %d", n, e->prog.rmax);
+    int st = use_device(e);
+    if (st) return st;
+    e->n = n;
+    e->dpx = dpx;
+    e->intra = intra;
+    e->dhi = std::min(dpx + 1, n - 1);
+    if (e->dhi < 4) return fail(e, MB200_ERR_ARG, "no diagonal >= 4 in the tile");
+    e->wc = e->dhi - 3;
+    e->vlo = 2 - e->prog.rmax;
+    e->wv = e->dhi + 2 * e->prog.rmax + 1;
+    e->nblocks = nblocks;
+    const double frac = record_fraction > 0 ? record_fraction : 0.125;
+    e->rec_cap = std::max<long long>(4096, (long long)(frac * (double)n * e->wc));
+    dim3 gh = kh_grid(e, 1);
+    e->ncta_h = gh.x * gh.y;
+    if ((st = set_smem_limits(e))) return st;
+    const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
+    const size_t B = nblocks;
+    if ((st = ensure(e, e->raw, B * n * e->wc * sizeof(double)))) return st;
+    if ((st = ensure(e, e->part_min, B * ns * e->ncta_h * sizeof(double)))) return st;
+    if ((st = ensure(e, e->part_sum, B * ns * e->ncta_h * sizeof(double)))) return st;
+    if ((st = ensure(e, e->rec_count, B * sizeof(unsigned long long)))) return st;
+    if ((st = ensure(e, e->nz_count, B * sizeof(unsigned long long)))) return st;
+    if ((st = ensure(e, e->nonfinite, B * sizeof(int)))) return st;
+    if ((st = ensure(e, e->rec_row, B * e->rec_cap * sizeof(int)))) return st;
+    if ((st = ensure(e, e->rec_col, B * e->rec_cap * sizeof(int)))) return st;
+    if ((st = ensure(e, e->rec_sidx, B * e->rec_cap * sizeof(int)))) return st;
+    if ((st = ensure(e, e->rec_v, B * e->rec_cap * sizeof(double)))) return st;
+    if ((st = ensure(e, e->rec_p, B * e->rec_cap * sizeof(double)))) return st;
+    if ((st = ensure(e, e->fit_loc, B * ns * sizeof(double)))) return st;
+    if ((st = ensure(e, e->fit_scale, B * ns * sizeof(double)))) return st;
+    // axis-0 scratch: as many blocks per pass as fit in ~80 % of what is free now (plus what V already holds)
+    size_t free_b = 0, total_b = 0;
+    CU(e, cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_block = v_bytes_per_block(e);
+    const size_t budget = (size_t)(0.8 * (double)(free_b + e->V.cap));
+    long long fit = (long long)(budget / per_block);
+    if (fit < 1) return fail(e, MB200_ERR_NOMEM, "axis-0 scratch for one block needs %zu bytes, %zu available", per_block, budget);
+    e->pass_blocks = (int)std::min<long long>(fit, nblocks);
+    if ((st = ensure(e, e->V, (size_t)e->pass_blocks * per_block))) return st;
+    CU(e, cudaMemsetAsync(e->raw.p, 0, B * n * e->wc * sizeof(double), e->stream));
+    e->configured = true;
+    e->ran = false;
+    e->counts_valid = false;
+    return MB200_OK;
+}
+
+int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const int32_t* cols, const double* vals,
+                          int64_t nnz) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(e, MB200_ERR_ARG, "bad COO arguments");
+    if ((st = use_device(e))) return st;
+    if (nnz == 0) return MB200_OK;
+    if ((st = ensure(e, e->st_rows, nnz * sizeof(int)))) return st;
+    if ((st = ensure(e, e->st_cols, nnz * sizeof(int)))) return st;
+    if ((st = ensure(e, e->st_vals, nnz * sizeof(double)))) return st;
+    CU(e, cudaMemcpyAsync(e->st_rows.p, rows, nnz * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->st_cols.p, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->st_vals.p, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 8);
+    scatter_coo_kernel<<<grid, 256, 0, e->stream>>>((const int*)e->st_rows.p, (const int*)e->st_cols.p,
+                                                    (const double*)e->st_vals.p, nnz, rawb, e->n, e->wc, e->dhi);
+    CU(e, cudaGetLastError());
+    // the staging buffers are reused by the next upload: keep uploads ordered on the stream (they are) and make
+    // sure the host arrays may be released when this call returns
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->ran = false;
+    return MB200_OK;
+}
+
+int mb200_upload_band_host(mb200_engine* e, int block, const double* band, int64_t wsrc) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (!band || wsrc < 1) return fail(e, MB200_ERR_ARG, "bad band arguments");
+    if ((st = use_device(e))) return st;
+    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    const size_t w = (size_t)std::min<int64_t>(wsrc, e->wc);
+    CU(e, cudaMemcpy2DAsync(rawb, (size_t)e->wc * sizeof(double), band, (size_t)wsrc * sizeof(double), w * sizeof(double),
+                            e->n, cudaMemcpyHostToDevice, e->stream));
+    e->ran = false;
+    return MB200_OK;
+}
+
+int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int64_t ld) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (!tile || ld < e->n) return fail(e, MB200_ERR_ARG, "bad dense arguments");
+    if ((st = use_device(e))) return st;
+    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    // Row i of the band starts at tile[i*ld + i + 4]: a pitched copy with source pitch (ld+1) moves exactly the band.
+    // Rows whose band segment would run past the end of the host array are copied one by one, clipped.
+    const int64_t total = (int64_t)(e->n - 1) * ld + e->n;                 // elements addressable in the host tile
+    int64_t safe_rows = (total - 4 - e->wc) / (ld + 1) + 1;               // rows i with i*(ld+1) + 4 + wc <= total
+    safe_rows = std::max<int64_t>(0, std::min<int64_t>(safe_rows, e->n));
+    if (safe_rows > 0)
+        CU(e, cudaMemcpy2DAsync(rawb, (size_t)e->wc * sizeof(double), tile + 4, (size_t)(ld + 1) * sizeof(double),
+                                (size_t)e->wc * sizeof(double), (size_t)safe_rows, cudaMemcpyHostToDevice, e->stream));
+    for (int64_t i = safe_rows; i < e->n; ++i) {
+        const int64_t w = std::min<int64_t>(e->wc, e->n - i - 4);
+        if (w > 0)
+            CU(e, cudaMemcpyAsync(rawb + (size_t)i * e->wc, tile + i * ld + i + 4, (size_t)w * sizeof(double),
+                                  cudaMemcpyHostToDevice, e->stream));
+    }
+    e->ran = false;
+    return MB200_OK;
+}
+
+int mb200_upload_dense_dev(mb200_engine* e, int block, const double* tile_dev, int64_t ld) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (!tile_dev || ld < e->n) return fail(e, MB200_ERR_ARG, "bad dense arguments");
+    if ((st = use_device(e))) return st;
+    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    band_from_dense_kernel<<<148 * 8, 256, 0, e->stream>>>(tile_dev, ld, rawb, e->n, e->wc);
+    CU(e, cudaGetLastError());
+    e->ran = false;
+    return MB200_OK;
+}
+
+int mb200_run(mb200_engine* e) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured) return fail(e, MB200_ERR_ARG, "mb200_configure has not been called");
+    int st = use_device(e);
+    if (st) return st;
+    const int B = e->nblocks;
+    e->launches = 0;
+    e->counts_valid = false;
+    const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
+    while ((int)e->ev_pass.size() < 3 * npass) {
+        cudaEvent_t ev;
+        CU(e, cudaEventCreate(&ev));
+        e->ev_pass.push_back(ev);
+    }
+    CU(e, cudaEventRecord(e->ev_begin, e->stream));
+    CU(e, cudaMemsetAsync(e->rec_count.p, 0, B * sizeof(unsigned long long), e->stream));
+    CU(e, cudaMemsetAsync(e->nz_count.p, 0, B * sizeof(unsigned long long), e->stream));
+    CU(e, cudaMemsetAsync(e->nonfinite.p, 0, B * sizeof(int), e->stream));
+    count_mask_kernel<<<dim3(148 * 2, B), 256, 0, e->stream>>>((const double*)e->raw.p, e->n, e->wc,
+                                                                (unsigned long long*)e->nz_count.p, (int*)e->nonfinite.p);
+    CU(e, cudaGetLastError());
+    e->launches += 1;
+    CU(e, cudaEventRecord(e->ev_prep, e->stream));
+    for (int p = 0; p < npass; ++p) {
+        const int first = p * e->pass_blocks, nb = std::min(e->pass_blocks, B - first);
+        CU(e, cudaEventRecord(e->ev_pass[3 * p], e->stream));
+        if ((st = launch_pass(e, first, nb, nullptr, e->ev_pass[3 * p + 1]))) return st;
+        CU(e, cudaEventRecord(e->ev_pass[3 * p + 2], e->stream));
+    }
+    if (e->prog.n_scored > 0) {
+        reduce_stats_kernel<<<dim3(e->prog.n_scored, B), 256, 0, e->stream>>>(
+            (const double*)e->part_min.p, (const double*)e->part_sum.p, e->ncta_h, e->prog.n_scored,
+            (const unsigned long long*)e->nz_count.p, (double*)e->fit_loc.p, (double*)e->fit_scale.p);
+        CU(e, cudaGetLastError());
+        finalise_kernel<<<dim3(64, B), 256, 0, e->stream>>>((const unsigned long long*)e->rec_count.p, e->rec_cap,
+                                                           (const double*)e->rec_v.p, (const int*)e->rec_sidx.p,
+                                                           e->prog.n_scored, (const double*)e->fit_loc.p,
+                                                           (const double*)e->fit_scale.p, (double*)e->rec_p.p);
+        CU(e, cudaGetLastError());
+        e->launches += 2;
+    }
+    CU(e, cudaEventRecord(e->ev_end, e->stream));
+    e->ran = true;
+    return MB200_OK;
+}
+
+int mb200_sync(mb200_engine* e) {
+    if (!e) return MB200_ERR_ARG;
+    int st = use_device(e);
+    if (st) return st;
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, int64_t* n_found) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if ((st = use_device(e))) return st;
+    if ((st = refresh_counts(e))) return st;
+    if (nz_count) *nz_count = (int64_t)e->h_nz[block];
+    if (n_found) *n_found = (int64_t)e->h_rec[block];
+    if (e->h_nonfinite[block]) return fail(e, MB200_ERR_NONFINITE, "block %d holds non-finite values", block);
+    if ((long long)e->h_rec[block] > e->rec_cap)
+        return fail(e, MB200_ERR_CAPACITY, "block %d produced %llu records, capacity %lld", block, e->h_rec[block], e->rec_cap);
+    return MB200_OK;
+}
+
+int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* rows, int32_t* cols, double* v,
+                        int32_t* score_id, double* p, int64_t* n_out) {
+    int64_t nz = 0, nf = 0;
+    int st = mb200_block_counts(e, block, &nz, &nf);
+    if (n_out) *n_out = nf;
+    if (st) return st;
+    const int64_t m = std::min<int64_t>(nf, capacity);
+    if (m <= 0) return MB200_OK;
+    if (!rows || !cols || !v || !score_id || !p) return fail(e, MB200_ERR_ARG, "null output array");
+    const size_t o = (size_t)block * e->rec_cap;
+    CU(e, cudaMemcpyAsync(rows, (int*)e->rec_row.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(cols, (int*)e->rec_col.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(score_id, (int*)e->rec_sidx.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(v, (double*)e->rec_v.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(p, (double*)e->rec_p.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    for (int64_t r = 0; r < m; ++r) score_id[r] = e->prog.score_id[score_id[r]];   // scored index -> octave*12 + i
+    return MB200_OK;
+}
+
+int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (!e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
+    if (n_scored) *n_scored = e->prog.n_scored;
+    const int m = std::min(capacity, e->prog.n_scored);
+    if (m <= 0) return MB200_OK;
+    if ((st = use_device(e))) return st;
+    const size_t o = (size_t)block * e->prog.n_scored;
+    if (loc) CU(e, cudaMemcpyAsync(loc, (double*)e->fit_loc.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (scale) CU(e, cudaMemcpyAsync(scale, (double*)e->fit_scale.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (score_id)
+        for (int t = 0; t < m; ++t) score_id[t] = e->prog.score_id[t];
+    return MB200_OK;
+}
+
+int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* fin_ms, float* total_ms) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
+    int st = use_device(e);
+    if (st) return st;
+    CU(e, cudaEventSynchronize(e->ev_end));
+    const int npass = (e->nblocks + e->pass_blocks - 1) / e->pass_blocks;
+    float kv = 0, kh = 0, t = 0;
+    for (int p = 0; p < npass; ++p) {
+        CU(e, cudaEventElapsedTime(&t, e->ev_pass[3 * p], e->ev_pass[3 * p + 1]));
+        kv += t;
+        CU(e, cudaEventElapsedTime(&t, e->ev_pass[3 * p + 1], e->ev_pass[3 * p + 2]));
+        kh += t;
+    }
+    CU(e, cudaEventElapsedTime(&e->t_prep, e->ev_begin, e->ev_prep));
+    CU(e, cudaEventElapsedTime(&e->t_fin, e->ev_pass[3 * (npass - 1) + 2], e->ev_end));
+    CU(e, cudaEventElapsedTime(&e->t_total, e->ev_begin, e->ev_end));
+    e->t_kv = kv;
+    e->t_kh = kh;
+    if (prep_ms) *prep_ms = e->t_prep;
+    if (kv_ms) *kv_ms = kv;
+    if (kh_ms) *kh_ms = kh;
+    if (fin_ms) *fin_ms = e->t_fin;
+    if (total_ms) *total_ms = e->t_total;
+    return MB200_OK;
+}
+
+int mb200_last_launches(mb200_engine* e, int* launches) {
+    if (!e || !launches) return MB200_ERR_ARG;
+    *launches = e->launches;
+    return MB200_OK;
+}
+
+int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, double* dog_out) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (step < 0 || step >= e->prog.n_steps) return fail(e, MB200_ERR_ARG, "step %d out of range", step);
+    if ((st = use_device(e))) return st;
+    const size_t bytes = (size_t)e->n * e->n * sizeof(double);
+    if ((st = ensure(e, e->dbgG, bytes))) return st;
+    if ((st = ensure(e, e->dbgL, bytes))) return st;
+    CU(e, cudaMemsetAsync(e->dbgG.p, 0, bytes, e->stream));
+    CU(e, cudaMemsetAsync(e->dbgL.p, 0, bytes, e->stream));
+    MbGeom g = make_geom(e, block, 1);
+    g.dbg_step = step;
+    g.dbgG = (double*)e->dbgG.p;
+    g.dbgL = (double*)e->dbgL.p;
+    // scratch counters of this block are clobbered: the batch has to be re-run before fetching records again
+    CU(e, cudaMemsetAsync(g.rec_count, 0, sizeof(unsigned long long), e->stream));
+    if ((st = launch_pass(e, block, 1, &g, nullptr))) return st;
+    e->ran = false;
+    e->counts_valid = false;
+    if (gauss_out) CU(e, cudaMemcpyAsync(gauss_out, e->dbgG.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (dog_out) CU(e, cudaMemcpyAsync(dog_out, e->dbgL.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return MB200_ERR_ARG;
+    return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MB200_OK : MB200_ERR_NOMEM;
+}
+
+int mb200_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? MB200_OK : MB200_ERR_CUDA; }
+
+int mb200_scale_space_dense(mb200_engine* e, const double* tile, int n, int64_t ld, int dpx, int intra, int64_t capacity,
+                            int32_t* rows, int32_t* cols, double* v, int32_t* score_id, double* p, int64_t* nz_count,
+                            int64_t* n_found) {
+    int st = mb200_configure(e, n, dpx, intra, 1, -1.0);
+    if (st) return st;
+    if ((st = mb200_upload_dense_host(e, 0, tile, ld))) return st;
+    if ((st = mb200_run(e))) return st;
+    int64_t nz = 0, nf = 0;
+    st = mb200_block_counts(e, 0, &nz, &nf);
+    if (nz_count) *nz_count = nz;
+    if (n_found) *n_found = nf;
+    if (st) return st;
+    if (nf > capacity) return fail(e, MB200_ERR_CAPACITY, "%lld records, caller capacity %lld", (long long)nf, (long long)capacity);
+    return mb200_fetch_records(e, 0, capacity, rows, cols, v, score_id, p, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// Scale-space kernels for sm_100a (B200).  FP64 end to end, bit-exact against scipy.ndimage.gaussian_filter.
+//
+// Replaces the body of mustache() between mustache.py:699 and mustache.py:772 (reference: ay-lab/mustache v1.3.3):
+//   K_V  (kv_kernel)   axis-0 pass of every Gaussian of the chain            mustache.py:719,725,734,751 (first half of
+//                      scipy gaussian_filter: correlate1d along axis 0, mode='reflect')
+//   K_H  (kh_kernel)   axis-1 pass + DoG + zero-padded 3x3 maxima + 5-clause extremum test + per-level |L| min/sum
+//                      mustache.py:728,738,754 (DoG) :740-743,757 (maximum_filter) :760-768 (test + state update)
+//   reduce / finalise  expon.fit (loc = min, scale = mean - min) and 1 - expon.cdf for the winners only   mustache.py:755-756
+//
+// Data layout in HBM ("band layout"): a block is an N x N tile but only diagonals d = j - i in [4, dhi] can hold data
+// (reader keeps |j-i| <= dpx+1, mask needs j-i >= 4), so a tile is stored as raw[i][d-4], i in [0,N), wc = dhi-3 doubles per
+// row; (i, j) with j >= N is never read.  The 2-fills (mustache.py:703-706) are applied on the fly when a tile is staged
+// into shared memory.  Axis-0 results are stored as V[step][block][i][j-i-vlo] for diagonals [vlo, vlo+wv), vlo = 2-rmax.
+//
+// Arithmetic: scipy's NI_Correlate1D symmetric branch,  out = x[0]*w[0]; for j=-R..-1: out += (x[j]+x[-j])*w[j],
+// with separate multiply and add (__dmul_rn/__dadd_rn are never contracted into FMA).  Each thread produces K = 8
+// consecutive outputs along the filter axis and keeps the two K-wide input windows in registers, sliding them by one
+// element per tap, so a tap costs 2 shared-memory loads + 1 constant load for 24 FP64 instructions.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define MB_MAX_STEPS 64
+#define MB_MAX_TAPS 1536
+#define MB_FLAG_RESTART 1   // chain is cut before this Gaussian: no DoG is formed with the previous one
+#define MB_FLAG_SCORE 2     // after forming this step's DoG, score the DoG before it (ring centre)
+#define MB_FLAG_DIFFREF 4   // this step's DoG is L_2 of its octave (the only difference-stack DoG diff_mustache uses)
+
+struct MbStep {
+    int radius;
+    int tap_off;     // taps[tap_off + j], j = 0..radius, weight at distance j
+    int flags;
+    int score_idx;   // 0-based index among scored steps (valid when MB_FLAG_SCORE)
+};
+
+struct MbProgram {
+    int n_steps;
+    int n_scored;
+    int rmax;
+    int pad;
+    MbStep st[MB_MAX_STEPS];
+    int score_id[MB_MAX_STEPS];   // per scored index: octave*12 + i  (reference's scales[o][i])
+    double taps[MB_MAX_TAPS];
+};
+
+struct MbGeom {
+    int n;        // tile side
+    int dpx;      // distance_in_px
+    int intra;    // chromosome == chromosome2 (upper 2-fill applies)
+    int dhi;      // last stored diagonal
+    int wc;       // dhi - 3
+    int vlo;      // first diagonal of V storage (2 - rmax)
+    int wv;       // diagonals in V storage
+    int nblk;     // blocks in this pass
+    int ncta_h;   // CTAs per block in kh_kernel (for the partial-statistics layout)
+    int dbg_step; // -1 or the step whose Gaussian is dumped to dbgG
+    long long rec_cap;              // record capacity per block
+    const double* raw;              // [nblk][n][wc]
+    double* V;                      // [n_steps][nblk][n][wv]
+    double* part_min;               // [nblk][n_scored][ncta_h]
+    double* part_sum;               // [nblk][n_scored][ncta_h]
+    unsigned long long* rec_count;  // [nblk]
+    int* rec_row;                   // [nblk][rec_cap]
+    int* rec_col;
+    double* rec_v;
+    int* rec_sidx;
+    double* dbgG;                   // dense [n][n] (block 0 of the pass) or nullptr
+    double* dbgL;                   // dense [n][n]: DoG formed at dbg_step
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile shapes
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KV_TH = 64;      // rows per CTA (axis-0 pass)
+constexpr int KV_TW = 32;      // columns per CTA = lanes
+constexpr int KV_K = 8;        // outputs per thread along the filter axis
+constexpr int KV_THREADS = (KV_TH / KV_K) * 32;   // 256
+
+constexpr int KH_TR = 32;      // tile rows = lanes (30 scored + 2 halo)
+constexpr int KH_TC = 64;      // tile columns (62 scored + 2 halo)
+constexpr int KH_K = 8;
+constexpr int KH_THREADS = (KH_TC / KH_K) * 32;   // 256
+constexpr int KH_SR = KH_TR - 2;   // scored rows per CTA
+constexpr int KH_SC = KH_TC - 2;   // scored columns per CTA
+constexpr int KH_LP = KH_TC + 1;   // pitch of the DoG slots (odd: lanes index rows)
+
+__host__ __device__ inline int kh_vbuf_pitch(int rmax) { return (KH_TC + 2 * rmax) | 1; }
+__host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
+__host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
+    return ((size_t)KH_TR * kh_vbuf_pitch(rmax) + 2 * (size_t)KH_TR * KH_LP + 2 * (size_t)KH_K * KH_THREADS
+            + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KH_THREADS / 32)) * sizeof(double);
+}
+
+// scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -1 - i;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
+}
+
+// Tile value after the 2-fills (mustache.py:703-706); (i, j) must be inside the tile.
+__device__ __forceinline__ double filled_at(const MbGeom& g, const double* __restrict__ rawb, int i, int j) {
+    const int d = j - i;
+    if (d <= 4) return 2.0;
+    if (g.intra && d >= g.dpx + 1) return 2.0;
+    if (d > g.dhi) return 0.0;
+    return rawb[(size_t)i * g.wc + (d - 4)];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// folded symmetric correlation, K outputs per thread, register windows sliding one element per tap
+//   x[q] = ctr[q * stride];  out[k] = x[k]*w0 + sum_{j=R..1} (x[k-j] + x[k+j]) * w[j]   (that order, no FMA)
+// ---------------------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const int stride, const int R,
+                                           const double* __restrict__ tp, double (&acc)[K]) {
+    double pl[K], pr[K];
+    const double w0 = tp[0];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = __dmul_rn(ctr[k * stride], w0);
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        pl[p] = ctr[(p - R) * stride];
+        pr[p] = ctr[(p + R) * stride];
+    }
+    int j = R;
+    for (; j >= K; j -= K) {
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const double w = tp[j - u];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]), w));
+            pl[u % K] = ctr[(u + K - j) * stride];
+            pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < K - 1; ++u) {
+        if (u < j) {
+            const double w = tp[j - u];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]), w));
+            pl[u % K] = ctr[(u + K - j) * stride];
+            pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_V: axis-0 pass for every step of the chain.  grid = (column tiles, row tiles, blocks)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KV_THREADS, 2)
+kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
+    extern __shared__ double smem[];
+    double* cs = smem;                              // [(KV_TH + 2 rmax)][KV_TW]
+    const int rmax = prog.rmax;
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * KV_TH;
+    const int vhi = g.vlo + g.wv - 1;
+    int jbase = i0 + g.vlo;                         // first column any row of this row tile can need
+    if (jbase < 0) jbase = 0;
+    const int j0 = jbase + blockIdx.x * KV_TW;
+    const int ilast = min(i0 + KV_TH, g.n) - 1;
+    if (j0 >= g.n || j0 > ilast + vhi) return;
+
+    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+    const int rows = KV_TH + 2 * rmax;
+    for (int e = threadIdx.x; e < rows * KV_TW; e += KV_THREADS) {
+        const int r = e / KV_TW, c = e % KV_TW;
+        const int ii = reflect_idx(i0 - rmax + r, g.n);
+        const int jj = j0 + c;
+        cs[e] = (jj < g.n) ? filled_at(g, rawb, ii, jj) : 0.0;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int rb = (threadIdx.x >> 5) * KV_K;
+    const int j = j0 + lane;
+    if (i0 + rb >= g.n) return;
+    const double* ctr = cs + (size_t)(rb + rmax) * KV_TW + lane;
+    const int dmin = j0 - (i0 + rb + KV_K - 1);
+    const int dmax = j0 + KV_TW - 1 - (i0 + rb);
+
+    for (int s = 0; s < prog.n_steps; ++s) {
+        const int R = prog.st[s].radius;
+        const int lo = 2 - R, hi = g.dhi + 2 + R;       // diagonals the axis-1 pass of this step will read
+        if (dmax < lo || dmin > hi) continue;           // warp-uniform
+        double acc[KV_K];
+        conv_slide<KV_K>(ctr, KV_TW, R, prog.taps + prog.st[s].tap_off, acc);
+        double* vout = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
+#pragma unroll
+        for (int k = 0; k < KV_K; ++k) {
+            const int i = i0 + rb + k;
+            const int d = j - i;
+            if (i < g.n && j < g.n && d >= lo && d <= hi) vout[(size_t)i * g.wv + (d - g.vlo)] = acc[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_H: axis-1 pass, DoG chain, 3x3 maxima, extremum test, per-level statistics.  grid = (col tiles, row tiles, blocks)
+// Thread (lane = tile row, warp = group of 8 tile columns) owns 8 pixels for the whole chain.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(KH_THREADS, 2)
+kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
+    extern __shared__ double smem[];
+    const int rmax = prog.rmax;
+    const int pv = kh_vbuf_pitch(rmax);
+    double* vbuf = smem;                                        // [KH_TR][pv]
+    double* lbuf = vbuf + (size_t)KH_TR * pv;                   // [2][KH_TR][KH_LP]
+    double* mbuf = lbuf + 2 * (size_t)KH_TR * KH_LP;            // [2][KH_K][KH_THREADS]   thread-private
+    double* pmin = mbuf + 2 * (size_t)KH_K * KH_THREADS;        // [n_scored][warps]
+    double* psum = pmin + (size_t)max(prog.n_scored, 1) * (KH_THREADS / 32);
+
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int is0 = blockIdx.y * KH_SR;                 // first scored row
+    const int i0 = is0 - 1;                             // tile row 0 (halo)
+    const int js = is0 + 4 + blockIdx.x * KH_SC;        // first scored column of this CTA
+    const int ilast = min(is0 + KH_SR, g.n) - 1;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool active = (js < g.n) && (js <= ilast + g.dhi);
+    if (!active) {
+        for (int t = threadIdx.x; t < prog.n_scored; t += KH_THREADS) {
+            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+            g.part_min[o] = __longlong_as_double(0x7ff0000000000000LL);
+            g.part_sum[o] = 0.0;
+        }
+        return;
+    }
+    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+    const int i = i0 + lane;                            // this thread's image row
+    const int c0 = warp * KH_K;                         // first tile column of this thread
+    const int jc0 = js - 1 + c0;                        // image column of its first pixel
+    const bool row_in = (i >= 0) && (i < g.n);
+    const bool row_scored = (lane >= 1) && (lane <= KH_SR) && row_in;
+
+    // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
+    unsigned mask = 0;
+    if (row_scored) {
+#pragma unroll
+        for (int k = 0; k < KH_K; ++k) {
+            const int c = c0 + k, j = jc0 + k, d = j - i;
+            if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) {
+                if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
+            }
+        }
+    }
+    // relevance of this warp's 32 x 8 chunk: any pixel inside the tile on a diagonal the maxima can touch
+    const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n) && (jc0 + KH_K - 1 >= 0);
+
+    double vbest[KH_K], gprev[KH_K];
+    unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
+#pragma unroll
+    for (int k = 0; k < KH_K; ++k) { vbest[k] = 0.0; gprev[k] = 0.0; }
+    unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
+    int nl = 0;                                         // DoGs formed so far (slot parity)
+
+    for (int s = 0; s < prog.n_steps; ++s) {
+        const int R = prog.st[s].radius;
+        const int flags = prog.st[s].flags;
+        // ---- stage V_s rows of the tile (+/- R columns, reflected at the tile border) ----
+        {
+            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
+            const int wlen = KH_TC + 2 * R;
+            for (int e = threadIdx.x; e < KH_TR * wlen; e += KH_THREADS) {
+                const int r = e / wlen, t = e - r * wlen;
+                const int ii = i0 + r;
+                double val = 0.0;
+                if (ii >= 0 && ii < g.n) {
+                    const int jj = reflect_idx(js - 1 - R + t, g.n);
+                    const int dd = jj - ii - g.vlo;
+                    if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
+                }
+                vbuf[(size_t)r * pv + t] = val;
+            }
+        }
+        __syncthreads();
+        // ---- axis-1 pass for the 8 owned pixels, DoG into the ring ----
+        double gnew[KH_K];
+        if (chunk_live && row_in) {
+            conv_slide<KH_K>(vbuf + (size_t)lane * pv + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
+        }
+        if (g.dbgG != nullptr && s == g.dbg_step && b == 0 && row_in) {
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) {
+                const int j = jc0 + k;
+                if (j >= 0 && j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
+            }
+        }
+        const bool form = !(flags & MB_FLAG_RESTART);
+        double* lnew = lbuf + (size_t)(nl & 1) * KH_TR * KH_LP;
+        if (form) {
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) {
+                const int j = jc0 + k;
+                // outside the image the maximum filter sees cval = 0 (mode='constant', mustache.py:741)
+                const double l = (row_in && j >= 0 && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                lnew[(size_t)lane * KH_LP + c0 + k] = l;
+                if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && row_in && j >= 0 && j < g.n)
+                    g.dbgL[(size_t)i * g.n + j] = l;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KH_K; ++k) gprev[k] = gnew[k];
+        __syncthreads();
+        if (!form) continue;
+        // ---- 3x3 maxima of the new DoG for the owned pixels (separable: rows first, then columns) ----
+        double mnew[KH_K];
+        unsigned e_new = 0;
+        if (row_scored) {
+            double vm[KH_K + 2];
+#pragma unroll
+            for (int t = 0; t < KH_K + 2; ++t) {
+                int c = c0 - 1 + t;
+                c = c < 0 ? 0 : (c > KH_TC - 1 ? KH_TC - 1 : c);        // clamped columns only feed halo pixels
+                const double a0 = lnew[(size_t)(lane - 1) * KH_LP + c];
+                const double a1 = lnew[(size_t)lane * KH_LP + c];
+                const double a2 = lnew[(size_t)(lane + 1) * KH_LP + c];
+                vm[t] = fmax(fmax(a0, a1), a2);
+            }
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) {
+                mnew[k] = fmax(fmax(vm[k], vm[k + 1]), vm[k + 2]);
+                const double own = lnew[(size_t)lane * KH_LP + c0 + k];
+                if (own == mnew[k]) e_new |= 1u << k;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) mnew[k] = 0.0;
+        }
+        double* m_slot_new = mbuf + (size_t)(nl & 1) * KH_K * KH_THREADS;      // holds M of DoG nl-2 until overwritten
+        if (flags & MB_FLAG_SCORE) {
+            const int sidx = prog.st[s].score_idx;
+            const double* lcur = lbuf + (size_t)((nl - 1) & 1) * KH_TR * KH_LP;
+            double tmin = __longlong_as_double(0x7ff0000000000000LL), tsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) {
+                if (mask & (1u << k)) {
+                    const double lc = lcur[(size_t)lane * KH_LP + c0 + k];
+                    const double a = fabs(lc);
+                    tmin = fmin(tmin, a);
+                    tsum = __dadd_rn(tsum, a);
+                    if (lc > vbest[k] && (e_cur & (1u << k))) {
+                        const double mp = m_slot_new[(size_t)k * KH_THREADS + threadIdx.x];     // M of the DoG before
+                        if (((e_prev | e_new) & (1u << k)) && lc > mp && lc > mnew[k]) {
+                            vbest[k] = lc;
+                            lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
+                        }
+                    }
+                }
+            }
+            tmin = warp_min(tmin);
+            tsum = warp_sum(tsum);
+            if (lane == 0) {
+                pmin[sidx * (KH_THREADS / 32) + warp] = tmin;
+                psum[sidx * (KH_THREADS / 32) + warp] = tsum;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KH_K; ++k) m_slot_new[(size_t)k * KH_THREADS + threadIdx.x] = mnew[k];
+        e_prev = e_cur;
+        e_cur = e_new;
+        ++nl;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < prog.n_scored; t += KH_THREADS) {
+        double mn = pmin[t * (KH_THREADS / 32)], sm = psum[t * (KH_THREADS / 32)];
+        for (int w = 1; w < KH_THREADS / 32; ++w) {
+            mn = fmin(mn, pmin[t * (KH_THREADS / 32) + w]);
+            sm = __dadd_rn(sm, psum[t * (KH_THREADS / 32) + w]);
+        }
+        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+        g.part_min[o] = mn;
+        g.part_sum[o] = sm;
+    }
+    // ---- emit the pixels that were ever updated (pAll != 2, mustache.py:774) ----
+    if (lvl != 0) {
+#pragma unroll
+        for (int k = 0; k < KH_K; ++k) {
+            const int id = (int)((lvl >> (8 * k)) & 0xff);
+            if (id) {
+                const unsigned long long slot = atomicAdd(g.rec_count + b, 1ULL);
+                if (slot < (unsigned long long)g.rec_cap) {
+                    const size_t o = (size_t)b * g.rec_cap + slot;
+                    g.rec_row[o] = i;
+                    g.rec_col[o] = jc0 + k;
+                    g.rec_v[o] = vbest[k];
+                    g.rec_sidx[o] = id - 1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// statistics and p-values
+// ---------------------------------------------------------------------------------------------------------------
+// grid = (n_scored, nblk); fixed-order tree so the result is deterministic.
+__global__ void __launch_bounds__(256)
+reduce_stats_kernel(const double* __restrict__ part_min, const double* __restrict__ part_sum, int ncta, int n_scored,
+                    const unsigned long long* __restrict__ nz_count, double* __restrict__ fit_loc,
+                    double* __restrict__ fit_scale) {
+    __shared__ double smn[256], ssm[256];
+    const int t = blockIdx.x, b = blockIdx.y;
+    const double* pm = part_min + ((size_t)b * n_scored + t) * ncta;
+    const double* ps = part_sum + ((size_t)b * n_scored + t) * ncta;
+    double mn = __longlong_as_double(0x7ff0000000000000LL), sm = 0.0;
+    for (int c = threadIdx.x; c < ncta; c += 256) {
+        mn = fmin(mn, pm[c]);
+        sm = __dadd_rn(sm, ps[c]);
+    }
+    smn[threadIdx.x] = mn;
+    ssm[threadIdx.x] = sm;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + o]);
+            ssm[threadIdx.x] = __dadd_rn(ssm[threadIdx.x], ssm[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double loc = smn[0];
+        const double mean = ssm[0] / (double)nz_count[b];
+        fit_loc[(size_t)b * n_scored + t] = loc;             // expon.fit: loc = min
+        fit_scale[(size_t)b * n_scored + t] = mean - loc;    //            scale = mean - loc
+    }
+}
+
+// p = 1 - expon.cdf(|L|, loc, scale) = 1 - (-expm1(-(x - loc)/scale))   (mustache.py:756); winners have L > 0.
+__global__ void __launch_bounds__(256)
+finalise_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const double* __restrict__ rec_v,
+                const int* __restrict__ rec_sidx, int n_scored, const double* __restrict__ fit_loc,
+                const double* __restrict__ fit_scale, double* __restrict__ rec_p) {
+    const int b = blockIdx.y;
+    unsigned long long n = rec_count[b];
+    if (n > (unsigned long long)rec_cap) n = rec_cap;
+    for (unsigned long long r = blockIdx.x * 256ULL + threadIdx.x; r < n; r += (unsigned long long)gridDim.x * 256ULL) {
+        const size_t o = (size_t)b * rec_cap + r;
+        const int t = rec_sidx[o];
+        const double y = (fabs(rec_v[o]) - fit_loc[(size_t)b * n_scored + t]) / fit_scale[(size_t)b * n_scored + t];
+        rec_p[o] = 1.0 - (-expm1(-y));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile preparation
+// ---------------------------------------------------------------------------------------------------------------
+// COO (block-local, duplicates already resolved by the host: last write wins, mustache.py:924) -> band tile
+__global__ void __launch_bounds__(256)
+scatter_coo_kernel(const int* __restrict__ rows, const int* __restrict__ cols, const double* __restrict__ vals,
+                   long long nnz, double* __restrict__ rawb, int n, int wc, int dhi) {
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < nnz; e += (long long)gridDim.x * 256LL) {
+        const int r = rows[e], c = cols[e], d = c - r;
+        if (r >= 0 && r < n && c >= 0 && c < n && d >= 4 && d <= dhi) rawb[(size_t)r * wc + (d - 4)] = vals[e];
+    }
+}
+
+// dense row-major tile on the device -> band tile
+__global__ void __launch_bounds__(256)
+band_from_dense_kernel(const double* __restrict__ c, long long ld, double* __restrict__ rawb, int n, int wc) {
+    const long long total = (long long)n * wc;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256LL) {
+        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
+        const int j = i + 4 + k;
+        rawb[e] = (j < n) ? c[(long long)i * ld + j] : 0.0;
+    }
+}
+
+// mask size (mustache.py:699-701) and a finiteness check (scipy.stats.expon.fit raises on non-finite data)
+__global__ void __launch_bounds__(256)
+count_mask_kernel(const double* __restrict__ raw, int n, int wc, unsigned long long* __restrict__ nz_count,
+                  int* __restrict__ nonfinite) {
+    const int b = blockIdx.y;
+    const double* rawb = raw + (size_t)b * n * wc;
+    const long long total = (long long)n * wc;
+    unsigned long long cnt = 0;
+    int bad = 0;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256LL) {
+        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
+        if (i + 4 + k < n) {
+            const double v = rawb[e];
+            if (v != 0.0) ++cnt;
+            if (!isfinite(v)) bad = 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(nz_count + b, cnt);
+        if (bad) atomicOr(nonfinite + b, 1);
+    }
+}

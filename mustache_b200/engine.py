@@ -1,0 +1,258 @@
+"""ctypes binding of the C-ABI scale-space engine (include/mustache_b200.h) and a small Python wrapper.
+
+There is NO CPU fallback: if the CUDA library is missing or no device is visible, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ladder
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmustache_b200.so")
+
+ERR_NAMES = {-1: "MB200_ERR_CUDA", -2: "MB200_ERR_ARG", -3: "MB200_ERR_CAPACITY", -4: "MB200_ERR_NONFINITE",
+             -5: "MB200_ERR_NOMEM"}
+STEP_RESTART, STEP_SCORE, STEP_DIFFREF = 1, 2, 4
+
+# every symbol include/mustache_b200.h declares: name -> (restype, argtypes)
+_i32p, _f64p, _i64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+_f32p = C.POINTER(C.c_float)
+_H = C.c_void_p
+SIGNATURES = {
+    "mb200_abi_version": (C.c_int, []),
+    "mb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mb200_create": (C.c_int, [C.c_int, C.POINTER(_H)]),
+    "mb200_destroy": (None, [_H]),
+    "mb200_last_error": (C.c_char_p, [_H]),
+    "mb200_set_program": (C.c_int, [_H, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int]),
+    "mb200_configure": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mb200_upload_coo_host": (C.c_int, [_H, C.c_int, _i32p, _i32p, _f64p, C.c_int64]),
+    "mb200_upload_dense_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "mb200_upload_dense_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "mb200_upload_band_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "mb200_run": (C.c_int, [_H]),
+    "mb200_sync": (C.c_int, [_H]),
+    "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
+    "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
+    "mb200_fetch_fits": (C.c_int, [_H, C.c_int, _f64p, _f64p, _i32p, C.c_int, C.POINTER(C.c_int)]),
+    "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p]),
+    "mb200_last_launches": (C.c_int, [_H, C.POINTER(C.c_int)]),
+    "mb200_debug_level": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "mb200_host_free": (C.c_int, [C.c_void_p]),
+    "mb200_scale_space_dense": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _i32p, _i32p,
+                                          _f64p, _i32p, _f64p, _i64p, _i64p]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERR_NAMES.get(code, "MB200_ERR"), code, msg))
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and bind every declared symbol.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError("CUDA library %s not built (run `python -m mustache_b200.build`); there is no CPU fallback" % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def program_arrays(prog):
+    """ScaleProgram -> the flat arrays mb200_set_program takes."""
+    radius, flags, sid, off, taps = [], [], [], [], []
+    for st in prog.steps:
+        r = st.radius
+        half = np.ascontiguousarray(st.taps[r:])            # w[0..R], centre first (taps are exactly symmetric)
+        assert np.array_equal(half, st.taps[:r + 1][::-1])
+        off.append(len(taps))
+        taps.extend(half.tolist())
+        radius.append(r)
+        flags.append((STEP_RESTART if st.restart else 0) | (STEP_SCORE if st.score_id else 0)
+                     | (STEP_DIFFREF if st.diff_ref else 0))
+        sid.append(st.score_id)
+    return (np.array(radius, np.int32), np.array(flags, np.int32), np.array(sid, np.int32), np.array(off, np.int32),
+            np.array(taps, np.float64))
+
+
+class PinnedBuffer:
+    """Page-locked host array (mb200_host_alloc) for full-speed uploads."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.lib = load_library()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        st = self.lib.mb200_host_alloc(C.byref(self.ptr), nbytes)
+        if st:
+            raise EngineError(st, "pinned allocation of %d bytes failed" % nbytes)
+        buf = (C.c_char * nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.mb200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ScaleSpaceEngine:
+    """One engine per GPU.  Typical use:
+        eng = ScaleSpaceEngine(0); eng.set_octaves([1.6, 3.2]); eng.configure(n, dpx, nblocks)
+        eng.upload_coo(b, rows, cols, vals) ...; eng.run(); rec = eng.records(b)
+    """
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        cnt = C.c_int(0)
+        self.lib.mb200_device_count(C.byref(cnt))
+        if cnt.value < 1:
+            raise RuntimeError("no CUDA device visible: the scale-space engine has no CPU fallback")
+        self.h = _H()
+        st = self.lib.mb200_create(int(device), C.byref(self.h))
+        if st:
+            raise EngineError(st, "mb200_create(device=%d) failed" % device)
+        self.device = int(device)
+        self.program = None
+        self.n = self.dpx = self.nblocks = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st:
+            raise EngineError(st, self.lib.mb200_last_error(self.h).decode())
+
+    # ---- scale table ----
+    def set_program(self, prog):
+        radius, flags, sid, off, taps = program_arrays(prog)
+        self._chk(self.lib.mb200_set_program(self.h, len(radius), _ptr(radius, _i32p), _ptr(flags, _i32p), _ptr(sid, _i32p),
+                                             _ptr(off, _i32p), _ptr(taps, _f64p), len(taps)))
+        self.program = prog
+
+    def set_octaves(self, octave_values, dedupe=True):
+        self.set_program(ladder.build_program(list(octave_values), dedupe=dedupe))
+
+    # ---- batch ----
+    def configure(self, n, dpx, nblocks=1, intra=True, record_fraction=-1.0):
+        self._chk(self.lib.mb200_configure(self.h, int(n), int(dpx), 1 if intra else 0, int(nblocks), float(record_fraction)))
+        self.n, self.dpx, self.nblocks = int(n), int(dpx), int(nblocks)
+
+    def upload_coo(self, block, rows, cols, vals):
+        rows = np.ascontiguousarray(rows, np.int32)
+        cols = np.ascontiguousarray(cols, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        self._chk(self.lib.mb200_upload_coo_host(self.h, int(block), _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(vals, _f64p),
+                                                 len(vals)))
+
+    def upload_dense(self, block, tile):
+        """tile: C-contiguous float64 numpy array (n x n) or anything with .data_ptr() on the engine's device."""
+        if hasattr(tile, "data_ptr"):
+            assert tile.is_cuda and tile.dtype.is_floating_point and tile.element_size() == 8 and tile.stride(1) == 1
+            self._chk(self.lib.mb200_upload_dense_dev(self.h, int(block), C.c_void_p(tile.data_ptr()), int(tile.stride(0))))
+            return
+        assert tile.dtype == np.float64 and tile.ndim == 2 and tile.strides[1] == 8
+        self._chk(self.lib.mb200_upload_dense_host(self.h, int(block), C.c_void_p(tile.ctypes.data), tile.strides[0] // 8))
+
+    def upload_band(self, block, band):
+        assert band.dtype == np.float64 and band.ndim == 2 and band.strides[1] == 8 and band.shape[0] == self.n
+        self._chk(self.lib.mb200_upload_band_host(self.h, int(block), C.c_void_p(band.ctypes.data), band.strides[0] // 8))
+
+    def run(self, sync=False):
+        self._chk(self.lib.mb200_run(self.h))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._chk(self.lib.mb200_sync(self.h))
+
+    def counts(self, block):
+        nz, nf = C.c_int64(0), C.c_int64(0)
+        self._chk(self.lib.mb200_block_counts(self.h, int(block), C.byref(nz), C.byref(nf)))
+        return nz.value, nf.value
+
+    def records(self, block, sort=True):
+        """Records of every updated pixel, sorted row-major (the order of c[nz] in the reference)."""
+        nz, nf = self.counts(block)
+        rows, cols = np.empty(nf, np.int32), np.empty(nf, np.int32)
+        v, p, sid = np.empty(nf, np.float64), np.empty(nf, np.float64), np.empty(nf, np.int32)
+        n_out = C.c_int64(0)
+        self._chk(self.lib.mb200_fetch_records(self.h, int(block), nf, _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(v, _f64p),
+                                               _ptr(sid, _i32p), _ptr(p, _f64p), C.byref(n_out)))
+        if sort and nf:
+            order = np.lexsort((cols, rows))
+            rows, cols, v, p, sid = rows[order], cols[order], v[order], p[order], sid[order]
+        sig = np.array([self.program.sigma_of_id[int(s)] for s in sid], dtype=np.float64) if nf else np.zeros(0)
+        return dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
+
+    def fits(self, block):
+        ns = self.program.n_scored
+        loc, sc, sid = np.empty(ns), np.empty(ns), np.empty(ns, np.int32)
+        n = C.c_int(0)
+        self._chk(self.lib.mb200_fetch_fits(self.h, int(block), _ptr(loc, _f64p), _ptr(sc, _f64p), _ptr(sid, _i32p), ns, C.byref(n)))
+        return dict(loc=loc, scale=sc, score_id=sid)
+
+    def timing(self):
+        f = [C.c_float(0) for _ in range(5)]
+        self._chk(self.lib.mb200_last_timing(self.h, *[C.byref(x) for x in f]))
+        return dict(zip(("prep_ms", "kv_ms", "kh_ms", "fin_ms", "total_ms"), [x.value for x in f]))
+
+    def launches(self):
+        n = C.c_int(0)
+        self._chk(self.lib.mb200_last_launches(self.h, C.byref(n)))
+        return n.value
+
+    def debug_level(self, block, step):
+        g = np.zeros((self.n, self.n))
+        l = np.zeros((self.n, self.n))
+        self._chk(self.lib.mb200_debug_level(self.h, int(block), int(step), C.c_void_p(g.ctypes.data), C.c_void_p(l.ctypes.data)))
+        return g, l
+
+    def scale_space_dense(self, tile, dpx, intra=True):
+        """One-call drop-in for the scale-space half of mustache(c, ...) on a host tile."""
+        n = tile.shape[0]
+        cap = max(4096, n * (min(dpx + 1, n - 1) - 3) // 8)
+        rows, cols = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        v, p, sid = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
+        nz, nf = C.c_int64(0), C.c_int64(0)
+        self._chk(self.lib.mb200_scale_space_dense(self.h, C.c_void_p(tile.ctypes.data), n, tile.strides[0] // 8, int(dpx),
+                                                   1 if intra else 0, cap, _ptr(rows, _i32p), _ptr(cols, _i32p),
+                                                   _ptr(v, _f64p), _ptr(sid, _i32p), _ptr(p, _f64p), C.byref(nz), C.byref(nf)))
+        self.n, self.dpx, self.nblocks = n, int(dpx), 1
+        k = nf.value
+        order = np.lexsort((cols[:k], rows[:k]))
+        sig = np.array([self.program.sigma_of_id[int(s)] for s in sid[:k][order]], dtype=np.float64)
+        return dict(rows=rows[:k][order], cols=cols[:k][order], v=v[:k][order], p=p[:k][order], score_id=sid[:k][order],
+                    sigma=sig, nz_count=nz.value, n_found=k)

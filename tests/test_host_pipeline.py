@@ -1,0 +1,112 @@
+"""Host-side product logic (no GPU): reader + normaliser + tiler + sparse post-processing against reference dumps."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from mustache_b200 import fdr, ladder, normalize, postprocess, readers, tiler
+from oracle import postprocess as opost
+from oracle import scalespace as osc
+from tests import synth
+
+G = synth.GOLDEN
+
+
+@pytest.fixture(scope="module")
+def chr21(tmp_path_factory):
+    d = tmp_path_factory.mktemp("chr21")
+    raw, kr = synth.write_chr21_text(str(d))
+    x, y, v = readers.read_text(raw, 2000000, kr, "21", 5000)
+    dpx = tiler.distance_in_px(2000000, 5000)
+    normalize.normalize_sparse(x, y, v, 5000, dpx)
+    return x, y, v, dpx
+
+
+def test_reader_and_normaliser_bit_exact(chr21):
+    x, y, v, dpx = chr21
+    z = np.load(os.path.join(G, "chr21_blocks.npz"))
+    assert dpx == int(z["dpx"]) and len(v) == int(z["nnz"])
+    dig = hashlib.sha256(np.ascontiguousarray(x, np.int64).tobytes() + np.ascontiguousarray(y, np.int64).tobytes()
+                         + np.ascontiguousarray(v, np.float64).tobytes()).digest()
+    assert np.array_equal(np.frombuffer(dig, np.uint8), z["coo_digest"])
+
+
+def test_block_geometry(chr21):
+    x, y, v, dpx = chr21
+    z = np.load(os.path.join(G, "chr21_blocks.npz"))
+    n = int(max(x.max(), y.max()) + 1)
+    chunk, starts, ends = tiler.block_geometry(n, dpx)
+    assert chunk == 2000 and starts == list(z["start"]) and ends == list(z["end"])
+    assert tiler.block_geometry(1500, 400) == (2000, [0], [1500])
+    assert [tiler.block_mask_size(i, starts, ends, dpx) for i in range(len(starts))] == [-1, 400, 400, 400, 400, 779]
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4, 5])
+def test_sparse_postprocess_matches_reference_loops(chr21, b):
+    """Feed the reference's own (row, col, p_raw, scale) dump of each chr21 block to the product's sparse
+    post-processing; the loops must equal what mustache() returned for that block (coordinates, FDR, scale)."""
+    x, y, v, dpx = chr21
+    z = np.load(os.path.join(G, "chr21_blocks.npz"))
+    start, end = int(z["start"][b]), int(z["end"][b])
+    xc, yc, vc = tiler.block_coo(x, y, v, start, end)
+    mr, mc, mv = tiler.block_mask_pixels(xc, yc, vc, 2000)
+    assert len(mr) == int(z["b%d_nz_count" % b])
+    loops, _ = postprocess.call_loops(2000, dpx, start, mr, mc, mv, z["b%d_rows" % b], z["b%d_cols" % b],
+                                      z["b%d_p" % b], z["b%d_scale" % b], st=0.8, pt=0.1)
+    ref = z["b%d_loops" % b]
+    got = np.array(loops, float).reshape(-1, 4)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name", list(synth.SYNTH_TILES))
+def test_sparse_postprocess_synthetic(name):
+    spec = synth.SYNTH_TILES[name]
+    z = np.load(os.path.join(G, "synth_%s.npz" % name))
+    c = synth.make_tile(**spec["gen"])
+    n = c.shape[0]
+    r, cc = np.nonzero((c != 0) & (np.subtract.outer(np.arange(n), np.arange(n)) <= -4))
+    loops, _ = postprocess.call_loops(n, spec["dpx"], 0, r, cc, c[r, cc], z["rows"], z["cols"], z["p"], z["scale"],
+                                      st=spec["st"], pt=spec["pt"])
+    assert np.array_equal(np.array(loops, float).reshape(-1, 4), z["loops"])
+
+
+def test_small_mask_returns_nothing():
+    r = np.arange(100)
+    loops, _ = postprocess.call_loops(2000, 400, 0, r, r + 10, np.ones(100), r[:5], r[:5] + 10, np.full(5, 1e-9),
+                                      np.full(5, 2.1), st=0.0, pt=0.5)
+    assert loops == []
+
+
+def test_fdr_matches_statsmodels_form():
+    rng = np.random.default_rng(3)
+    p = rng.random(4000) ** 4
+    p[10:20] = p[10]
+    assert np.array_equal(fdr.fdr_bh(p), opost.bh_statsmodels_form(p))
+    assert fdr.fdr_bh(np.zeros(0)).size == 0
+
+
+def test_program_matches_oracle_ladder():
+    for octs in ([1.6, 3.2], [1.6, 3.2, 6.4, 12.8], [1.6], [2.0, 4.0, 8.0]):
+        lad = osc.sigma_ladder(octs)
+        prog = ladder.build_program(octs, dedupe=False)
+        assert len(prog.steps) == len(lad)
+        for st, lv in zip(prog.steps, lad):
+            assert st.sigma == lv["sigma"] and st.radius == lv["radius"] and np.array_equal(st.taps, lv["taps"])
+            assert st.restart == (lv["k"] == 1)
+            i = lv["k"] - 1
+            assert st.score_id == (lv["octave"] * 12 + i if 3 <= i <= 11 else 0)
+            if st.score_id:
+                assert st.score_sigma == osc.level_sigma(octs[lv["octave"]], i)
+        ded = ladder.build_program(octs, dedupe=True)
+        assert len(ded.steps) == len(lad) - 2 * (len(octs) - 1)        # default-style ladders share 2 levels/octave
+        assert [s.score_id for s in ded.steps if s.score_id] == [s.score_id for s in prog.steps if s.score_id]
+    odd = ladder.build_program([1.6, 3.0], dedupe=True)                 # not a factor of 2: nothing to share
+    assert len(odd.steps) == 24 and odd.steps[12].restart
+
+
+def test_mask_pixels_last_write_wins():
+    xc = np.array([3, 3, 5, 0]); yc = np.array([9, 9, 8, 2]); vc = np.array([1.0, 7.0, 2.0, 4.0])
+    r, c, v = tiler.block_mask_pixels(xc, yc, vc, 100)
+    assert list(r) == [3] and list(c) == [9] and list(v) == [7.0]       # (5,8): d=3 < 4; (0,2): d=2

@@ -98,6 +98,17 @@ MB200_API int mb200_last_launches(mb200_engine* e, int* launches);
  * arrays (valid on the diagonals 2..dhi+2 the detector reads; zero elsewhere).  Either pointer may be NULL. */
 MB200_API int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, double* dog_out);
 
+/* Differential mode (diff_mustache.py:260-425).  Blocks 2k and 2k+1 of the batch hold map 1 and map 2 of pair k.
+ * mb200_set_diff_program: the difference stack's chain -- per octave the Gaussians of levels 2 and 3, the second
+ * flagged MB200_STEP_DIFFREF (the reference only ever uses L_2 = G_2 - G_3 of c1 - c2, diff_mustache.py:336, 371-378;
+ * its `Lc` is never rotated, :413-425).  mb200_run_differential = mb200_run on both maps + the difference stack +
+ * norm.fit over the common mask + the two-sided normal p (pPair, :372-385, 412, 421) of every record.  Octave of a
+ * record = score_id / 12.  mb200_fetch_pair returns pPair in the same order as mb200_fetch_records. */
+MB200_API int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags,
+                                     const int32_t* tap_off, const double* half_taps, int n_taps);
+MB200_API int mb200_run_differential(mb200_engine* e);
+MB200_API int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair, int64_t* n_out);
+
 /* Pinned host memory for callers that want full-speed uploads. */
 MB200_API int mb200_host_alloc(void** ptr, int64_t bytes);
 MB200_API int mb200_host_free(void* ptr);

@@ -23,14 +23,17 @@ struct mb200_engine {
     cudaStream_t stream = nullptr;
     char err[512] = {0};
     MbProgram prog;
+    MbProgram dprog;                 // difference-stack chain (diff_mustache): G_2, G_3 of every octave
     bool have_prog = false;
+    bool have_dprog = false;
+    bool ran_diff = false;
     bool configured = false;
     bool ran = false;
     int n = 0, dpx = 0, intra = 1, dhi = 0, wc = 0, vlo = 0, wv = 0, nblocks = 0, pass_blocks = 0;
     long long rec_cap = 0;
     int ncta_h = 0;
     DevBuf raw, V, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
-        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL;
+        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
     bool counts_valid = false;
@@ -114,6 +117,8 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.rec_sidx = (int*)e->rec_sidx.p + (size_t)first_block * e->rec_cap;
     g.dbgG = nullptr;
     g.dbgL = nullptr;
+    g.fill = 2.0;                      // mustache.py:703-706
+    g.dout = nullptr;
     return g;
 }
 
@@ -142,13 +147,15 @@ int set_smem_limits(mb200_engine* e) {
     return MB200_OK;
 }
 
-int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cudaEvent_t after_kv) {
+int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cudaEvent_t after_kv,
+                const MbProgram* program = nullptr) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
-    const size_t kvb = kv_smem_bytes(e->prog.rmax), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
-    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(e->prog, g);
+    const MbProgram& pg = program ? *program : e->prog;
+    const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
+    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(pg, g);
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
-    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(e->prog, g);
+    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, g);
     CU(e, cudaGetLastError());
     e->launches += 2;
     return MB200_OK;
@@ -215,7 +222,8 @@ void mb200_destroy(mb200_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     DevBuf* all[] = {&e->raw, &e->V, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
-                     &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL};
+                     &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
+                     &e->d_score_id};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -227,12 +235,11 @@ void mb200_destroy(mb200_engine* e) {
 
 const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null engine"; }
 
-int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags, const int32_t* score_id,
-                      const int32_t* tap_off, const double* half_taps, int n_taps) {
+static int parse_program(mb200_engine* e, MbProgram& p, int n_steps, const int32_t* radius, const int32_t* flags,
+                         const int32_t* score_id, const int32_t* tap_off, const double* half_taps, int n_taps) {
     if (!e || !radius || !flags || !score_id || !tap_off || !half_taps) return fail(e, MB200_ERR_ARG, "null argument");
     if (n_steps < 1 || n_steps > MB_MAX_STEPS) return fail(e, MB200_ERR_ARG, "n_steps %d not in [1,%d]", n_steps, MB_MAX_STEPS);
     if (n_taps < 1 || n_taps > MB_MAX_TAPS) return fail(e, MB200_ERR_ARG, "n_taps %d not in [1,%d]", n_taps, MB_MAX_TAPS);
-    MbProgram& p = e->prog;
     memset(&p, 0, sizeof(p));
     p.n_steps = n_steps;
     int formed = 0;
@@ -256,8 +263,32 @@ int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const
     }
     if (p.n_scored > 254) return fail(e, MB200_ERR_ARG, "too many scored steps");
     memcpy(p.taps, half_taps, (size_t)n_taps * sizeof(double));
+    return MB200_OK;
+}
+
+int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags, const int32_t* score_id,
+                      const int32_t* tap_off, const double* half_taps, int n_taps) {
+    if (!e) return MB200_ERR_ARG;
+    int st = parse_program(e, e->prog, n_steps, radius, flags, score_id, tap_off, half_taps, n_taps);
+    if (st) return st;
     e->have_prog = true;
     e->configured = false;
+    return MB200_OK;
+}
+
+int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, const int32_t* flags, const int32_t* tap_off,
+                           const double* half_taps, int n_taps) {
+    if (!e) return MB200_ERR_ARG;
+    std::vector<int32_t> zero(n_steps > 0 ? n_steps : 1, 0);
+    int st = parse_program(e, e->dprog, n_steps, radius, flags, zero.data(), tap_off, half_taps, n_taps);
+    if (st) return st;
+    int nd = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        if (flags[s] & MB200_STEP_SCORE) return fail(e, MB200_ERR_ARG, "the difference chain never scores");
+        if (flags[s] & MB200_STEP_DIFFREF) ++nd;
+    }
+    if (nd < 1) return fail(e, MB200_ERR_ARG, "the difference chain needs at least one MB200_STEP_DIFFREF step");
+    e->have_dprog = true;
     return MB200_OK;
 }
 
@@ -396,6 +427,7 @@ int mb200_run(mb200_engine* e) {
     const int B = e->nblocks;
     e->launches = 0;
     e->counts_valid = false;
+    e->ran_diff = false;
     const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
     while ((int)e->ev_pass.size() < 3 * npass) {
         cudaEvent_t ev;
@@ -546,6 +578,69 @@ int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, d
     e->counts_valid = false;
     if (gauss_out) CU(e, cudaMemcpyAsync(gauss_out, e->dbgG.p, bytes, cudaMemcpyDeviceToHost, e->stream));
     if (dog_out) CU(e, cudaMemcpyAsync(dog_out, e->dbgL.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_run_differential(mb200_engine* e) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured) return fail(e, MB200_ERR_ARG, "mb200_configure has not been called");
+    if (!e->have_dprog) return fail(e, MB200_ERR_ARG, "mb200_set_diff_program has not been called");
+    if (e->nblocks % 2) return fail(e, MB200_ERR_ARG, "differential batches hold map 1 / map 2 tiles in blocks 2k / 2k+1");
+    if (e->dprog.rmax > e->prog.rmax) return fail(e, MB200_ERR_ARG, "difference chain radius exceeds the main chain's");
+    int st = mb200_run(e);                       // both maps, scored independently (diff_mustache.py:289-425)
+    if (st) return st;
+    const int npairs = e->nblocks / 2;
+    int ndiff = 0, oct_max = 0;
+    for (int s = 0; s < e->dprog.n_steps; ++s) ndiff += (e->dprog.st[s].flags & MB_FLAG_DIFFREF) ? 1 : 0;
+    for (int t = 0; t < e->prog.n_scored; ++t) oct_max = std::max(oct_max, e->prog.score_id[t] / 12);
+    if (oct_max >= ndiff) return fail(e, MB200_ERR_ARG, "difference chain has %d octaves, main chain scores octave %d", ndiff, oct_max);
+    const size_t tile = (size_t)e->n * e->wc;
+    if ((st = ensure(e, e->rawD, (size_t)npairs * tile * sizeof(double)))) return st;
+    if ((st = ensure(e, e->dout, (size_t)ndiff * npairs * tile * sizeof(double)))) return st;
+    if ((st = ensure(e, e->dmu, (size_t)ndiff * npairs * sizeof(double)))) return st;
+    if ((st = ensure(e, e->dsd, (size_t)ndiff * npairs * sizeof(double)))) return st;
+    if ((st = ensure(e, e->rec_pair, (size_t)e->nblocks * e->rec_cap * sizeof(double)))) return st;
+    if ((st = ensure(e, e->d_score_id, MB_MAX_STEPS * sizeof(int)))) return st;
+    CU(e, cudaMemcpyAsync(e->d_score_id.p, e->prog.score_id, MB_MAX_STEPS * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    diff_tile_kernel<<<dim3(148 * 2, npairs), 256, 0, e->stream>>>((const double*)e->raw.p, (double*)e->rawD.p, e->n, e->wc, e->dpx);
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemsetAsync(e->dout.p, 0, (size_t)ndiff * npairs * tile * sizeof(double), e->stream));
+    // difference stack: same kernels, constant regions are 0 (c = zeros; c[nz] = c1[nz] - c2[nz]), nothing is scored
+    for (int first = 0; first < npairs; first += e->pass_blocks) {
+        const int nb = std::min(e->pass_blocks, npairs - first);
+        MbGeom g = make_geom(e, 0, nb);
+        g.raw = (const double*)e->rawD.p + (size_t)first * tile;
+        g.fill = 0.0;
+        g.rec_cap = 0;
+        // dout is indexed [ndiff][nblk of the pass]; with several passes each pass writes its own slice per octave
+        if (npairs > e->pass_blocks) return fail(e, MB200_ERR_NOMEM, "differential batch does not fit one pass (%d pairs > %d)", npairs, e->pass_blocks);
+        g.dout = (double*)e->dout.p;
+        if ((st = launch_pass(e, 0, nb, &g, nullptr, &e->dprog))) return st;
+    }
+    diff_stats_kernel<<<dim3(ndiff, npairs), 1024, 0, e->stream>>>((const double*)e->raw.p, (const double*)e->dout.p, e->n, e->wc,
+                                                                  npairs, (double*)e->dmu.p, (double*)e->dsd.p);
+    CU(e, cudaGetLastError());
+    diff_pair_kernel<<<dim3(32, e->nblocks), 256, 0, e->stream>>>(
+        (const unsigned long long*)e->rec_count.p, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p,
+        (const int*)e->rec_sidx.p, (const int*)e->d_score_id.p, (const double*)e->dout.p, (const double*)e->dmu.p,
+        (const double*)e->dsd.p, e->n, e->wc, npairs, (double*)e->rec_pair.p);
+    CU(e, cudaGetLastError());
+    e->launches += 3;
+    e->ran_diff = true;
+    return MB200_OK;
+}
+
+int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair, int64_t* n_out) {
+    int64_t nz = 0, nf = 0;
+    int st = mb200_block_counts(e, block, &nz, &nf);
+    if (n_out) *n_out = nf;
+    if (st) return st;
+    if (!e->ran_diff) return fail(e, MB200_ERR_ARG, "mb200_run_differential has not been called for this batch");
+    const int64_t m = std::min<int64_t>(nf, capacity);
+    if (m <= 0) return MB200_OK;
+    if (!pair) return fail(e, MB200_ERR_ARG, "null output array");
+    CU(e, cudaMemcpyAsync(pair, (double*)e->rec_pair.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
     return MB200_OK;
 }

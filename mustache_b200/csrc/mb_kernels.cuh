@@ -66,6 +66,8 @@ struct MbGeom {
     int* rec_sidx;
     double* dbgG;                   // dense [n][n] (block 0 of the pass) or nullptr
     double* dbgL;                   // dense [n][n]: DoG formed at dbg_step
+    double fill;                    // value of the constant regions (2.0; 0.0 for the difference stack of diff_mustache)
+    double* dout;                   // [n_diffref][nblk][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -101,8 +103,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 // Tile value after the 2-fills (mustache.py:703-706); (i, j) must be inside the tile.
 __device__ __forceinline__ double filled_at(const MbGeom& g, const double* __restrict__ rawb, int i, int j) {
     const int d = j - i;
-    if (d <= 4) return 2.0;
-    if (g.intra && d >= g.dpx + 1) return 2.0;
+    if (d <= 4) return g.fill;
+    if (g.intra && d >= g.dpx + 1) return g.fill;
     if (d > g.dhi) return 0.0;
     return rawb[(size_t)i * g.wc + (d - 4)];
 }
@@ -268,6 +270,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     for (int k = 0; k < KH_K; ++k) { vbest[k] = 0.0; gprev[k] = 0.0; }
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
     int nl = 0;                                         // DoGs formed so far (slot parity)
+    int ndiff = 0;                                      // MB_FLAG_DIFFREF steps seen so far
+    const bool need_max = prog.n_scored > 0;
 
     for (int s = 0; s < prog.n_steps; ++s) {
         const int R = prog.st[s].radius;
@@ -317,10 +321,22 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
                     g.dbgL[(size_t)i * g.n + j] = l;
             }
         }
+        if (form && (flags & MB_FLAG_DIFFREF)) {
+            if (g.dout != nullptr && row_scored) {
+                double* dst = g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc;
+#pragma unroll
+                for (int k = 0; k < KH_K; ++k) {
+                    const int c = c0 + k, j = jc0 + k, d = j - i;
+                    if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = __dsub_rn(gprev[k], gnew[k]);
+                }
+            }
+            ++ndiff;
+        }
 #pragma unroll
         for (int k = 0; k < KH_K; ++k) gprev[k] = gnew[k];
         __syncthreads();
         if (!form) continue;
+        if (!need_max) { ++nl; continue; }
         // ---- 3x3 maxima of the new DoG for the owned pixels (separable: rows first, then columns) ----
         double mnew[KH_K];
         unsigned e_new = 0;
@@ -508,5 +524,91 @@ count_mask_kernel(const double* __restrict__ raw, int n, int wc, unsigned long l
     if ((threadIdx.x & 31) == 0) {
         if (cnt) atomicAdd(nz_count + b, cnt);
         if (bad) atomicOr(nonfinite + b, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// differential path (diff_mustache.py:262-425)
+// ---------------------------------------------------------------------------------------------------------------
+// c = c1 - c2 on the common mask, 0 elsewhere, taken AFTER the 2-fills (diff_mustache.py:268-276): diagonals 4 and
+// >= dpx+1 are 2 - 2 = 0.  raw1/raw2/rawd: [npairs][n][wc] with the two maps interleaved (block 2k, 2k+1).
+__global__ void __launch_bounds__(256)
+diff_tile_kernel(const double* __restrict__ raw, double* __restrict__ rawd, int n, int wc, int dpx) {
+    const int pr = blockIdx.y;
+    const double* r1 = raw + (size_t)(2 * pr) * n * wc;
+    const double* r2 = raw + (size_t)(2 * pr + 1) * n * wc;
+    double* out = rawd + (size_t)pr * n * wc;
+    const long long total = (long long)n * wc;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256LL) {
+        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
+        const int d = k + 4;
+        const double a = r1[e], b = r2[e];
+        out[e] = (i + d < n && d >= 5 && d <= dpx && a != 0.0 && b != 0.0) ? __dsub_rn(a, b) : 0.0;
+    }
+}
+
+__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = sh[threadIdx.x];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// norm.fit over the common mask (diff_mustache.py:371): mean and population std, two passes, one CTA per (octave, pair).
+__global__ void __launch_bounds__(1024)
+diff_stats_kernel(const double* __restrict__ raw, const double* __restrict__ dout, int n, int wc, int npairs,
+                  double* __restrict__ mu, double* __restrict__ sd) {
+    __shared__ double sh[33];
+    const int o = blockIdx.x, pr = blockIdx.y;
+    const double* r1 = raw + (size_t)(2 * pr) * n * wc;
+    const double* r2 = raw + (size_t)(2 * pr + 1) * n * wc;
+    const double* dd = dout + ((size_t)o * npairs + pr) * n * wc;
+    const long long total = (long long)n * wc;
+    double s = 0.0, cnt = 0.0;
+    for (long long e = threadIdx.x; e < total; e += 1024) {
+        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
+        if (i + 4 + k < n && r1[e] != 0.0 && r2[e] != 0.0) { s += dd[e]; cnt += 1.0; }
+    }
+    const double tot = block_sum_1024(s, sh);
+    const double num = block_sum_1024(cnt, sh);
+    const double mean = tot / num;
+    double q = 0.0;
+    for (long long e = threadIdx.x; e < total; e += 1024) {
+        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
+        if (i + 4 + k < n && r1[e] != 0.0 && r2[e] != 0.0) { const double t = dd[e] - mean; q += t * t; }
+    }
+    const double ss = block_sum_1024(q, sh);
+    if (threadIdx.x == 0) {
+        mu[(size_t)o * npairs + pr] = mean;
+        sd[(size_t)o * npairs + pr] = sqrt(ss / num);
+    }
+}
+
+// two-sided normal p of the difference DoG at each record's pixel (diff_mustache.py:372-385, 412, 421)
+__global__ void __launch_bounds__(256)
+diff_pair_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const int* __restrict__ rec_row,
+                 const int* __restrict__ rec_col, const int* __restrict__ rec_sidx,
+                 const int* __restrict__ score_id, const double* __restrict__ dout, const double* __restrict__ mu,
+                 const double* __restrict__ sd, int n, int wc, int npairs, double* __restrict__ rec_pair) {
+    const int b = blockIdx.y, pr = b >> 1;
+    unsigned long long m = rec_count[b];
+    if (m > (unsigned long long)rec_cap) m = rec_cap;
+    for (unsigned long long r = blockIdx.x * 256ULL + threadIdx.x; r < m; r += (unsigned long long)gridDim.x * 256ULL) {
+        const size_t o = (size_t)b * rec_cap + r;
+        const int oct = score_id[rec_sidx[o]] / 12;                 // score id = octave*12 + i
+        const int i = rec_row[o], j = rec_col[o];
+        const double x = dout[((size_t)oct * npairs + pr) * n * wc + (size_t)i * wc + (j - i - 4)];
+        double p = normcdf((x - mu[(size_t)oct * npairs + pr]) / sd[(size_t)oct * npairs + pr]);
+        if (!isfinite(p)) p = 1.0;                                  // np.nan_to_num(..., nan=1, posinf=1, neginf=1)
+        if (p > 0.5) p = 1.0 - p;
+        rec_pair[o] = 2.0 * p;
     }
 }

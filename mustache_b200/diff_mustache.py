@@ -1,0 +1,298 @@
+#!/usr/bin/env python3
+"""Drop-in mirror of the reference's mustache/diff_mustache.py interface (two-map differential loop calling) with the
+three scale-space stacks on the B200.
+
+  diff_mustache   diff_mustache.py:260-569   per block: both maps scored, difference stack, BH per map, filters,
+                                             clustering, differential selection (pair < pt2 and v_self > v_other)
+  regulator       diff_mustache.py:572-690   reads both maps, normalises each, tiles, batches block pairs on the GPU
+  main            diff_mustache.py:720-906   -f1 -f2 -b1 -b2 -pt -pt2 ...; writes .loop1 .loop2 .diffloop1 .diffloop2
+Reference quirks kept for parity: #13 `-b1` is never applied to map 1 for text input (the CLI
+reads `args.biasfile1` into `biasf` instead of `biasf1`), #15 pt2 thresholds the raw two-sided normal p, #16 explicit
+-d is capped at 2000*res.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import postprocess, readers, tiler
+from .mustache import HEADER, _dist_env, _set_octaves, format_row, get_engine, parseBP, resolve_distance
+from .normalize import normalize_sparse
+
+_DIFF_KEY = {}
+
+
+def _set_octaves_diff(eng, octave_values):
+    key = tuple(float(o) for o in octave_values)
+    if _DIFF_KEY.get(id(eng)) != key:
+        eng.set_octaves(key, differential=True)
+        _DIFF_KEY[id(eng)] = key
+        from . import mustache as _m
+        _m._PROGRAM_KEY[id(eng)] = key
+
+
+def _dense_lookup(index, values, rows, cols, on_mask_default, off_mask):
+    pos = index.lookup(rows, cols)
+    return np.where(pos >= 0, values[np.maximum(pos, 0)], off_mask)
+
+
+def select_differential(n, dpx, start, masks, recs, st, pt, pt2):
+    """diff_mustache.py:428-569 for one block pair.  masks/recs: [(rows, cols, vals)] and engine records per map."""
+    if any(len(m[0]) < 50 for m in masks):                              # diff_mustache.py:266-267
+        return [], [], [], []
+    if any(len(m[0]) < postprocess.MIN_MASK_FOR_BH for m in masks):      # diff_mustache.py:430-431
+        return [], [], [], []
+    outs, auxs = [], []
+    for m, r in zip(masks, recs):
+        loops, aux = postprocess.call_loops(n, dpx, start, m[0], m[1], m[2], r["rows"], r["cols"], r["p"], r["sigma"],
+                                            st, pt, candidate_order="rowmajor", partial=True)
+        outs.append(loops)
+        auxs.append(aux)
+    # the reference bails out of the whole block when either map has no candidate left after the filters
+    if any(a.get("empty_after_filters") for a in auxs):                  # diff_mustache.py:507-508, 519-520, 526-527
+        return [], [], [], []
+    dense = []
+    for m, r, a in zip(masks, recs, auxs):
+        idx = a["index"]
+        pos = idx.lookup(r["rows"], r["cols"])
+        pair = np.full(idx.keys.size, 2.0)                               # pPair initialised to 2 (diff_mustache.py:290)
+        vall = np.zeros(idx.keys.size)                                   # vAll initialised to 0 (diff_mustache.py:292)
+        pair[pos] = r["pair"]
+        vall[pos] = r["v"]
+        dense.append((idx, pair, vall))
+
+    def lookup(which, vals, rows, cols):
+        idx = dense[which][0]
+        pos = idx.lookup(rows, cols)
+        return np.where(pos >= 0, vals[np.maximum(pos, 0)], 1.0)        # np.ones_like off the mask (:447-453)
+
+    diffs = []
+    for me, other in ((0, 1), (1, 0)):
+        keep = []
+        for loop in outs[me]:
+            rr, cc = [loop[0] - start], [loop[1] - start]
+            pr = lookup(me, dense[me][1], rr, cc)[0]
+            v_self = lookup(me, dense[me][2], rr, cc)[0]
+            v_other = lookup(other, dense[other][2], rr, cc)[0]
+            if pr < pt2 and v_self > v_other:                            # diff_mustache.py:567-568
+                keep.append(loop)
+        diffs.append(keep)
+    return outs[0], diffs[0], outs[1], diffs[1]
+
+
+def diff_mustache(c1, c2, chromosome, chromosome2, res, start, end, mask_size, distance_in_px, octave_values, st, pt, pt2):
+    """Same contract as the reference's diff_mustache() (diff_mustache.py:260-569) for one pair of dense tiles."""
+    if chromosome != chromosome2:
+        raise NotImplementedError("inter-chromosomal tiles are not supported (broken in the reference)")
+    n = c1.shape[0]
+    d = np.subtract.outer(np.arange(n), np.arange(n)) * -1
+    masks = []
+    for c in (c1, c2):
+        r, cc = np.nonzero((c != 0) & (d >= 4))
+        masks.append((r, cc, c[r, cc]))
+    if any(len(m[0]) < 50 for m in masks):
+        return [], [], [], []
+    eng = get_engine()
+    _set_octaves_diff(eng, octave_values)
+    eng.configure(n, distance_in_px, 2)
+    eng.upload_dense(0, np.ascontiguousarray(c1, dtype=np.float64))
+    eng.upload_dense(1, np.ascontiguousarray(c2, dtype=np.float64))
+    eng.run_differential()
+    recs = [eng.records(0, pair=True), eng.records(1, pair=True)]
+    for c in (c1, c2):
+        c[d <= 4] = 2
+        c[d >= distance_in_px + 1] = 2
+    return select_differential(n, distance_in_px, start, masks, recs, st, pt, pt2)
+
+
+def call_block_pairs(xyv1, xyv2, n, dpx, octave_values, st, pt, pt2, verbose=True, rank=0, world=1):
+    """Tile both normalised maps, run this rank's block pairs in one batch, gather, select.  Returns tagged loops
+    [[x, y, fdr, scale, tag]], tag 1/2/3/4 = loops1 / diffloops1 / loops2 / diffloops2 (diff_mustache.py:704-715)."""
+    from . import gather
+    chunk, start, end = tiler.block_geometry(n, dpx)
+    nb = len(start)
+    mine = [b for b in range(nb) if b % world == rank]
+    eng = get_engine()
+    _set_octaves_diff(eng, octave_values)
+    masks = {}
+
+    def block_masks(b):
+        out = []
+        for (x, y, v) in (xyv1, xyv2):
+            xc, yc, vc = tiler.block_coo(x, y, v, start[b], end[b])
+            out.append(tiler.block_mask_pixels(xc, yc, vc, chunk))
+        return out
+
+    recs = {}
+    if mine:
+        eng.configure(chunk, dpx, 2 * len(mine))
+        for k, b in enumerate(mine):
+            if verbose:
+                print("Starting block ", b + 1, "/", nb, "...", sep="")
+            masks[b] = block_masks(b)
+            eng.upload_coo(2 * k, *masks[b][0])
+            eng.upload_coo(2 * k + 1, *masks[b][1])
+        eng.run_differential()
+        for k, b in enumerate(mine):
+            recs[b] = [eng.records(2 * k, pair=True), eng.records(2 * k + 1, pair=True)]
+    if world > 1:
+        import torch
+        dev = torch.device("cuda", eng.device) if torch.cuda.is_available() else torch.device("cpu")
+        flat = [recs[b][w] for b in mine for w in (0, 1)]
+        ids = [2 * b + w for b in mine for w in (0, 1)]
+        by = gather.split_by_block(gather.all_gather_records(flat, rank, world, dev, block_ids=ids, with_pair=True))
+        if rank != 0:
+            return []
+        lut = eng._sigma_lut()
+        recs = {}
+        for b in range(nb):
+            masks.setdefault(b, block_masks(b))
+            pair_recs = []
+            for w in (0, 1):
+                r = by.get((0, 2 * b + w))
+                if r is None:
+                    r = dict(rows=np.zeros(0, np.int32), cols=np.zeros(0, np.int32), v=np.zeros(0), p=np.zeros(0),
+                             score_id=np.zeros(0, np.int32), pair=np.zeros(0), nz_count=len(masks[b][w][0]))
+                r["sigma"] = lut[r["score_id"]]
+                pair_recs.append(r)
+            recs[b] = pair_recs
+    out = []
+    for b in range(nb):
+        ms = tiler.block_mask_size(b, start, end, dpx)
+        res4 = select_differential(chunk, dpx, start[b], masks[b], recs[b], st, pt, pt2)
+        for tag, loops in zip((1, 2, 3, 4), res4):
+            for loop in loops:
+                if tiler.keep_after_overlap(loop, start[b], ms):
+                    out.append([loop[0], loop[1], loop[2], loop[3], tag])
+        if verbose:
+            print("Block", b + 1, "done.")
+    return out
+
+
+def regulator(f1, f2, norm_method, CHRM_SIZE, outdir, bed1="", bed2="", res=5000, sigma0=1.6, s=10, pt=0.1, pt2=0.1,
+              st=0.88, octaves=2, verbose=True, nprocesses=4, distance_filter=2000000, bias1=False, bias2=False,
+              chromosome="n", chromosome2=None):
+    if not chromosome2 or chromosome2 == "n":
+        chromosome2 = chromosome
+    if chromosome != chromosome2:
+        print("Interchromosomal analysis is only supported for .hic and .cool input formats.")
+        raise FileNotFoundError
+    octave_values = [sigma0 * (2 ** i) for i in range(octaves)]
+    rank, world = _dist_env()
+    if verbose:
+        print("Reading contact map...")
+    maps = []
+    for f, b in ((f1, bias1), (f2, bias2)):
+        if f.endswith(".hic"):
+            got = readers.read_hic(f, norm_method, CHRM_SIZE, distance_filter, chromosome, chromosome2, res)
+        elif f.endswith(".cool") or f.endswith(".mcool"):
+            got = readers.read_cool(f, distance_filter, chromosome, chromosome2, norm_method, res)
+        else:
+            got = readers.read_text(f, distance_filter, b, chromosome, res)
+        if got is None or len(got[2]) == 0:
+            return []
+        maps.append([np.asarray(a) for a in got])
+    if verbose:
+        print("Normalizing contact map...")
+    dpx = tiler.distance_in_px(distance_filter, res)
+    n = int(max(max(m[0].max(), m[1].max()) + 1 for m in maps))
+    for m in maps:
+        normalize_sparse(m[0], m[1], m[2], res, dpx)
+    if verbose:
+        print("Loop calling...")
+    return call_block_pairs(maps[0], maps[1], n, dpx, octave_values, st, pt, pt2, verbose=verbose, rank=rank, world=world)
+
+
+def parse_args(args):
+    """diff_mustache.py:29-180."""
+    p = argparse.ArgumentParser(description="Check the help flag")
+    p.add_argument("-f1", "--file1", dest="f_path1", required=False)
+    p.add_argument("-f2", "--file2", dest="f_path2", required=False)
+    p.add_argument("-d", "--distance", dest="distFilter", required=False)
+    p.add_argument("-o", "--outfile", dest="outdir", required=True)
+    p.add_argument("-r", "--resolution", dest="resolution", required=True)
+    p.add_argument("-bed1", "--bed1", dest="bed1", default="", required=False)
+    p.add_argument("-bed2", "--bed2", dest="bed2", default="", required=False)
+    p.add_argument("-m1", "--matrix1", dest="mat1", default="", required=False)
+    p.add_argument("-m2", "--matrix2", dest="mat2", default="", required=False)
+    p.add_argument("-b1", "--biases1", dest="biasfile1", required=False)
+    p.add_argument("-b2", "--biases2", dest="biasfile2", required=False)
+    p.add_argument("-cz", "--chromosomeSize", default="", dest="chrSize_file", required=False)
+    p.add_argument("-norm", "--normalization", default=False, dest="norm_method", required=False)
+    p.add_argument("-st", "--sparsityThreshold", dest="st", type=float, default=0.88, required=False)
+    p.add_argument("-pt", "--pThreshold", dest="pt", type=float, default=0.2, required=False)
+    p.add_argument("-pt2", "--pThreshold2", dest="pt2", type=float, default=0.1, required=False)
+    p.add_argument("-sz", "--sigmaZero", dest="s_z", type=float, default=1.6, required=False)
+    p.add_argument("-oc", "--octaves", dest="octaves", default=2, type=int, required=False)
+    p.add_argument("-i", "--iterations", dest="s", default=10, type=int, required=False)
+    p.add_argument("-p", "--processes", dest="nprocesses", default=4, type=int, required=False)
+    p.add_argument("-ch", "--chromosome", dest="chromosome", nargs="+", default="n", required=False)
+    p.add_argument("-ch2", "--chromosome2", dest="chromosome2", nargs="+", default="n", required=False)
+    p.add_argument("-v", "--verbose", dest="verbose", type=bool, default=True, required=False)
+    return p.parse_args(args)
+
+
+def main(argv=None):
+    start_time = time.time()
+    args = parse_args(sys.argv[1:] if argv is None else argv)
+    rank, world = _dist_env()
+    quiet = rank != 0
+    f1, f2 = args.f_path1, args.f_path2
+    if args.bed1 and args.mat1:
+        f1 = args.mat1
+    if args.bed2 and args.mat2:
+        f2 = args.mat2
+    if not f1 or not f2 or not os.path.exists(f1) or not os.path.exists(f2):
+        print("Error: Couldn't find the specified contact files")
+        return
+    res = parseBP(args.resolution)
+    if not res:
+        print("Error: Invalid resolution")
+        return
+    if not args.chromosome or args.chromosome == "n":
+        print("Error: Please enter the chromosome name.")
+        return
+    distFilter = resolve_distance(args.distFilter, res, cap=2000)       # diff_mustache.py:770-778 (quirk #16)
+    chr_list = list(args.chromosome)
+    chr_list2 = list(args.chromosome2) if isinstance(args.chromosome2, list) else list(chr_list)
+    first = True
+    for chromosome, chromosome2 in zip(chr_list, chr_list2):
+        # quirk #13 (diff_mustache.py:824-827, 850): `biasf = args.biasfile1` -- biasf1 stays False, so map 1 is never
+        # bias-corrected for text input; only -b2 takes effect.
+        biasf1, biasf2 = False, False
+        if args.biasfile1 and not os.path.exists(args.biasfile1):
+            print("Error: Couldn't find specified bias file1")
+            return
+        if args.biasfile2:
+            if os.path.exists(args.biasfile2):
+                biasf2 = args.biasfile2
+            else:
+                print("Error: Couldn't find specified bias file2")
+                return
+        o = regulator(f1, f2, args.norm_method, False, args.outdir, bed1=args.bed1, bed2=args.bed2, res=res, sigma0=args.s_z,
+                      s=args.s, verbose=args.verbose and not quiet, pt=args.pt, pt2=args.pt2, st=args.st,
+                      distance_filter=distFilter, nprocesses=args.nprocesses, bias1=biasf1, bias2=biasf2,
+                      chromosome=chromosome, chromosome2=chromosome2, octaves=args.octaves)
+        if quiet:
+            continue
+        names = {1: ".loop1", 2: ".diffloop1", 3: ".loop2", 4: ".diffloop2"}
+        if first:
+            for suf in names.values():
+                with open(args.outdir + suf, "w") as fh:
+                    fh.write(HEADER)
+            first = False
+        counts = {t: 0 for t in names}
+        for loop in o:
+            counts[loop[4]] += 1
+            with open(args.outdir + names[loop[4]], "a") as fh:
+                fh.write(format_row(chromosome, chromosome2, loop, res))
+        print(f"({counts[1]},{counts[3]}) loops and ({counts[2]},{counts[4]}) differential-loops found in "
+              f"chrmosome={chromosome} for detection-fdr<{args.pt} and difference-fdr<{args.pt2} in "
+              f"{time.time() - start_time:.2f}sec")
+        start_time = time.time()
+
+
+if __name__ == "__main__":
+    main()

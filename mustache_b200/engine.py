@@ -40,6 +40,9 @@ SIGNATURES = {
     "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p]),
     "mb200_last_launches": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "mb200_debug_level": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "mb200_set_diff_program": (C.c_int, [_H, C.c_int, _i32p, _i32p, _i32p, _f64p, C.c_int]),
+    "mb200_run_differential": (C.c_int, [_H]),
+    "mb200_fetch_pair": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "mb200_host_free": (C.c_int, [C.c_void_p]),
     "mb200_scale_space_dense": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _i32p, _i32p,
@@ -162,8 +165,18 @@ class ScaleSpaceEngine:
                                              _ptr(off, _i32p), _ptr(taps, _f64p), len(taps)))
         self.program = prog
 
-    def set_octaves(self, octave_values, dedupe=True):
+    def _sigma_lut(self):
+        lut = np.zeros(256)
+        for k, sg in self.program.sigma_of_id.items():
+            lut[k] = sg
+        return lut
+
+    def set_octaves(self, octave_values, dedupe=True, differential=False):
         self.set_program(ladder.build_program(list(octave_values), dedupe=dedupe))
+        if differential:
+            radius, flags, sid, off, taps = program_arrays(ladder.build_diff_program(list(octave_values)))
+            self._chk(self.lib.mb200_set_diff_program(self.h, len(radius), _ptr(radius, _i32p), _ptr(flags, _i32p),
+                                                      _ptr(off, _i32p), _ptr(taps, _f64p), len(taps)))
 
     # ---- batch ----
     def configure(self, n, dpx, nblocks=1, intra=True, record_fraction=-1.0):
@@ -195,6 +208,10 @@ class ScaleSpaceEngine:
         if sync:
             self.sync()
 
+    def run_differential(self):
+        """Blocks 2k / 2k+1 = map 1 / map 2 of pair k: both maps scored + pPair of every record."""
+        self._chk(self.lib.mb200_run_differential(self.h))
+
     def sync(self):
         self._chk(self.lib.mb200_sync(self.h))
 
@@ -203,9 +220,14 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_block_counts(self.h, int(block), C.byref(nz), C.byref(nf)))
         return nz.value, nf.value
 
-    def records(self, block, sort=True):
+    def records(self, block, sort=True, pair=False):
         """Records of every updated pixel, sorted row-major (the order of c[nz] in the reference)."""
         nz, nf = self.counts(block)
+        pp = None
+        if pair:
+            pp = np.empty(nf, np.float64)
+            n2 = C.c_int64(0)
+            self._chk(self.lib.mb200_fetch_pair(self.h, int(block), nf, _ptr(pp, _f64p), C.byref(n2)))
         rows, cols = np.empty(nf, np.int32), np.empty(nf, np.int32)
         v, p, sid = np.empty(nf, np.float64), np.empty(nf, np.float64), np.empty(nf, np.int32)
         n_out = C.c_int64(0)
@@ -214,8 +236,13 @@ class ScaleSpaceEngine:
         if sort and nf:
             order = np.lexsort((cols, rows))
             rows, cols, v, p, sid = rows[order], cols[order], v[order], p[order], sid[order]
-        sig = np.array([self.program.sigma_of_id[int(s)] for s in sid], dtype=np.float64) if nf else np.zeros(0)
-        return dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
+            if pp is not None:
+                pp = pp[order]
+        sig = self._sigma_lut()[sid] if nf else np.zeros(0)
+        out = dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
+        if pp is not None:
+            out["pair"] = pp
+        return out
 
     def fits(self, block):
         ns = self.program.n_scored
@@ -253,6 +280,6 @@ class ScaleSpaceEngine:
         self.n, self.dpx, self.nblocks = n, int(dpx), 1
         k = nf.value
         order = np.lexsort((cols[:k], rows[:k]))
-        sig = np.array([self.program.sigma_of_id[int(s)] for s in sid[:k][order]], dtype=np.float64)
+        sig = self._sigma_lut()[sid[:k][order]]
         return dict(rows=rows[:k][order], cols=cols[:k][order], v=v[:k][order], p=p[:k][order], score_id=sid[:k][order],
                     sigma=sig, nz_count=nz.value, n_found=k)

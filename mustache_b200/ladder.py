@@ -95,3 +95,16 @@ def build_program(octave_values, dedupe=True):
                 prog.octave_of_id[sid] = oi
         prev_tail = (taps[11], taps[12])
     return prog
+
+
+def build_diff_program(octave_values):
+    """Chain for the difference stack of diff_mustache: per octave only G_2 and G_3 are ever used, because the
+    reference computes `Lc = Gc - Gn` once before the level loop (diff_mustache.py:336) and never rotates it
+    (diff_mustache.py:413-425), so norm.fit / norm.cdf (:371-378) always see that octave's L_2."""
+    prog = ScaleProgram()
+    for oi, o in enumerate(octave_values):
+        for k in (2, 3):
+            sg = level_sigma(o, k)
+            r, taps = scipy_taps(sg)
+            prog.steps.append(Step(sigma=sg, radius=r, taps=taps, restart=(k == 2), score_id=0, diff_ref=(k == 3), octave=oi))
+    return prog

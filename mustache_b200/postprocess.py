@@ -138,11 +138,14 @@ def cluster_representatives(x, y, o_of):
 
 
 def call_loops(n, dpx, start, mask_rows, mask_cols, mask_vals, rec_rows, rec_cols, rec_p, rec_sigma, st, pt,
-               intra=True, candidate_order="sorted"):
+               intra=True, candidate_order="sorted", partial=False):
     """Everything after the scale-space loop for one block (mustache.py:774-850).
 
     Returns (loops, aux): loops = [[x+start, y+start, fdr, sigma], ...]; aux carries q (per record) and the
-    lookup helpers the differential selection needs.
+    lookup helpers the differential selection needs; aux["empty_after_filters"] is set when the sparsity or the
+    enrichment filter left nothing (diff_mustache.py:507-508, 519-520, 526-527 abandon the whole block pair then).
+    candidate_order: "sorted" = argsort(o) as mustache.py:792, "rowmajor" = np.where(o < pt) as diff_mustache.py:458;
+    only the candidate SET influences the result.
     """
     aux = {}
     if len(mask_rows) < MIN_MASK_FOR_BH:
@@ -180,6 +183,7 @@ def call_loops(n, dpx, start, mask_rows, mask_cols, mask_vals, rec_rows, rec_col
     keep = sparsity_filter(index, x, y, sc, st)
     x, y = x[keep], y[keep]
     if len(x) == 0:
+        aux["empty_after_filters"] = True
         return [], aux
     if intra:
         d = y - x
@@ -190,6 +194,7 @@ def call_loops(n, dpx, start, mask_rows, mask_cols, mask_vals, rec_rows, rec_col
         with np.errstate(invalid="ignore"):
             passing = cxy > 2 * mvec
         if passing.sum() == 0:
+            aux["empty_after_filters"] = True
             return [], aux
         x, y = x[passing], y[passing]
     reps = cluster_representatives(x, y, o_of)

@@ -1,0 +1,111 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/mustache_b200.h declares
+(no compute calls without a GPU), error behaviour without a device, and the world_size-2 record gather over gloo."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "mustache_b200.h")).read()
+    return sorted(set(re.findall(r"MB200_API\s+[\w\s\*]+?\b(mb200_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mustache_b200 import build, engine
+    build.build()
+    lib = engine.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 24
+    for name in names:
+        assert hasattr(lib, name), name
+        assert name in engine.SIGNATURES, "ctypes binding missing for " + name
+    assert set(engine.SIGNATURES) == set(names)
+    assert lib.mb200_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mustache_b200 import engine
+    with pytest.raises(RuntimeError):
+        engine.ScaleSpaceEngine(0)
+    lib = engine.load_library()
+    h = C.c_void_p()
+    assert lib.mb200_create(0, C.byref(h)) < 0 and not h.value
+    assert lib.mb200_last_error(None) == b"null engine"
+    assert lib.mb200_run(None) < 0
+
+
+def test_cli_parsers_match_reference_defaults():
+    from mustache_b200 import diff_mustache, mustache
+    a = mustache.parse_args(["-f", "x", "-r", "5kb", "-o", "out", "-ch", "21"])
+    assert (a.pt, a.st, a.s_z, a.octaves, a.s, a.nprocesses) == (0.2, 0.88, 1.6, 2, 10, 4)
+    assert a.chromosome == ["21"] and a.chromosome2 == "n"
+    assert mustache.parseBP("5kb") == 5000 and mustache.parseBP("2mb") == 2000000 and mustache.parseBP("12") == 12
+    assert mustache.parseBP("kb") is False and mustache.parseBP("") is False
+    assert mustache.resolve_distance(None, 5000) == 2000000 and mustache.resolve_distance(None, 100000) == 20000000
+    assert mustache.resolve_distance(None, 500) == 1000000 and mustache.resolve_distance("100mb", 5000) == 50000000
+    assert mustache.resolve_distance("100mb", 5000, cap=2000) == 10000000
+    d = diff_mustache.parse_args(["-f1", "a", "-f2", "b", "-r", "5kb", "-o", "o", "-ch", "1", "-pt2", "0.05"])
+    assert d.pt2 == 0.05 and d.pt == 0.2
+    row = mustache.format_row("21", "21", [3161, 3224, 0.0919438088559645, 2.111212657236631], 5000)
+    assert row == "21\t15805000\t15810000\t21\t16120000\t16125000\t0.0919438088559645\t2.111212657236631\n"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mustache_b200 import gather
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    recs, ids = [], []
+    for b in range(rank, 5, world):                 # round-robin block shard, ragged sizes, one empty block
+        m = 0 if b == 3 else 3 + 2 * b
+        recs.append(dict(rows=rng.integers(0, 2000, m).astype(np.int32), cols=rng.integers(0, 2000, m).astype(np.int32),
+                         v=rng.random(m), score_id=rng.integers(3, 23, m).astype(np.int32), p=rng.random(m),
+                         pair=rng.random(m), nz_count=1000 + b))
+        ids.append(b)
+    got = gather.all_gather_records(recs, rank, world, torch.device("cpu"), block_ids=ids, with_pair=True)
+    q.put((rank, got, gather.pack_records(recs, 0, ids, with_pair=True)))
+    dist.destroy_process_group()
+
+
+def test_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    from mustache_b200 import gather
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = np.concatenate([res[0][2], res[1][2]], axis=0)
+    for rank, got, _ in res:
+        assert np.array_equal(got, full)            # every rank sees every record, rank order, bit-exact
+    by = gather.split_by_block(full)
+    assert sorted(k[1] for k in by) == [0, 1, 2, 4]  # block 3 had no records
+    r4 = by[(0, 4)]
+    assert r4["n_found"] == 11 and r4["nz_count"] == 1004 and "pair" in r4
+    assert (np.diff(r4["rows"].astype(np.int64) * 4096 + r4["cols"]) >= 0).all()    # row-major within a block

@@ -88,6 +88,8 @@ int use_device(mb200_engine* e) {
     return MB200_OK;
 }
 
+constexpr size_t V_GUARD_BYTES = 64 * 1024;   // slack on both sides of the axis-0 scratch for 16-byte-aligned row copies
+
 size_t v_bytes_per_block(const mb200_engine* e) {
     return (size_t)e->prog.n_steps * e->n * e->wv * sizeof(double);
 }
@@ -107,7 +109,7 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.rec_cap = e->rec_cap;
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
     g.raw = (const double*)e->raw.p + (size_t)first_block * e->n * e->wc;
-    g.V = (double*)e->V.p;
+    g.V = (double*)((char*)e->V.p + V_GUARD_BYTES);     // bulk copies may start a few elements before a row
     g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
     g.part_sum = (double*)e->part_sum.p + (size_t)first_block * ns * e->ncta_h;
     g.rec_count = (unsigned long long*)e->rec_count.p + first_block;
@@ -307,7 +309,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if (e->dhi < 4) return fail(e, MB200_ERR_ARG, "no diagonal >= 4 in the tile");
     e->wc = e->dhi - 3;
     e->vlo = 2 - e->prog.rmax;
-    e->wv = e->dhi + 2 * e->prog.rmax + 1;
+    e->wv = (e->dhi + 2 * e->prog.rmax + 1 + 1) & ~1;   // even: rows of the axis-0 scratch stay 16-byte aligned
     e->nblocks = nblocks;
     const double frac = record_fraction > 0 ? record_fraction : 0.125;
     e->rec_cap = std::max<long long>(4096, (long long)(frac * (double)n * e->wc));
@@ -333,11 +335,11 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     size_t free_b = 0, total_b = 0;
     CU(e, cudaMemGetInfo(&free_b, &total_b));
     const size_t per_block = v_bytes_per_block(e);
-    const size_t budget = (size_t)(0.8 * (double)(free_b + e->V.cap));
+    const size_t budget = (size_t)(0.8 * (double)(free_b + e->V.cap)) - 2 * V_GUARD_BYTES;
     long long fit = (long long)(budget / per_block);
     if (fit < 1) return fail(e, MB200_ERR_NOMEM, "axis-0 scratch for one block needs %zu bytes, %zu available", per_block, budget);
     e->pass_blocks = (int)std::min<long long>(fit, nblocks);
-    if ((st = ensure(e, e->V, (size_t)e->pass_blocks * per_block))) return st;
+    if ((st = ensure(e, e->V, (size_t)e->pass_blocks * per_block + 2 * V_GUARD_BYTES))) return st;
     CU(e, cudaMemsetAsync(e->raw.p, 0, B * n * e->wc * sizeof(double), e->stream));
     e->configured = true;
     e->ran = false;

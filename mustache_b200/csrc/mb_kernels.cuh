@@ -86,11 +86,12 @@ constexpr int KH_SR = KH_TR - 2;   // scored rows per CTA
 constexpr int KH_SC = KH_TC - 2;   // scored columns per CTA
 constexpr int KH_LP = KH_TC + 1;   // pitch of the DoG slots (odd: lanes index rows)
 
-__host__ __device__ inline int kh_vbuf_pitch(int rmax) { return (KH_TC + 2 * rmax) | 1; }
+// even pitch (16-byte aligned rows for the bulk copies) with room for the parity shift and the even-rounded tail
+__host__ __device__ inline int kh_vbuf_pitch(int rmax) { return KH_TC + 2 * rmax + 4; }
 __host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
-    return ((size_t)KH_TR * kh_vbuf_pitch(rmax) + 2 * (size_t)KH_TR * KH_LP + 2 * (size_t)KH_K * KH_THREADS
-            + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KH_THREADS / 32)) * sizeof(double);
+    return (2 * (size_t)KH_TR * kh_vbuf_pitch(rmax) + 2 * (size_t)KH_TR * KH_LP
+            + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KH_THREADS / 32) + 2) * sizeof(double);
 }
 
 // scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
@@ -203,7 +204,10 @@ kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // K_H: axis-1 pass, DoG chain, 3x3 maxima, extremum test, per-level statistics.  grid = (col tiles, row tiles, blocks)
-// Thread (lane = tile row, warp = group of 8 tile columns) owns 8 pixels for the whole chain.
+// Thread (lane = tile row, warp = group of 8 tile columns) owns 8 pixels for the whole chain and keeps their state
+// (previous Gaussian, best response, winning level, the maxima of the two previous DoGs) in registers; one CTA per SM.
+// The V_s rows of the tile are brought in by TMA bulk copies (cp.async.bulk, one per tile row, issued by warp 0) into a
+// two-stage ring guarded by mbarriers, so the copy for step s+1 is in flight while step s is filtered and scored.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
@@ -216,16 +220,41 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(KH_THREADS, 2)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(KH_THREADS, 1)
 kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int rmax = prog.rmax;
-    const int pv = kh_vbuf_pitch(rmax);
-    double* vbuf = smem;                                        // [KH_TR][pv]
-    double* lbuf = vbuf + (size_t)KH_TR * pv;                   // [2][KH_TR][KH_LP]
-    double* mbuf = lbuf + 2 * (size_t)KH_TR * KH_LP;            // [2][KH_K][KH_THREADS]   thread-private
-    double* pmin = mbuf + 2 * (size_t)KH_K * KH_THREADS;        // [n_scored][warps]
+    const int pv = kh_vbuf_pitch(rmax);                         // even: every tile row starts 16-byte aligned
+    double* vbuf = smem;                                        // [2][KH_TR][pv]
+    double* lbuf = vbuf + 2 * (size_t)KH_TR * pv;               // [2][KH_TR][KH_LP]
+    double* pmin = lbuf + 2 * (size_t)KH_TR * KH_LP;            // [n_scored][warps]
     double* psum = pmin + (size_t)max(prog.n_scored, 1) * (KH_THREADS / 32);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * (KH_THREADS / 32));   // [2]
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,6 +278,15 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     const int jc0 = js - 1 + c0;                        // image column of its first pixel
     const bool row_in = (i >= 0) && (i < g.n);
     const bool row_scored = (lane >= 1) && (lane <= KH_SR) && row_in;
+    // tiles whose +/- rmax column halo leaves the image need 'reflect' indexing: generic (slow) staging for those
+    const bool border = (js - 1 - rmax < 0) || (js - 1 + KH_TC + rmax > g.n);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 32);
+        mbar_init(&mbar[1], 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
     unsigned mask = 0;
@@ -264,39 +302,66 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     // relevance of this warp's 32 x 8 chunk: any pixel inside the tile on a diagonal the maxima can touch
     const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n) && (jc0 + KH_K - 1 >= 0);
 
-    double vbest[KH_K], gprev[KH_K];
+    // issue the bulk copies of step s into stage s&1 (warp 0, one row per lane)
+    auto issue = [&](int s) {
+        const int R = prog.st[s].radius;
+        uint64_t* bar = &mbar[s & 1];
+        uint32_t bytes = 0;
+        if (row_in) {
+            const int a = js - 1 - R - i - g.vlo;               // first needed diagonal slot of this row (may be < 0)
+            const int a0 = a & ~1;                              // floor to even: 16-byte aligned source
+            const int cnt = ((a - a0) + KH_TC + 2 * R + 1) & ~1;
+            bytes = (uint32_t)cnt * 8u;
+            const double* src = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv + (long long)i * g.wv + a0;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_row(vbuf + (size_t)(s & 1) * KH_TR * pv + (size_t)lane * pv, src, bytes, bar);
+        } else {
+            mbar_arrive_expect_tx(bar, 0);
+        }
+    };
+    if (!border && warp == 0) issue(0);
+
+    double vbest[KH_K], gprev[KH_K], lcur[KH_K], mprev[KH_K], mcur[KH_K];
     unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
 #pragma unroll
-    for (int k = 0; k < KH_K; ++k) { vbest[k] = 0.0; gprev[k] = 0.0; }
+    for (int k = 0; k < KH_K; ++k) { vbest[k] = 0.0; gprev[k] = 0.0; lcur[k] = 0.0; mprev[k] = 0.0; mcur[k] = 0.0; }
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
     int nl = 0;                                         // DoGs formed so far (slot parity)
     int ndiff = 0;                                      // MB_FLAG_DIFFREF steps seen so far
     const bool need_max = prog.n_scored > 0;
+    const int lrow = lane * KH_LP + c0;                 // this thread's first pixel inside a DoG slot
 
     for (int s = 0; s < prog.n_steps; ++s) {
         const int R = prog.st[s].radius;
         const int flags = prog.st[s].flags;
-        // ---- stage V_s rows of the tile (+/- R columns, reflected at the tile border) ----
-        {
+        double* vst = vbuf + (size_t)(s & 1) * KH_TR * pv;
+        const int shift = (js - 1 - R - i - g.vlo) & 1;          // element offset of this row inside its staged copy
+        if (!border) {
+            // stage s+1 was last read by the filter of step s-1, which every thread finished before the barrier of step s-1
+            if (warp == 0 && s + 1 < prog.n_steps) issue(s + 1);
+            mbar_wait(&mbar[s & 1], (s >> 1) & 1);
+        } else {
             const double* vin = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
             const int wlen = KH_TC + 2 * R;
-            for (int e = threadIdx.x; e < KH_TR * wlen; e += KH_THREADS) {
-                const int r = e / wlen, t = e - r * wlen;
+            for (int r = warp; r < KH_TR; r += KH_THREADS / 32) {
                 const int ii = i0 + r;
-                double val = 0.0;
-                if (ii >= 0 && ii < g.n) {
-                    const int jj = reflect_idx(js - 1 - R + t, g.n);
-                    const int dd = jj - ii - g.vlo;
-                    if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
+                const int sh = (js - 1 - R - ii - g.vlo) & 1;
+                for (int t = lane; t < wlen; t += 32) {
+                    double val = 0.0;
+                    if (ii >= 0 && ii < g.n) {
+                        const int jj = reflect_idx(js - 1 - R + t, g.n);
+                        const int dd = jj - ii - g.vlo;
+                        if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
+                    }
+                    vst[(size_t)r * pv + sh + t] = val;
                 }
-                vbuf[(size_t)r * pv + t] = val;
             }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- axis-1 pass for the 8 owned pixels, DoG into the ring ----
         double gnew[KH_K];
         if (chunk_live && row_in) {
-            conv_slide<KH_K>(vbuf + (size_t)lane * pv + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
+            conv_slide<KH_K>(vst + (size_t)lane * pv + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
@@ -309,32 +374,36 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
             }
         }
         const bool form = !(flags & MB_FLAG_RESTART);
-        double* lnew = lbuf + (size_t)(nl & 1) * KH_TR * KH_LP;
+        double* lnew = lbuf + (nl & 1) * (KH_TR * KH_LP);
+        double lown[KH_K];
         if (form) {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
                 const int j = jc0 + k;
                 // outside the image the maximum filter sees cval = 0 (mode='constant', mustache.py:741)
-                const double l = (row_in && j >= 0 && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-                lnew[(size_t)lane * KH_LP + c0 + k] = l;
-                if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && row_in && j >= 0 && j < g.n)
-                    g.dbgL[(size_t)i * g.n + j] = l;
+                lown[k] = (row_in && j >= 0 && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                lnew[lrow + k] = lown[k];
             }
-        }
-        if (form && (flags & MB_FLAG_DIFFREF)) {
-            if (g.dout != nullptr && row_scored) {
+            if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && row_in) {
+#pragma unroll
+                for (int k = 0; k < KH_K; ++k) {
+                    const int j = jc0 + k;
+                    if (j >= 0 && j < g.n) g.dbgL[(size_t)i * g.n + j] = lown[k];
+                }
+            }
+            if ((flags & MB_FLAG_DIFFREF) && g.dout != nullptr && row_scored) {
                 double* dst = g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc;
 #pragma unroll
                 for (int k = 0; k < KH_K; ++k) {
                     const int c = c0 + k, j = jc0 + k, d = j - i;
-                    if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = __dsub_rn(gprev[k], gnew[k]);
+                    if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = lown[k];
                 }
             }
-            ++ndiff;
+            if (flags & MB_FLAG_DIFFREF) ++ndiff;
         }
 #pragma unroll
         for (int k = 0; k < KH_K; ++k) gprev[k] = gnew[k];
-        __syncthreads();
+        __syncthreads();            // DoG slot complete; also: every thread is done reading stage s&1 and slot (nl-1)&1
         if (!form) continue;
         if (!need_max) { ++nl; continue; }
         // ---- 3x3 maxima of the new DoG for the owned pixels (separable: rows first, then columns) ----
@@ -342,44 +411,40 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
         unsigned e_new = 0;
         if (row_scored) {
             double vm[KH_K + 2];
+            const double* up = lnew + lrow - KH_LP;
 #pragma unroll
             for (int t = 0; t < KH_K + 2; ++t) {
-                int c = c0 - 1 + t;
-                c = c < 0 ? 0 : (c > KH_TC - 1 ? KH_TC - 1 : c);        // clamped columns only feed halo pixels
-                const double a0 = lnew[(size_t)(lane - 1) * KH_LP + c];
-                const double a1 = lnew[(size_t)lane * KH_LP + c];
-                const double a2 = lnew[(size_t)(lane + 1) * KH_LP + c];
+                int c = t - 1;                                          // column relative to the first owned pixel
+                if (warp == 0 && t == 0) c = 0;                         // clamped columns only feed halo pixels
+                if (warp == KH_THREADS / 32 - 1 && t == KH_K + 1) c = KH_K - 1;
+                const double a0 = up[c];
+                const double a1 = (t >= 1 && t <= KH_K) ? lown[t - 1] : up[KH_LP + c];
+                const double a2 = up[2 * KH_LP + c];
                 vm[t] = fmax(fmax(a0, a1), a2);
             }
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
                 mnew[k] = fmax(fmax(vm[k], vm[k + 1]), vm[k + 2]);
-                const double own = lnew[(size_t)lane * KH_LP + c0 + k];
-                if (own == mnew[k]) e_new |= 1u << k;
+                if (lown[k] == mnew[k]) e_new |= 1u << k;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) mnew[k] = 0.0;
         }
-        double* m_slot_new = mbuf + (size_t)(nl & 1) * KH_K * KH_THREADS;      // holds M of DoG nl-2 until overwritten
         if (flags & MB_FLAG_SCORE) {
             const int sidx = prog.st[s].score_idx;
-            const double* lcur = lbuf + (size_t)((nl - 1) & 1) * KH_TR * KH_LP;
             double tmin = __longlong_as_double(0x7ff0000000000000LL), tsum = 0.0;
+            const unsigned cand = mask & e_cur & (e_prev | e_new);
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
                 if (mask & (1u << k)) {
-                    const double lc = lcur[(size_t)lane * KH_LP + c0 + k];
-                    const double a = fabs(lc);
+                    const double a = fabs(lcur[k]);
                     tmin = fmin(tmin, a);
                     tsum = __dadd_rn(tsum, a);
-                    if (lc > vbest[k] && (e_cur & (1u << k))) {
-                        const double mp = m_slot_new[(size_t)k * KH_THREADS + threadIdx.x];     // M of the DoG before
-                        if (((e_prev | e_new) & (1u << k)) && lc > mp && lc > mnew[k]) {
-                            vbest[k] = lc;
-                            lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
-                        }
-                    }
+                }
+                if ((cand & (1u << k)) && lcur[k] > vbest[k] && lcur[k] > mprev[k] && lcur[k] > mnew[k]) {
+                    vbest[k] = lcur[k];
+                    lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
                 }
             }
             tmin = warp_min(tmin);
@@ -390,7 +455,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < KH_K; ++k) m_slot_new[(size_t)k * KH_THREADS + threadIdx.x] = mnew[k];
+        for (int k = 0; k < KH_K; ++k) { mprev[k] = mcur[k]; mcur[k] = mnew[k]; lcur[k] = lown[k]; }
         e_prev = e_cur;
         e_cur = e_new;
         ++nl;

@@ -89,8 +89,9 @@ MB200_API int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, 
 MB200_API int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored);
 
 /* Device time of the last mb200_run in milliseconds (CUDA events on the engine's stream):
- * prep (mask count), axis-0 kernel, axis-1+extremum kernel, statistics+p-values, total. */
-MB200_API int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* fin_ms, float* total_ms);
+ * prep (mask count), axis-0 kernel, axis-1 + DoG kernel, extremum/scoring kernel, statistics + p-values, total. */
+MB200_API int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* ks_ms, float* fin_ms,
+                                float* total_ms);
 /* Kernel launches issued by the last mb200_run. */
 MB200_API int mb200_last_launches(mb200_engine* e, int* launches);
 

@@ -23,23 +23,26 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+def _compile(lib, extra, verbose):
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed (%d)" % r.returncode)
+
+
+def build(force=False, verbose=False):
+    if force or needs_build(LIB):
+        _compile(LIB, [], verbose)
     return LIB
 
 

@@ -29,19 +29,19 @@ struct mb200_engine {
     bool ran_diff = false;
     bool configured = false;
     bool ran = false;
-    int n = 0, dpx = 0, intra = 1, dhi = 0, wc = 0, vlo = 0, wv = 0, nblocks = 0, pass_blocks = 0;
+    int n = 0, dpx = 0, intra = 1, dhi = 0, wc = 0, vlo = 0, wv = 0, wl = 0, nblocks = 0, pass_blocks = 0;
     long long rec_cap = 0;
     int ncta_h = 0;
-    DevBuf raw, V, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
+    DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
     bool counts_valid = false;
     cudaEvent_t ev_begin = nullptr, ev_prep = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ev_pass;   // 3 per pass: start, after kv, after kh
-    float t_prep = 0, t_kv = 0, t_kh = 0, t_fin = 0, t_total = 0;
+    std::vector<cudaEvent_t> ev_pass;   // 4 per pass: start, after kv, after kh, after ks
+    float t_prep = 0, t_kv = 0, t_kh = 0, t_ks = 0, t_fin = 0, t_total = 0;
     int launches = 0;
-    size_t kv_smem_set = 0, kh_smem_set = 0;
+    size_t kv_smem_set = 0, kh_smem_set = 0, ks_smem_set = 0;
 };
 
 namespace {
@@ -94,6 +94,10 @@ size_t v_bytes_per_block(const mb200_engine* e) {
     return (size_t)e->prog.n_steps * e->n * e->wv * sizeof(double);
 }
 
+size_t l_bytes_per_block(const mb200_engine* e) {
+    return (size_t)e->prog.n_steps * e->n * e->wl * sizeof(double);
+}
+
 MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     MbGeom g;
     g.n = e->n;
@@ -110,6 +114,9 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
     g.raw = (const double*)e->raw.p + (size_t)first_block * e->n * e->wc;
     g.V = (double*)((char*)e->V.p + V_GUARD_BYTES);     // bulk copies may start a few elements before a row
+    g.L = (double*)((char*)e->Lb.p + V_GUARD_BYTES);
+    g.wl = e->wl;
+    g.pad0 = 0;
     g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
     g.part_sum = (double*)e->part_sum.p + (size_t)first_block * ns * e->ncta_h;
     g.rec_count = (unsigned long long*)e->rec_count.p + first_block;
@@ -130,8 +137,13 @@ dim3 kv_grid(const mb200_engine* e, int nblk) {
 }
 
 dim3 kh_grid(const mb200_engine* e, int nblk) {
-    const int span = (e->dhi - 4 + 1) + KH_SR - 1;
-    return dim3((span + KH_SC - 1) / KH_SC, (e->n + KH_SR - 1) / KH_SR, nblk);
+    const int span = (e->dhi + 1) + KH_TR - 1;            // diagonals 2..dhi+2 over the rows of one tile
+    return dim3((span + KH_TC - 1) / KH_TC, (e->n + KH_TR - 1) / KH_TR, nblk);
+}
+
+dim3 ks_grid(const mb200_engine* e, int nblk) {
+    const int span = (e->dhi - 4 + 1) + KS_SR - 1;
+    return dim3((span + KS_SC - 1) / KS_SC, (e->n + KS_SR - 1) / KS_SR, nblk);
 }
 
 int set_smem_limits(mb200_engine* e) {
@@ -146,11 +158,15 @@ int set_smem_limits(mb200_engine* e) {
         CU(e, cudaFuncSetAttribute(kh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
         e->kh_smem_set = khb;
     }
+    if (ks_smem_bytes() != e->ks_smem_set) {
+        CU(e, cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem_bytes()));
+        e->ks_smem_set = ks_smem_bytes();
+    }
     return MB200_OK;
 }
 
 int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cudaEvent_t after_kv,
-                const MbProgram* program = nullptr) {
+                const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
     const MbProgram& pg = program ? *program : e->prog;
     const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
@@ -159,7 +175,13 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
     kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, g);
     CU(e, cudaGetLastError());
+    if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
     e->launches += 2;
+    if (pg.n_scored > 0) {
+        ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(), e->stream>>>(pg, g);
+        CU(e, cudaGetLastError());
+        e->launches += 1;
+    }
     return MB200_OK;
 }
 
@@ -222,7 +244,7 @@ void mb200_destroy(mb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    DevBuf* all[] = {&e->raw, &e->V, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
+    DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
                      &e->d_score_id};
@@ -313,7 +335,8 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->nblocks = nblocks;
     const double frac = record_fraction > 0 ? record_fraction : 0.125;
     e->rec_cap = std::max<long long>(4096, (long long)(frac * (double)n * e->wc));
-    dim3 gh = kh_grid(e, 1);
+    e->wl = (e->dhi + 1 + 1) & ~1;                       // diagonals 2..dhi+2, even row length
+    dim3 gh = ks_grid(e, 1);
     e->ncta_h = gh.x * gh.y;
     if ((st = set_smem_limits(e))) return st;
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
@@ -334,12 +357,13 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     // axis-0 scratch: as many blocks per pass as fit in ~80 % of what is free now (plus what V already holds)
     size_t free_b = 0, total_b = 0;
     CU(e, cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_block = v_bytes_per_block(e);
-    const size_t budget = (size_t)(0.8 * (double)(free_b + e->V.cap)) - 2 * V_GUARD_BYTES;
+    const size_t per_block = v_bytes_per_block(e) + l_bytes_per_block(e);
+    const size_t budget = (size_t)(0.8 * (double)(free_b + e->V.cap + e->Lb.cap)) - 4 * V_GUARD_BYTES;
     long long fit = (long long)(budget / per_block);
     if (fit < 1) return fail(e, MB200_ERR_NOMEM, "axis-0 scratch for one block needs %zu bytes, %zu available", per_block, budget);
     e->pass_blocks = (int)std::min<long long>(fit, nblocks);
-    if ((st = ensure(e, e->V, (size_t)e->pass_blocks * per_block + 2 * V_GUARD_BYTES))) return st;
+    if ((st = ensure(e, e->V, (size_t)e->pass_blocks * v_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
+    if ((st = ensure(e, e->Lb, (size_t)e->pass_blocks * l_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     CU(e, cudaMemsetAsync(e->raw.p, 0, B * n * e->wc * sizeof(double), e->stream));
     e->configured = true;
     e->ran = false;
@@ -431,7 +455,7 @@ int mb200_run(mb200_engine* e) {
     e->counts_valid = false;
     e->ran_diff = false;
     const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
-    while ((int)e->ev_pass.size() < 3 * npass) {
+    while ((int)e->ev_pass.size() < 4 * npass) {
         cudaEvent_t ev;
         CU(e, cudaEventCreate(&ev));
         e->ev_pass.push_back(ev);
@@ -447,9 +471,9 @@ int mb200_run(mb200_engine* e) {
     CU(e, cudaEventRecord(e->ev_prep, e->stream));
     for (int p = 0; p < npass; ++p) {
         const int first = p * e->pass_blocks, nb = std::min(e->pass_blocks, B - first);
-        CU(e, cudaEventRecord(e->ev_pass[3 * p], e->stream));
-        if ((st = launch_pass(e, first, nb, nullptr, e->ev_pass[3 * p + 1]))) return st;
-        CU(e, cudaEventRecord(e->ev_pass[3 * p + 2], e->stream));
+        CU(e, cudaEventRecord(e->ev_pass[4 * p], e->stream));
+        if ((st = launch_pass(e, first, nb, nullptr, e->ev_pass[4 * p + 1], nullptr, e->ev_pass[4 * p + 2]))) return st;
+        CU(e, cudaEventRecord(e->ev_pass[4 * p + 3], e->stream));
     }
     if (e->prog.n_scored > 0) {
         reduce_stats_kernel<<<dim3(e->prog.n_scored, B), 256, 0, e->stream>>>(
@@ -526,22 +550,27 @@ int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int
     return MB200_OK;
 }
 
-int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* fin_ms, float* total_ms) {
+int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* ks_ms, float* fin_ms,
+                      float* total_ms) {
     if (!e) return MB200_ERR_ARG;
     if (!e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
     int st = use_device(e);
     if (st) return st;
     CU(e, cudaEventSynchronize(e->ev_end));
     const int npass = (e->nblocks + e->pass_blocks - 1) / e->pass_blocks;
-    float kv = 0, kh = 0, t = 0;
+    float kv = 0, kh = 0, ks = 0, t = 0;
     for (int p = 0; p < npass; ++p) {
-        CU(e, cudaEventElapsedTime(&t, e->ev_pass[3 * p], e->ev_pass[3 * p + 1]));
+        CU(e, cudaEventElapsedTime(&t, e->ev_pass[4 * p], e->ev_pass[4 * p + 1]));
         kv += t;
-        CU(e, cudaEventElapsedTime(&t, e->ev_pass[3 * p + 1], e->ev_pass[3 * p + 2]));
+        CU(e, cudaEventElapsedTime(&t, e->ev_pass[4 * p + 1], e->ev_pass[4 * p + 2]));
         kh += t;
+        CU(e, cudaEventElapsedTime(&t, e->ev_pass[4 * p + 2], e->ev_pass[4 * p + 3]));
+        ks += t;
     }
     CU(e, cudaEventElapsedTime(&e->t_prep, e->ev_begin, e->ev_prep));
-    CU(e, cudaEventElapsedTime(&e->t_fin, e->ev_pass[3 * (npass - 1) + 2], e->ev_end));
+    CU(e, cudaEventElapsedTime(&e->t_fin, e->ev_pass[4 * (npass - 1) + 3], e->ev_end));
+    e->t_ks = ks;
+    if (ks_ms) *ks_ms = ks;
     CU(e, cudaEventElapsedTime(&e->t_total, e->ev_begin, e->ev_end));
     e->t_kv = kv;
     e->t_kh = kh;
@@ -615,6 +644,7 @@ int mb200_run_differential(mb200_engine* e) {
         g.raw = (const double*)e->rawD.p + (size_t)first * tile;
         g.fill = 0.0;
         g.rec_cap = 0;
+        g.L = nullptr;                      // nothing is scored on the difference stack: its DoGs go to dout only
         // dout is indexed [ndiff][nblk of the pass]; with several passes each pass writes its own slice per octave
         if (npairs > e->pass_blocks) return fail(e, MB200_ERR_NOMEM, "differential batch does not fit one pass (%d pairs > %d)", npairs, e->pass_blocks);
         g.dout = (double*)e->dout.p;

@@ -3,8 +3,10 @@
 // Replaces the body of mustache() between mustache.py:699 and mustache.py:772 (reference: ay-lab/mustache v1.3.3):
 //   K_V  (kv_kernel)   axis-0 pass of every Gaussian of the chain            mustache.py:719,725,734,751 (first half of
 //                      scipy gaussian_filter: correlate1d along axis 0, mode='reflect')
-//   K_H  (kh_kernel)   axis-1 pass + DoG + zero-padded 3x3 maxima + 5-clause extremum test + per-level |L| min/sum
-//                      mustache.py:728,738,754 (DoG) :740-743,757 (maximum_filter) :760-768 (test + state update)
+//   K_H  (kh_kernel)   axis-1 pass + DoG, written to HBM                     mustache.py:728,738,754 (second half of
+//                      gaussian_filter + the subtraction)
+//   K_S  (ks_kernel)   zero-padded 3x3 maxima + 5-clause extremum test + running best + per-level |L| min/sum
+//                      mustache.py:740-743,757 (maximum_filter) :760-768 (test + state update)
 //   reduce / finalise  expon.fit (loc = min, scale = mean - min) and 1 - expon.cdf for the winners only   mustache.py:755-756
 //
 // Data layout in HBM ("band layout"): a block is an N x N tile but only diagonals d = j - i in [4, dhi] can hold data
@@ -57,6 +59,9 @@ struct MbGeom {
     long long rec_cap;              // record capacity per block
     const double* raw;              // [nblk][n][wc]
     double* V;                      // [n_steps][nblk][n][wv]
+    double* L;                      // [n_steps][nblk][n][wl]  DoG formed at each step, diagonals 2..dhi+2 (nullptr: not stored)
+    int wl;                         // diagonals per row of L (even)
+    int pad0;
     double* part_min;               // [nblk][n_scored][ncta_h]
     double* part_sum;               // [nblk][n_scored][ncta_h]
     unsigned long long* rec_count;  // [nblk]
@@ -78,20 +83,33 @@ constexpr int KV_TW = 32;      // columns per CTA = lanes
 constexpr int KV_K = 8;        // outputs per thread along the filter axis
 constexpr int KV_THREADS = (KV_TH / KV_K) * 32;   // 256
 
-constexpr int KH_TR = 32;      // tile rows = lanes (30 scored + 2 halo)
-constexpr int KH_TC = 64;      // tile columns (62 scored + 2 halo)
+constexpr int KH_TR = 32;      // tile rows = lanes (axis-1 pass)
+constexpr int KH_TC = 64;      // tile columns
 constexpr int KH_K = 8;
 constexpr int KH_THREADS = (KH_TC / KH_K) * 32;   // 256
-constexpr int KH_SR = KH_TR - 2;   // scored rows per CTA
-constexpr int KH_SC = KH_TC - 2;   // scored columns per CTA
-constexpr int KH_LP = KH_TC + 1;   // pitch of the DoG slots (odd: lanes index rows)
 
-// even pitch (16-byte aligned rows for the bulk copies) with room for the parity shift and the even-rounded tail
-__host__ __device__ inline int kh_vbuf_pitch(int rmax) { return KH_TC + 2 * rmax + 4; }
+constexpr int KS_TR = 32;      // scoring tile rows = lanes (30 scored + 2 halo)
+constexpr int KS_TC = 64;      // scoring tile columns (62 scored + 2 halo)
+constexpr int KS_K = 8;
+constexpr int KS_THREADS = (KS_TC / KS_K) * 32;   // 256
+constexpr int KS_SR = KS_TR - 2;   // scored rows per CTA
+constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
+constexpr int KS_PITCH = KS_TC + 6;   // 70: even and == 2 (mod 4); room for the parity shift, the even tail, the bank stagger
+
+// even pitch (16-byte aligned rows for the bulk copies) with room for the parity shift, the even-rounded tail and the
+// 2-element bank stagger; forced to 2 (mod 4) so that lanes (= rows) spread over all banks (see kh_kernel)
+__host__ __device__ inline int kh_vbuf_pitch(int rmax) {
+    const int p = KH_TC + 2 * rmax + 6;
+    return (p % 4 == 2) ? p : p + 2;
+}
 __host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
-    return (2 * (size_t)KH_TR * kh_vbuf_pitch(rmax) + 2 * (size_t)KH_TR * KH_LP
-            + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KH_THREADS / 32) + 2) * sizeof(double);
+    (void)n_scored;
+    return (2 * (size_t)KH_TR * kh_vbuf_pitch(rmax) + 2) * sizeof(double);          // vbuf[2] + 2 mbarriers
+}
+
+__host__ __device__ inline size_t ks_smem_bytes() {
+    return (2 * (size_t)KS_TR * KS_PITCH + 4 * (size_t)KS_THREADS + 2) * sizeof(double);   // rows[2] + statistics + mbarriers
 }
 
 // scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
@@ -131,9 +149,13 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
 #pragma unroll
         for (int u = 0; u < K; ++u) {
             const double w = tp[j - u];
+            double t[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]), w));
+            for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);
             pl[u % K] = ctr[(u + K - j) * stride];
             pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
         }
@@ -142,9 +164,13 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
     for (int u = 0; u < K - 1; ++u) {
         if (u < j) {
             const double w = tp[j - u];
+            double t[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]), w));
+            for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);
+#pragma unroll
+            for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);
             pl[u % K] = ctr[(u + K - j) * stride];
             pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
         }
@@ -245,41 +271,36 @@ __device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-__global__ void __launch_bounds__(KH_THREADS, 1)
+// ---------------------------------------------------------------------------------------------------------------
+// K_H (kh_kernel): axis-1 pass of every step + DoG, written to HBM.  grid = (column tiles, row tiles, blocks).
+// Thread (lane = tile row, warp = group of 8 tile columns) produces 8 consecutive outputs along the filter axis; the
+// previous Gaussian of its pixels stays in registers, so L_s = G_{s-1} - G_s costs one subtraction.  No halo: the tiles
+// partition the band, the scoring kernel reads its own halo.  Two CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KH_THREADS, 2)
 kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int NW = KH_THREADS / 32;
     const int rmax = prog.rmax;
-    const int pv = kh_vbuf_pitch(rmax);                         // even: every tile row starts 16-byte aligned
-    double* vbuf = smem;                                        // [2][KH_TR][pv]
-    double* lbuf = vbuf + 2 * (size_t)KH_TR * pv;               // [2][KH_TR][KH_LP]
-    double* pmin = lbuf + 2 * (size_t)KH_TR * KH_LP;            // [n_scored][warps]
-    double* psum = pmin + (size_t)max(prog.n_scored, 1) * (KH_THREADS / 32);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * (KH_THREADS / 32));   // [2]
+    const int pv = kh_vbuf_pitch(rmax);                         // even, == 2 (mod 4)
+    double* vbuf = smem;                                        // [2][KH_TR][pv]   staged axis-0 rows (TMA destination)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(vbuf + 2 * (size_t)KH_TR * pv);   // [2]
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int is0 = blockIdx.y * KH_SR;                 // first scored row
-    const int i0 = is0 - 1;                             // tile row 0 (halo)
-    const int js = is0 + 4 + blockIdx.x * KH_SC;        // first scored column of this CTA
-    const int ilast = min(is0 + KH_SR, g.n) - 1;
-    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    const bool active = (js < g.n) && (js <= ilast + g.dhi);
-    if (!active) {
-        for (int t = threadIdx.x; t < prog.n_scored; t += KH_THREADS) {
-            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
-            g.part_min[o] = __longlong_as_double(0x7ff0000000000000LL);
-            g.part_sum[o] = 0.0;
-        }
-        return;
-    }
-    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+    const int i0 = blockIdx.y * KH_TR;                  // first row of the tile
+    const int js = i0 + 2 + blockIdx.x * KH_TC;         // first column: diagonal 2 of the first row
+    const int ilast = min(i0 + KH_TR, g.n) - 1;
+    if (js >= g.n || js > ilast + g.dhi + 2) return;    // tile entirely right of the band / of the image
     const int i = i0 + lane;                            // this thread's image row
-    const int c0 = warp * KH_K;                         // first tile column of this thread
-    const int jc0 = js - 1 + c0;                        // image column of its first pixel
-    const bool row_in = (i >= 0) && (i < g.n);
-    const bool row_scored = (lane >= 1) && (lane <= KH_SR) && row_in;
+    const int c0 = warp * KH_K;
+    const int jc0 = js + c0;                            // image column of its first pixel
+    const bool row_in = i < g.n;
     // tiles whose +/- rmax column halo leaves the image need 'reflect' indexing: generic (slow) staging for those
-    const bool border = (js - 1 - rmax < 0) || (js - 1 + KH_TC + rmax > g.n);
+    const bool border = (js - rmax < 0) || (js + KH_TC + rmax > g.n);
+    // staged row r starts at r*pv + 2*((r>>3)&1): with pv == 2 (mod 4) and the alternating parity shift of the bulk
+    // copies this makes the 16 rows of a half-warp hit 16 different 8-byte banks
+    const int vrow = lane * pv + 2 * ((lane >> 3) & 1);
 
     if (threadIdx.x == 0) {
         mbar_init(&mbar[0], 32);
@@ -287,81 +308,59 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // any pixel of this warp's 32 x 8 chunk on a diagonal the detector reads (2 .. dhi+2)?
+    const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n);
 
-    // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
-    unsigned mask = 0;
-    if (row_scored) {
-#pragma unroll
-        for (int k = 0; k < KH_K; ++k) {
-            const int c = c0 + k, j = jc0 + k, d = j - i;
-            if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) {
-                if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
-            }
-        }
-    }
-    // relevance of this warp's 32 x 8 chunk: any pixel inside the tile on a diagonal the maxima can touch
-    const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n) && (jc0 + KH_K - 1 >= 0);
-
-    // issue the bulk copies of step s into stage s&1 (warp 0, one row per lane)
-    auto issue = [&](int s) {
+    auto issue = [&](int s) {                                   // bulk copies of step s into stage s&1 (warp 0)
         const int R = prog.st[s].radius;
         uint64_t* bar = &mbar[s & 1];
-        uint32_t bytes = 0;
         if (row_in) {
-            const int a = js - 1 - R - i - g.vlo;               // first needed diagonal slot of this row (may be < 0)
+            const int a = js - R - i - g.vlo;                   // first needed diagonal slot of this row (may be < 0)
             const int a0 = a & ~1;                              // floor to even: 16-byte aligned source
             const int cnt = ((a - a0) + KH_TC + 2 * R + 1) & ~1;
-            bytes = (uint32_t)cnt * 8u;
+            const uint32_t bytes = (uint32_t)cnt * 8u;
             const double* src = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv + (long long)i * g.wv + a0;
             mbar_arrive_expect_tx(bar, bytes);
-            tma_load_row(vbuf + (size_t)(s & 1) * KH_TR * pv + (size_t)lane * pv, src, bytes, bar);
+            tma_load_row(vbuf + (s & 1) * (KH_TR * pv) + vrow, src, bytes, bar);
         } else {
             mbar_arrive_expect_tx(bar, 0);
         }
     };
     if (!border && warp == 0) issue(0);
 
-    double vbest[KH_K], gprev[KH_K], lcur[KH_K], mprev[KH_K], mcur[KH_K];
-    unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
+    double gA[KH_K], gB[KH_K];
 #pragma unroll
-    for (int k = 0; k < KH_K; ++k) { vbest[k] = 0.0; gprev[k] = 0.0; lcur[k] = 0.0; mprev[k] = 0.0; mcur[k] = 0.0; }
-    unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
-    int nl = 0;                                         // DoGs formed so far (slot parity)
-    int ndiff = 0;                                      // MB_FLAG_DIFFREF steps seen so far
-    const bool need_max = prog.n_scored > 0;
-    const int lrow = lane * KH_LP + c0;                 // this thread's first pixel inside a DoG slot
+    for (int k = 0; k < KH_K; ++k) gA[k] = gB[k] = 0.0;
+    int ndiff = 0;
 
-    for (int s = 0; s < prog.n_steps; ++s) {
+    auto step = [&](const int s, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
         const int R = prog.st[s].radius;
         const int flags = prog.st[s].flags;
-        double* vst = vbuf + (size_t)(s & 1) * KH_TR * pv;
-        const int shift = (js - 1 - R - i - g.vlo) & 1;          // element offset of this row inside its staged copy
+        double* vst = vbuf + (s & 1) * (KH_TR * pv);
+        const int shift = (js - R - i - g.vlo) & 1;              // element offset of this row inside its staged copy
         if (!border) {
-            // stage s+1 was last read by the filter of step s-1, which every thread finished before the barrier of step s-1
-            if (warp == 0 && s + 1 < prog.n_steps) issue(s + 1);
+            if (warp == 0 && s + 1 < prog.n_steps) issue(s + 1); // stage (s+1)&1 is free since the barrier of step s-1
             mbar_wait(&mbar[s & 1], (s >> 1) & 1);
         } else {
             const double* vin = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
             const int wlen = KH_TC + 2 * R;
-            for (int r = warp; r < KH_TR; r += KH_THREADS / 32) {
+            for (int r = warp; r < KH_TR; r += NW) {
                 const int ii = i0 + r;
-                const int sh = (js - 1 - R - ii - g.vlo) & 1;
+                const int sh = ((js - R - ii - g.vlo) & 1) + 2 * ((r >> 3) & 1);
                 for (int t = lane; t < wlen; t += 32) {
                     double val = 0.0;
-                    if (ii >= 0 && ii < g.n) {
-                        const int jj = reflect_idx(js - 1 - R + t, g.n);
+                    if (ii < g.n) {
+                        const int jj = reflect_idx(js - R + t, g.n);
                         const int dd = jj - ii - g.vlo;
                         if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
                     }
-                    vst[(size_t)r * pv + sh + t] = val;
+                    vst[r * pv + sh + t] = val;
                 }
             }
             __syncthreads();
         }
-        // ---- axis-1 pass for the 8 owned pixels, DoG into the ring ----
-        double gnew[KH_K];
         if (chunk_live && row_in) {
-            conv_slide<KH_K>(vst + (size_t)lane * pv + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
+            conv_slide<KH_K>(vst + vrow + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
@@ -370,111 +369,226 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
                 const int j = jc0 + k;
-                if (j >= 0 && j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
+                if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
             }
         }
-        const bool form = !(flags & MB_FLAG_RESTART);
-        double* lnew = lbuf + (nl & 1) * (KH_TR * KH_LP);
-        double lown[KH_K];
-        if (form) {
+        if (!(flags & MB_FLAG_RESTART) && row_in) {
+            // DoG row i, diagonals 2..dhi+2 -> L[s][b][i][d-2]; columns past the image hold the maximum filter's cval 0
+            double* lout = g.L + ((size_t)s * g.nblk + b) * g.n * g.wl + (size_t)i * g.wl;
+            double* dst = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF))
+                              ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc : nullptr;
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
-                const int j = jc0 + k;
-                // outside the image the maximum filter sees cval = 0 (mode='constant', mustache.py:741)
-                lown[k] = (row_in && j >= 0 && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-                lnew[lrow + k] = lown[k];
-            }
-            if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && row_in) {
-#pragma unroll
-                for (int k = 0; k < KH_K; ++k) {
-                    const int j = jc0 + k;
-                    if (j >= 0 && j < g.n) g.dbgL[(size_t)i * g.n + j] = lown[k];
+                const int j = jc0 + k, d = j - i;
+                if (d >= 2 && d <= g.dhi + 2) {
+                    const double l = (j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                    if (g.L != nullptr) lout[d - 2] = l;
+                    if (dst != nullptr && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = l;
+                    if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && j < g.n) g.dbgL[(size_t)i * g.n + j] = l;
                 }
             }
-            if ((flags & MB_FLAG_DIFFREF) && g.dout != nullptr && row_scored) {
-                double* dst = g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc;
-#pragma unroll
-                for (int k = 0; k < KH_K; ++k) {
-                    const int c = c0 + k, j = jc0 + k, d = j - i;
-                    if (c >= 1 && c <= KH_SC && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = lown[k];
-                }
-            }
-            if (flags & MB_FLAG_DIFFREF) ++ndiff;
         }
+        if (!(flags & MB_FLAG_RESTART) && (flags & MB_FLAG_DIFFREF)) ++ndiff;
+        __syncthreads();            // every thread is done reading stage s&1 before it is refilled two steps later
+    };
+
+    int s = 0;
+    for (; s + 1 < prog.n_steps; s += 2) {
+        step(s, gB, gA);
+        step(s + 1, gA, gB);
+    }
+    if (s < prog.n_steps) step(s, gB, gA);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_S (ks_kernel): 3x3 maxima, 5-clause extremum test, running best and |L| statistics, streaming the DoG levels from
+// HBM.  grid = (column tiles, row tiles, blocks); tile = 30 x 62 scored pixels + 1-pixel halo; thread (lane = tile row,
+// warp = 8 tile columns) owns 8 pixels for the whole chain and keeps their state in registers (best response, winning
+// level, own value and maxima of the two previous DoGs).  Each level's tile rows arrive by TMA bulk copies into a
+// two-stage ring, prefetched one level ahead.  Everything is exact FP64 comparison; the kernel is HBM/latency bound.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KS_THREADS, 2)
+ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NW = KS_THREADS / 32;
+    constexpr int PL = KS_PITCH;                                // even, == 2 (mod 4)
+    double* lst = smem;                                         // [2][KS_TR][PL]   staged DoG rows
+    double* tpart = lst + 2 * KS_TR * PL;                       // [2][2][KS_THREADS] per-thread (min, sum) of |L| by parity
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(tpart + 4 * KS_THREADS);   // [2]
+
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int is0 = blockIdx.y * KS_SR;                 // first scored row
+    const int i0 = is0 - 1;                             // tile row 0 (halo)
+    const int js = is0 + 4 + blockIdx.x * KS_SC;        // first scored column of this CTA
+    const int ilast = min(is0 + KS_SR, g.n) - 1;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool active = (js < g.n) && (js <= ilast + g.dhi);
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    if (!active) {
+        for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+            g.part_min[o] = kInf;
+            g.part_sum[o] = 0.0;
+        }
+        return;
+    }
+    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+    const int i = i0 + lane;                            // this thread's image row
+    const int c0 = warp * KS_K;                         // first tile column of this thread
+    const int jc0 = js - 1 + c0;                        // image column of its first pixel
+    const bool row_in = (i >= 0) && (i < g.n);
+    const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
+
+    // staged row r: element of tile column t sits at r*PL + 2*((r>>3)&1) + par(r) + t, par(r) = parity of its first
+    // diagonal slot (the bulk copy starts at the even slot below); rows r-1 / r+1 have the opposite parity
+    const int a_first = js - 1 - i - 2;                 // diagonal slot (d-2) of tile column 0 in row i  (may be < 0)
+    const int par = a_first & 1;
+    const int off_c = lane * PL + 2 * ((lane >> 3) & 1) + par + c0;
+    const int off_u = (lane - 1) * PL + 2 * (((lane - 1) >> 3) & 1) + (par ^ 1) + c0;
+    const int off_d = (lane + 1) * PL + 2 * (((lane + 1) >> 3) & 1) + (par ^ 1) + c0;
+
+    // rows outside the image are never copied: they must read as the maximum filter's cval 0
+    for (int e = threadIdx.x; e < 2 * KS_TR * PL; e += KS_THREADS) lst[e] = 0.0;
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 32);
+        mbar_init(&mbar[1], 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zero fill before async-proxy copies
+    __syncthreads();
+
+    // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
+    unsigned mask = 0;
+    if (row_scored) {
 #pragma unroll
-        for (int k = 0; k < KH_K; ++k) gprev[k] = gnew[k];
-        __syncthreads();            // DoG slot complete; also: every thread is done reading stage s&1 and slot (nl-1)&1
-        if (!form) continue;
-        if (!need_max) { ++nl; continue; }
-        // ---- 3x3 maxima of the new DoG for the owned pixels (separable: rows first, then columns) ----
-        double mnew[KH_K];
-        unsigned e_new = 0;
-        if (row_scored) {
-            double vm[KH_K + 2];
-            const double* up = lnew + lrow - KH_LP;
-#pragma unroll
-            for (int t = 0; t < KH_K + 2; ++t) {
-                int c = t - 1;                                          // column relative to the first owned pixel
-                if (warp == 0 && t == 0) c = 0;                         // clamped columns only feed halo pixels
-                if (warp == KH_THREADS / 32 - 1 && t == KH_K + 1) c = KH_K - 1;
-                const double a0 = up[c];
-                const double a1 = (t >= 1 && t <= KH_K) ? lown[t - 1] : up[KH_LP + c];
-                const double a2 = up[2 * KH_LP + c];
-                vm[t] = fmax(fmax(a0, a1), a2);
+        for (int k = 0; k < KS_K; ++k) {
+            const int c = c0 + k, j = jc0 + k, d = j - i;
+            if (c >= 1 && c <= KS_SC && j < g.n && d >= 4 && d <= g.dhi) {
+                if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
             }
-#pragma unroll
-            for (int k = 0; k < KH_K; ++k) {
-                mnew[k] = fmax(fmax(vm[k], vm[k + 1]), vm[k + 2]);
-                if (lown[k] == mnew[k]) e_new |= 1u << k;
-            }
+        }
+    }
+
+    auto issue = [&](int s, int nl) {                           // DoG of step s into stage nl&1 (warp 0, one row per lane)
+        uint64_t* bar = &mbar[nl & 1];
+        if (row_in) {
+            const int a0 = a_first & ~1;
+            const int cnt = ((a_first - a0) + KS_TC + 1) & ~1;
+            const uint32_t bytes = (uint32_t)cnt * 8u;
+            const double* src = g.L + ((size_t)s * g.nblk + b) * g.n * g.wl + (long long)i * g.wl + a0;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_row(lst + (nl & 1) * (KS_TR * PL) + lane * PL + 2 * ((lane >> 3) & 1), src, bytes, bar);
         } else {
-#pragma unroll
-            for (int k = 0; k < KH_K; ++k) mnew[k] = 0.0;
+            mbar_arrive_expect_tx(bar, 0);
         }
-        if (flags & MB_FLAG_SCORE) {
-            const int sidx = prog.st[s].score_idx;
-            double tmin = __longlong_as_double(0x7ff0000000000000LL), tsum = 0.0;
-            const unsigned cand = mask & e_cur & (e_prev | e_new);
+    };
+    auto next_formed = [&](int s) {                             // next step that forms a DoG
+        ++s;
+        while (s < prog.n_steps && (prog.st[s].flags & MB_FLAG_RESTART)) ++s;
+        return s;
+    };
+
+    double vbest[KS_K], lA[KS_K], lB[KS_K], mA[KS_K], mB[KS_K];
+    unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
 #pragma unroll
-            for (int k = 0; k < KH_K; ++k) {
-                if (mask & (1u << k)) {
+    for (int k = 0; k < KS_K; ++k) { vbest[k] = 0.0; lA[k] = lB[k] = mA[k] = mB[k] = 0.0; }
+    unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
+    int pending = -1, pending_par = 0;                  // scored index whose per-thread statistics await reduction
+
+    auto reduce_pending = [&](int sidx, int parity) {  // CTA-wide (min, sum) by one warp, fixed order (deterministic)
+        const double* pm = tpart + (parity * 2 + 0) * KS_THREADS;
+        const double* ps = tpart + (parity * 2 + 1) * KS_THREADS;
+        double mn = kInf, sm = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            mn = fmin(mn, pm[q * 32 + lane]);
+            sm = __dadd_rn(sm, ps[q * 32 + lane]);
+        }
+        mn = warp_min(mn);
+        sm = warp_sum(sm);
+        if (lane == 0) {
+            const size_t o = ((size_t)b * prog.n_scored + sidx) * g.ncta_h + cta;
+            g.part_min[o] = mn;
+            g.part_sum[o] = sm;
+        }
+    };
+
+    // One DoG level.  Register arrays alternate roles between consecutive levels (the loop is unrolled by two): lcur / mcur
+    // belong to the previous level, mold to the one before and is overwritten with this level's maxima.
+    auto level = [&](const int s, const int nl, const int s_next, const double (&lcur)[KS_K], double (&lown)[KS_K],
+                     double (&mold)[KS_K], const double (&mcur)[KS_K]) {
+        (void)mcur;
+        const int flags = prog.st[s].flags;
+        if (warp == 0 && s_next < prog.n_steps) issue(s_next, nl + 1);   // stage (nl+1)&1 is free since the last barrier
+        mbar_wait(&mbar[nl & 1], (nl >> 1) & 1);
+        const double* st = lst + (nl & 1) * (KS_TR * PL);
+        // statistics of the previous scored level: one warp folds the partials (round-robin over warps)
+        if (pending >= 0 && warp == (nl % NW)) reduce_pending(pending, pending_par);
+        pending = -1;
+        unsigned e_new = 0;
+        double tmin = kInf, tsum = 0.0;
+        const bool score = (flags & MB_FLAG_SCORE) != 0;
+        const int sidx = prog.st[s].score_idx;
+        if (row_scored) {
+            double vm[KS_K + 2];
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) lown[k] = st[off_c + k];
+#pragma unroll
+            for (int t = 0; t < KS_K + 2; ++t) {
+                int c = t - 1;                                          // column relative to the first owned pixel
+                if (t == 0 && warp == 0) c = 0;                         // clamped columns only feed halo pixels
+                if (t == KS_K + 1 && warp == NW - 1) c = KS_K - 1;
+                const double a1 = (t >= 1 && t <= KS_K) ? lown[t - 1] : st[off_c + c];
+                vm[t] = fmax(fmax(st[off_u + c], a1), st[off_d + c]);
+            }
+            const unsigned cand = score ? (mask & e_cur) : 0u;
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) {
+                const unsigned bit = 1u << k;
+                const double mnew = fmax(fmax(vm[k], vm[k + 1]), vm[k + 2]);
+                const bool en = (lown[k] == mnew);
+                if (en) e_new |= bit;
+                if (score && (mask & bit)) {
                     const double a = fabs(lcur[k]);
                     tmin = fmin(tmin, a);
                     tsum = __dadd_rn(tsum, a);
                 }
-                if ((cand & (1u << k)) && lcur[k] > vbest[k] && lcur[k] > mprev[k] && lcur[k] > mnew[k]) {
+                // mustache.py:760-765
+                if ((cand & bit) && (en || (e_prev & bit)) && lcur[k] > vbest[k] && lcur[k] > mold[k] && lcur[k] > mnew) {
                     vbest[k] = lcur[k];
                     lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
                 }
-            }
-            tmin = warp_min(tmin);
-            tsum = warp_sum(tsum);
-            if (lane == 0) {
-                pmin[sidx * (KH_THREADS / 32) + warp] = tmin;
-                psum[sidx * (KH_THREADS / 32) + warp] = tsum;
+                mold[k] = mnew;
             }
         }
-#pragma unroll
-        for (int k = 0; k < KH_K; ++k) { mprev[k] = mcur[k]; mcur[k] = mnew[k]; lcur[k] = lown[k]; }
+        if (score) {
+            tpart[((nl & 1) * 2 + 0) * KS_THREADS + threadIdx.x] = tmin;
+            tpart[((nl & 1) * 2 + 1) * KS_THREADS + threadIdx.x] = tsum;
+            pending = sidx;
+            pending_par = nl & 1;
+        }
         e_prev = e_cur;
         e_cur = e_new;
-        ++nl;
+        __syncthreads();            // stage nl&1 and the statistics partials of this level are complete / released
+    };
+
+    int s = next_formed(-1), nl = 0;
+    if (s < prog.n_steps && warp == 0) issue(s, 0);
+    while (s < prog.n_steps) {
+        int sn = next_formed(s);
+        level(s, nl, sn, lB, lA, mA, mB);       // even level: own values into lA, maxima into mA (held level nl-2)
+        s = sn; ++nl;
+        if (s >= prog.n_steps) break;
+        sn = next_formed(s);
+        level(s, nl, sn, lA, lB, mB, mA);
+        s = sn; ++nl;
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < prog.n_scored; t += KH_THREADS) {
-        double mn = pmin[t * (KH_THREADS / 32)], sm = psum[t * (KH_THREADS / 32)];
-        for (int w = 1; w < KH_THREADS / 32; ++w) {
-            mn = fmin(mn, pmin[t * (KH_THREADS / 32) + w]);
-            sm = __dadd_rn(sm, psum[t * (KH_THREADS / 32) + w]);
-        }
-        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
-        g.part_min[o] = mn;
-        g.part_sum[o] = sm;
-    }
+    if (pending >= 0 && warp == 0) reduce_pending(pending, pending_par);
     // ---- emit the pixels that were ever updated (pAll != 2, mustache.py:774) ----
     if (lvl != 0) {
 #pragma unroll
-        for (int k = 0; k < KH_K; ++k) {
+        for (int k = 0; k < KS_K; ++k) {
             const int id = (int)((lvl >> (8 * k)) & 0xff);
             if (id) {
                 const unsigned long long slot = atomicAdd(g.rec_count + b, 1ULL);

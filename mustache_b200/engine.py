@@ -37,7 +37,7 @@ SIGNATURES = {
     "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
     "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
     "mb200_fetch_fits": (C.c_int, [_H, C.c_int, _f64p, _f64p, _i32p, C.c_int, C.POINTER(C.c_int)]),
-    "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p]),
+    "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
     "mb200_last_launches": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "mb200_debug_level": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mb200_set_diff_program": (C.c_int, [_H, C.c_int, _i32p, _i32p, _i32p, _f64p, C.c_int]),
@@ -63,7 +63,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MUSTACHE_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError("CUDA library %s not built (run `python -m mustache_b200.build`); there is no CPU fallback" % p)
     lib = C.CDLL(p)
@@ -129,8 +129,8 @@ class ScaleSpaceEngine:
         eng.upload_coo(b, rows, cols, vals) ...; eng.run(); rec = eng.records(b)
     """
 
-    def __init__(self, device=0):
-        self.lib = load_library()
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load_library(lib_path)
         cnt = C.c_int(0)
         self.lib.mb200_device_count(C.byref(cnt))
         if cnt.value < 1:
@@ -252,9 +252,9 @@ class ScaleSpaceEngine:
         return dict(loc=loc, scale=sc, score_id=sid)
 
     def timing(self):
-        f = [C.c_float(0) for _ in range(5)]
+        f = [C.c_float(0) for _ in range(6)]
         self._chk(self.lib.mb200_last_timing(self.h, *[C.byref(x) for x in f]))
-        return dict(zip(("prep_ms", "kv_ms", "kh_ms", "fin_ms", "total_ms"), [x.value for x in f]))
+        return dict(zip(("prep_ms", "kv_ms", "kh_ms", "ks_ms", "fin_ms", "total_ms"), [x.value for x in f]))
 
     def launches(self):
         n = C.c_int(0)

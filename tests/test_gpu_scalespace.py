@@ -158,3 +158,4 @@ def test_error_codes(eng):
     with pytest.raises(EngineError) as ei:
         eng.records(0)
     assert ei.value.code == -4
+

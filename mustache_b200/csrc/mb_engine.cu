@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -42,6 +43,10 @@ struct mb200_engine {
     float t_prep = 0, t_kv = 0, t_kh = 0, t_ks = 0, t_fin = 0, t_total = 0;
     int launches = 0;
     size_t kv_smem_set = 0, kh_smem_set = 0, ks_smem_set = 0;
+    MbTensorMaps tmaps;              // main chain (host copy)
+    MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
+    DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
+    long long plane_v = 0, plane_l = 0;
 };
 
 namespace {
@@ -91,11 +96,54 @@ int use_device(mb200_engine* e) {
 constexpr size_t V_GUARD_BYTES = 64 * 1024;   // slack on both sides of the axis-0 scratch for 16-byte-aligned row copies
 
 size_t v_bytes_per_block(const mb200_engine* e) {
-    return (size_t)e->prog.n_steps * e->n * e->wv * sizeof(double);
+    return (size_t)e->prog.n_steps * e->plane_v * sizeof(double);
 }
 
 size_t l_bytes_per_block(const mb200_engine* e) {
-    return (size_t)e->prog.n_steps * e->n * e->wl * sizeof(double);
+    return (size_t)e->prog.n_steps * e->plane_l * sizeof(double);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Skewed 3-D view of a band-layout scratch array (see MbTensorMaps): x = column index, y = image row, z = plane.
+int encode_skewed(mb200_engine* e, CUtensorMap* map, void* base, int row_len, long long plane, int planes, int box_w) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return fail(e, MB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)(e->n + row_len), (cuuint64_t)e->n, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)(row_len - 1) * sizeof(double), (cuuint64_t)plane * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)KH_TR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(e, MB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) row_len=%d box=%d", (int)r, row_len, box_w);
+    return MB200_OK;
+}
+
+int encode_maps(mb200_engine* e, const MbProgram& pg, MbTensorMaps& tm, bool with_l) {
+    void* vbase = (char*)e->V.p + V_GUARD_BYTES;
+    void* lbase = (char*)e->Lb.p + V_GUARD_BYTES;
+    const int planes_v = e->prog.n_steps * e->pass_blocks;       // capacity of the scratch arrays
+    memset(&tm, 0, sizeof(tm));
+    for (int s = 0; s < pg.n_steps; ++s) {
+        int st = encode_skewed(e, &tm.v[s], vbase, e->wv, e->plane_v, planes_v, kh_box_width(pg.st[s].radius));
+        if (st) return st;
+    }
+    if (with_l) return encode_skewed(e, &tm.l, lbase, e->wl, e->plane_l, planes_v, KS_PITCH);
+    return MB200_OK;
 }
 
 MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
@@ -116,7 +164,10 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.V = (double*)((char*)e->V.p + V_GUARD_BYTES);     // bulk copies may start a few elements before a row
     g.L = (double*)((char*)e->Lb.p + V_GUARD_BYTES);
     g.wl = e->wl;
-    g.pad0 = 0;
+    g.kh_depth = kh_depth_for(e->prog.rmax);
+    g.dbg_flags = getenv("MB200_DBG") ? atoi(getenv("MB200_DBG")) : 0;
+    g.plane_v = e->plane_v;
+    g.plane_l = e->plane_l;
     g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
     g.part_sum = (double*)e->part_sum.p + (size_t)first_block * ns * e->ncta_h;
     g.rec_count = (unsigned long long*)e->rec_count.p + first_block;
@@ -158,9 +209,10 @@ int set_smem_limits(mb200_engine* e) {
         CU(e, cudaFuncSetAttribute(kh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
         e->kh_smem_set = khb;
     }
-    if (ks_smem_bytes() != e->ks_smem_set) {
-        CU(e, cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem_bytes()));
-        e->ks_smem_set = ks_smem_bytes();
+    const size_t ksb = ks_smem_bytes(e->prog.n_scored);
+    if (ksb != e->ks_smem_set) {
+        CU(e, cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksb));
+        e->ks_smem_set = ksb;
     }
     return MB200_OK;
 }
@@ -169,16 +221,18 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
                 const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
     const MbProgram& pg = program ? *program : e->prog;
+    g.kh_depth = kh_depth_for(pg.rmax);
     const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
+    const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
     kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(pg, g);
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
-    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, g);
+    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
     CU(e, cudaGetLastError());
     if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
     e->launches += 2;
-    if (pg.n_scored > 0) {
-        ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(), e->stream>>>(pg, g);
+    if (pg.n_scored > 0 && !(g.dbg_flags & 4)) {
+        ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(pg.n_scored), e->stream>>>(pg, tm, g);
         CU(e, cudaGetLastError());
         e->launches += 1;
     }
@@ -247,7 +301,7 @@ void mb200_destroy(mb200_engine* e) {
     DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
-                     &e->d_score_id};
+                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -313,6 +367,7 @@ int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, 
     }
     if (nd < 1) return fail(e, MB200_ERR_ARG, "the difference chain needs at least one MB200_STEP_DIFFREF step");
     e->have_dprog = true;
+    e->configured = false;          // the TMA descriptors of the difference chain are built by mb200_configure
     return MB200_OK;
 }
 
@@ -331,11 +386,14 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if (e->dhi < 4) return fail(e, MB200_ERR_ARG, "no diagonal >= 4 in the tile");
     e->wc = e->dhi - 3;
     e->vlo = 2 - e->prog.rmax;
-    e->wv = (e->dhi + 2 * e->prog.rmax + 1 + 1) & ~1;   // even: rows of the axis-0 scratch stay 16-byte aligned
+    // odd row lengths: the skewed TMA view has row stride (len-1)*8 bytes, which must be a multiple of 16
+    e->wv = (e->dhi + 2 * e->prog.rmax + 1) | 1;
     e->nblocks = nblocks;
     const double frac = record_fraction > 0 ? record_fraction : 0.125;
     e->rec_cap = std::max<long long>(4096, (long long)(frac * (double)n * e->wc));
-    e->wl = (e->dhi + 1 + 1) & ~1;                       // diagonals 2..dhi+2, even row length
+    e->wl = (e->dhi + 1) | 1;                            // diagonals 2..dhi+2, odd row length (skewed TMA view)
+    e->plane_v = ((long long)n * e->wv + 1) & ~1LL;      // plane strides: multiples of 16 bytes
+    e->plane_l = ((long long)n * e->wl + 1) & ~1LL;
     dim3 gh = ks_grid(e, 1);
     e->ncta_h = gh.x * gh.y;
     if ((st = set_smem_limits(e))) return st;
@@ -365,6 +423,15 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if ((st = ensure(e, e->V, (size_t)e->pass_blocks * v_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     if ((st = ensure(e, e->Lb, (size_t)e->pass_blocks * l_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     CU(e, cudaMemsetAsync(e->raw.p, 0, B * n * e->wc * sizeof(double), e->stream));
+    if ((st = encode_maps(e, e->prog, e->tmaps, true))) return st;
+    if ((st = ensure(e, e->d_tmaps, sizeof(MbTensorMaps)))) return st;
+    CU(e, cudaMemcpyAsync(e->d_tmaps.p, &e->tmaps, sizeof(MbTensorMaps), cudaMemcpyHostToDevice, e->stream));
+    if (e->have_dprog && e->dprog.rmax <= e->prog.rmax) {
+        if ((st = encode_maps(e, e->dprog, e->dtmaps, false))) return st;
+        if ((st = ensure(e, e->d_dtmaps, sizeof(MbTensorMaps)))) return st;
+        CU(e, cudaMemcpyAsync(e->d_dtmaps.p, &e->dtmaps, sizeof(MbTensorMaps), cudaMemcpyHostToDevice, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));      // the host copies may be re-encoded by the next configure
     e->configured = true;
     e->ran = false;
     e->counts_valid = false;
@@ -674,6 +741,13 @@ int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair,
     if (!pair) return fail(e, MB200_ERR_ARG, "null output array");
     CU(e, cudaMemcpyAsync(pair, (double*)e->rec_pair.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+// development aid: raw bytes of a TMA descriptor (which < 0: the L map, else the V map of that step)
+MB200_API int mb200_debug_tensormap(mb200_engine* e, int which, void* out128) {
+    if (!e || !out128) return MB200_ERR_ARG;
+    memcpy(out128, which < 0 ? (void*)&e->tmaps.l : (void*)&e->tmaps.v[which], 128);
     return MB200_OK;
 }
 

@@ -20,6 +20,7 @@
 // element per tap, so a tap costs 2 shared-memory loads + 1 constant load for 24 FP64 instructions.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #define MB_MAX_STEPS 64
@@ -45,6 +46,19 @@ struct MbProgram {
     double taps[MB_MAX_TAPS];
 };
 
+// TMA descriptors (cuTensorMapEncodeTiled, built by the host per batch geometry).  Both scratch arrays are addressed
+// through a skewed 3-D view (x = column index, y = image row, z = step * nblk + block) whose row stride is one element
+// shorter than the band row, so that a rectangular box of the view is a rectangular (i, j) tile of the image:
+//   V: element (i, j) sits at  plane + i*wv + (j - i - vlo) = plane + i*(wv-1) + (j - vlo)   ->  x = j - vlo
+//   L: element (i, j) sits at  plane + i*wl + (j - i - 2)   = plane + i*(wl-1) + (j - 2)     ->  x = j - 2
+// Rows outside the image are out of bounds in y and arrive as zeros.  One descriptor per step for V (the box is as
+// wide as that step's filter support), one for L.  The descriptors live in global memory (64-byte aligned) and are
+// written by the host only.
+struct MbTensorMaps {
+    CUtensorMap v[MB_MAX_STEPS];
+    CUtensorMap l;
+};
+
 struct MbGeom {
     int n;        // tile side
     int dpx;      // distance_in_px
@@ -61,7 +75,10 @@ struct MbGeom {
     double* V;                      // [n_steps][nblk][n][wv]
     double* L;                      // [n_steps][nblk][n][wl]  DoG formed at each step, diagonals 2..dhi+2 (nullptr: not stored)
     int wl;                         // diagonals per row of L (even)
-    int pad0;
+    int kh_depth;                   // stages of kh_kernel's staging ring
+    int dbg_flags;                  // development switches (0 in production)
+    long long plane_v;              // elements between consecutive (step, block) planes of V (>= n*wv, even)
+    long long plane_l;              // same for L
     double* part_min;               // [nblk][n_scored][ncta_h]
     double* part_sum;               // [nblk][n_scored][ncta_h]
     unsigned long long* rec_count;  // [nblk]
@@ -94,22 +111,32 @@ constexpr int KS_K = 8;
 constexpr int KS_THREADS = (KS_TC / KS_K) * 32;   // 256
 constexpr int KS_SR = KS_TR - 2;   // scored rows per CTA
 constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
-constexpr int KS_PITCH = KS_TC + 6;   // 70: even and == 2 (mod 4); room for the parity shift, the even tail, the bank stagger
+constexpr int KS_PITCH = KS_TC + 2;   // 66: box width of the staged DoG tile, == 2 (mod 4)
+constexpr int KS_DEPTH = 4;           // levels in flight per CTA
 
-// even pitch (16-byte aligned rows for the bulk copies) with room for the parity shift, the even-rounded tail and the
-// 2-element bank stagger; forced to 2 (mod 4) so that lanes (= rows) spread over all banks (see kh_kernel)
-__host__ __device__ inline int kh_vbuf_pitch(int rmax) {
-    const int p = KH_TC + 2 * rmax + 6;
+// width of the staged box of a step with radius R: the filter support of the tile plus one element (the box must start
+// on an even column: TMA needs 16-byte aligned box rows), padded to 2 (mod 4) elements so that the dense rows the TMA
+// writes put the 32 lanes (= rows) on 8 different 8-byte bank pairs (2-way conflicts)
+__host__ __device__ inline int kh_box_width(int R) {
+    const int p = KH_TC + 2 * R + 2;
     return (p % 4 == 2) ? p : p + 2;
+}
+__host__ __device__ inline int kh_vbuf_pitch(int rmax) { return kh_box_width(rmax); }
+// ring depth of kh_kernel: as many stages (2..4) as fit in half an SM's shared memory (two CTAs per SM)
+__host__ __device__ inline int kh_depth_for(int rmax) {
+    const size_t stage = (size_t)KH_TR * kh_vbuf_pitch(rmax) * sizeof(double);
+    int d = (int)((112 * 1024 - 64) / stage);
+    return d < 2 ? 2 : (d > 4 ? 4 : d);
 }
 __host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
     (void)n_scored;
-    return (2 * (size_t)KH_TR * kh_vbuf_pitch(rmax) + 2) * sizeof(double);          // vbuf[2] + 2 mbarriers
+    return ((size_t)kh_depth_for(rmax) * KH_TR * kh_vbuf_pitch(rmax) + 8) * sizeof(double);   // stages + 2 x 4 mbarriers
 }
 
-__host__ __device__ inline size_t ks_smem_bytes() {
-    return (2 * (size_t)KS_TR * KS_PITCH + 4 * (size_t)KS_THREADS + 2) * sizeof(double);   // rows[2] + statistics + mbarriers
+__host__ __device__ inline size_t ks_smem_bytes(int n_scored) {
+    return ((size_t)KS_DEPTH * KS_TR * KS_PITCH + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KS_THREADS / 32) + 2 * KS_DEPTH)
+           * sizeof(double);                                                       // stages + per-warp statistics + mbarriers
 }
 
 // scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
@@ -218,7 +245,7 @@ kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
         if (dmax < lo || dmin > hi) continue;           // warp-uniform
         double acc[KV_K];
         conv_slide<KV_K>(ctr, KV_TW, R, prog.taps + prog.st[s].tap_off, acc);
-        double* vout = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
+        double* vout = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
 #pragma unroll
         for (int k = 0; k < KV_K; ++k) {
             const int i = i0 + rb + k;
@@ -253,6 +280,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -277,14 +307,32 @@ __device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_
 // previous Gaussian of its pixels stays in registers, so L_s = G_{s-1} - G_s costs one subtraction.  No halo: the tiles
 // partition the band, the scoring kernel reads its own halo.  Two CTAs per SM.
 // ---------------------------------------------------------------------------------------------------------------
+// one lane of a converged warp (elect.sync): keeps the TMA operands provably uniform for the compiler
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
+// TMA tiled copy global -> shared of one box of a 3-D tensor map (SASS: UTMALDG), completion in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_box3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(KH_THREADS, 2)
-kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
-    extern __shared__ __align__(16) double smem[];
+kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
+    extern __shared__ __align__(128) double smem[];
     constexpr int NW = KH_THREADS / 32;
     const int rmax = prog.rmax;
-    const int pv = kh_vbuf_pitch(rmax);                         // even, == 2 (mod 4)
-    double* vbuf = smem;                                        // [2][KH_TR][pv]   staged axis-0 rows (TMA destination)
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(vbuf + 2 * (size_t)KH_TR * pv);   // [2]
+    const int pv = kh_vbuf_pitch(rmax);                         // stage size: the widest box of the chain
+    const int D = g.kh_depth;                                   // ring depth (2..4 stages, as shared memory allows)
+    double* vbuf = smem;                                        // [D][KH_TR][box width of the step]   TMA destination
+    uint64_t* full = reinterpret_cast<uint64_t*>(vbuf + (size_t)D * KH_TR * pv);   // [D] bytes landed
+    uint64_t* empty = full + 4;                                 // [D] every warp is done reading the stage
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,35 +346,33 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     const bool row_in = i < g.n;
     // tiles whose +/- rmax column halo leaves the image need 'reflect' indexing: generic (slow) staging for those
     const bool border = (js - rmax < 0) || (js + KH_TC + rmax > g.n);
-    // staged row r starts at r*pv + 2*((r>>3)&1): with pv == 2 (mod 4) and the alternating parity shift of the bulk
-    // copies this makes the 16 rows of a half-warp hit 16 different 8-byte banks
-    const int vrow = lane * pv + 2 * ((lane >> 3) & 1);
 
     if (threadIdx.x == 0) {
-        mbar_init(&mbar[0], 32);
-        mbar_init(&mbar[1], 32);
+        for (int d = 0; d < D; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], NW);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // any pixel of this warp's 32 x 8 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n);
 
-    auto issue = [&](int s) {                                   // bulk copies of step s into stage s&1 (warp 0)
+    // Producer side (one thread): one TMA box copy per step -- the 32 x (TC + 2R) axis-0 tile of step s into stage s % D,
+    // after every warp released the stage's previous contents (step s - D).
+    auto issue = [&](int s) {
+        const int u = s / D, st = s - u * D;
+        if (u > 0) mbar_wait(&empty[st], (u - 1) & 1);
         const int R = prog.st[s].radius;
-        uint64_t* bar = &mbar[s & 1];
-        if (row_in) {
-            const int a = js - R - i - g.vlo;                   // first needed diagonal slot of this row (may be < 0)
-            const int a0 = a & ~1;                              // floor to even: 16-byte aligned source
-            const int cnt = ((a - a0) + KH_TC + 2 * R + 1) & ~1;
-            const uint32_t bytes = (uint32_t)cnt * 8u;
-            const double* src = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv + (long long)i * g.wv + a0;
-            mbar_arrive_expect_tx(bar, bytes);
-            tma_load_row(vbuf + (s & 1) * (KH_TR * pv) + vrow, src, bytes, bar);
-        } else {
-            mbar_arrive_expect_tx(bar, 0);
-        }
+        const uint32_t bytes = (uint32_t)(KH_TR * kh_box_width(R)) * 8u;
+        mbar_arrive_expect_tx(&full[st], bytes);
+        // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned box rows)
+        tma_load_box3d(vbuf + st * (KH_TR * pv), &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[st]);
     };
-    if (!border && warp == 0) issue(0);
+#ifndef MB_DBG_NOTMA
+    if (!border && warp == 0 && elect_one())
+        for (int s = 0; s < D - 1 && s < prog.n_steps; ++s) issue(s);
+#endif
 
     double gA[KH_K], gB[KH_K];
 #pragma unroll
@@ -336,17 +382,21 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     auto step = [&](const int s, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
         const int R = prog.st[s].radius;
         const int flags = prog.st[s].flags;
-        double* vst = vbuf + (s & 1) * (KH_TR * pv);
-        const int shift = (js - R - i - g.vlo) & 1;              // element offset of this row inside its staged copy
+        const int u = s / D, st = s - u * D;
+        double* vst = vbuf + (border ? 0 : st) * (KH_TR * pv);
+        const int bw = kh_box_width(R);                          // row pitch of this step's staged box
+        const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-            if (warp == 0 && s + 1 < prog.n_steps) issue(s + 1); // stage (s+1)&1 is free since the barrier of step s-1
-            mbar_wait(&mbar[s & 1], (s >> 1) & 1);
+#ifndef MB_DBG_NOTMA
+            if (warp == 0 && s + D - 1 < prog.n_steps && !(g.dbg_flags & 1) && elect_one()) issue(s + D - 1);
+            mbar_wait(&full[st], u & 1);
+#endif
         } else {
-            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.n * g.wv;
+            __syncthreads();                                     // previous step's readers are done with stage 0
+            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
             const int wlen = KH_TC + 2 * R;
             for (int r = warp; r < KH_TR; r += NW) {
                 const int ii = i0 + r;
-                const int sh = ((js - R - ii - g.vlo) & 1) + 2 * ((r >> 3) & 1);
                 for (int t = lane; t < wlen; t += 32) {
                     double val = 0.0;
                     if (ii < g.n) {
@@ -354,16 +404,24 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
                         const int dd = jj - ii - g.vlo;
                         if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
                     }
-                    vst[r * pv + sh + t] = val;
+                    vst[r * bw + t] = val;
                 }
             }
             __syncthreads();
         }
+#ifdef MB_DBG_NOCONV
+        if (false) {
+#else
         if (chunk_live && row_in) {
-            conv_slide<KH_K>(vst + vrow + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
+#endif
+            conv_slide<KH_K>(vst + lane * bw + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
+        }
+        if (!border) {                                           // release the stage: one arrival per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
         }
         if (g.dbgG != nullptr && s == g.dbg_step && b == 0 && row_in) {
 #pragma unroll
@@ -372,9 +430,13 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
                 if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
             }
         }
-        if (!(flags & MB_FLAG_RESTART) && row_in) {
+#ifndef MB_DBG_NOSTORE
+        if (!(flags & MB_FLAG_RESTART) && row_in && chunk_live) {
+#else
+        if (false) {
+#endif
             // DoG row i, diagonals 2..dhi+2 -> L[s][b][i][d-2]; columns past the image hold the maximum filter's cval 0
-            double* lout = g.L + ((size_t)s * g.nblk + b) * g.n * g.wl + (size_t)i * g.wl;
+            double* lout = g.L + ((size_t)s * g.nblk + b) * g.plane_l + (size_t)i * g.wl;
             double* dst = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF))
                               ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc : nullptr;
 #pragma unroll
@@ -389,15 +451,15 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
             }
         }
         if (!(flags & MB_FLAG_RESTART) && (flags & MB_FLAG_DIFFREF)) ++ndiff;
-        __syncthreads();            // every thread is done reading stage s&1 before it is refilled two steps later
     };
 
     int s = 0;
-    for (; s + 1 < prog.n_steps; s += 2) {
+    const int nst = (g.dbg_flags & 1) ? min(prog.n_steps, D - 1) : prog.n_steps;
+    for (; s + 1 < nst; s += 2) {
         step(s, gB, gA);
         step(s + 1, gA, gB);
     }
-    if (s < prog.n_steps) step(s, gB, gA);
+    if (s < nst) step(s, gB, gA);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -408,13 +470,16 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
 // two-stage ring, prefetched one level ahead.  Everything is exact FP64 comparison; the kernel is HBM/latency bound.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KS_THREADS, 2)
-ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
-    extern __shared__ __align__(16) double smem[];
+ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
+    extern __shared__ __align__(128) double smem[];
     constexpr int NW = KS_THREADS / 32;
     constexpr int PL = KS_PITCH;                                // even, == 2 (mod 4)
-    double* lst = smem;                                         // [2][KS_TR][PL]   staged DoG rows
-    double* tpart = lst + 2 * KS_TR * PL;                       // [2][2][KS_THREADS] per-thread (min, sum) of |L| by parity
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(tpart + 4 * KS_THREADS);   // [2]
+    constexpr int D = KS_DEPTH;
+    double* lst = smem;                                         // [D][KS_TR][PL]   staged DoG rows
+    double* pmin = lst + D * KS_TR * PL;                        // [n_scored][NW] per-warp min of |L|
+    double* psum = pmin + (size_t)max(prog.n_scored, 1) * NW;   // [n_scored][NW] per-warp sum of |L|
+    uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * NW);   // [D]
+    uint64_t* empty = full + D;                                 // [D]
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -440,22 +505,20 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     const bool row_in = (i >= 0) && (i < g.n);
     const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
 
-    // staged row r: element of tile column t sits at r*PL + 2*((r>>3)&1) + par(r) + t, par(r) = parity of its first
-    // diagonal slot (the bulk copy starts at the even slot below); rows r-1 / r+1 have the opposite parity
-    const int a_first = js - 1 - i - 2;                 // diagonal slot (d-2) of tile column 0 in row i  (may be < 0)
-    const int par = a_first & 1;
-    const int off_c = lane * PL + 2 * ((lane >> 3) & 1) + par + c0;
-    const int off_u = (lane - 1) * PL + 2 * (((lane - 1) >> 3) & 1) + (par ^ 1) + c0;
-    const int off_d = (lane + 1) * PL + 2 * (((lane + 1) >> 3) & 1) + (par ^ 1) + c0;
+    // the staged tile is a dense [KS_TR][PL] box; rows outside the image are out of bounds for the TMA and arrive as the
+    // maximum filter's cval 0
+    const int x_first = js - 1 - 2;                     // column index (skewed view of L) of tile column 0
+    const int off_c = lane * PL + (x_first & 1) + c0;   // the box starts on the even column below
+    const int off_u = off_c - PL;
+    const int off_d = off_c + PL;
 
-    // rows outside the image are never copied: they must read as the maximum filter's cval 0
-    for (int e = threadIdx.x; e < 2 * KS_TR * PL; e += KS_THREADS) lst[e] = 0.0;
     if (threadIdx.x == 0) {
-        mbar_init(&mbar[0], 32);
-        mbar_init(&mbar[1], 32);
+        for (int d = 0; d < D; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], NW);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy zero fill before async-proxy copies
     __syncthreads();
 
     // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
@@ -470,18 +533,12 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
         }
     }
 
-    auto issue = [&](int s, int nl) {                           // DoG of step s into stage nl&1 (warp 0, one row per lane)
-        uint64_t* bar = &mbar[nl & 1];
-        if (row_in) {
-            const int a0 = a_first & ~1;
-            const int cnt = ((a_first - a0) + KS_TC + 1) & ~1;
-            const uint32_t bytes = (uint32_t)cnt * 8u;
-            const double* src = g.L + ((size_t)s * g.nblk + b) * g.n * g.wl + (long long)i * g.wl + a0;
-            mbar_arrive_expect_tx(bar, bytes);
-            tma_load_row(lst + (nl & 1) * (KS_TR * PL) + lane * PL + 2 * ((lane >> 3) & 1), src, bytes, bar);
-        } else {
-            mbar_arrive_expect_tx(bar, 0);
-        }
+    // Producer side (one thread): the DoG tile of step s, the nl-th level of the stream, into stage nl % D
+    auto issue = [&](int s, int nl) {
+        const int u = nl / D, st = nl - u * D;
+        if (u > 0) mbar_wait(&empty[st], (u - 1) & 1);
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
+        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, s * g.nblk + b, &full[st]);
     };
     auto next_formed = [&](int s) {                             // next step that forms a DoG
         ++s;
@@ -494,38 +551,20 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
 #pragma unroll
     for (int k = 0; k < KS_K; ++k) { vbest[k] = 0.0; lA[k] = lB[k] = mA[k] = mB[k] = 0.0; }
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
-    int pending = -1, pending_par = 0;                  // scored index whose per-thread statistics await reduction
+    int s_issue = next_formed(-1), nl_issue = 0;        // producer cursor (warp 0, uniform)
 
-    auto reduce_pending = [&](int sidx, int parity) {  // CTA-wide (min, sum) by one warp, fixed order (deterministic)
-        const double* pm = tpart + (parity * 2 + 0) * KS_THREADS;
-        const double* ps = tpart + (parity * 2 + 1) * KS_THREADS;
-        double mn = kInf, sm = 0.0;
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            mn = fmin(mn, pm[q * 32 + lane]);
-            sm = __dadd_rn(sm, ps[q * 32 + lane]);
-        }
-        mn = warp_min(mn);
-        sm = warp_sum(sm);
-        if (lane == 0) {
-            const size_t o = ((size_t)b * prog.n_scored + sidx) * g.ncta_h + cta;
-            g.part_min[o] = mn;
-            g.part_sum[o] = sm;
-        }
-    };
-
-    // One DoG level.  Register arrays alternate roles between consecutive levels (the loop is unrolled by two): lcur / mcur
-    // belong to the previous level, mold to the one before and is overwritten with this level's maxima.
-    auto level = [&](const int s, const int nl, const int s_next, const double (&lcur)[KS_K], double (&lown)[KS_K],
-                     double (&mold)[KS_K], const double (&mcur)[KS_K]) {
-        (void)mcur;
+    // One DoG level.  Register arrays alternate roles between consecutive levels (the loop is unrolled by two): lcur belongs
+    // to the previous level, mold holds the maxima of the level before that and is overwritten with this level's.
+    auto level = [&](const int s, const int nl, const double (&lcur)[KS_K], double (&lown)[KS_K], double (&mold)[KS_K]) {
         const int flags = prog.st[s].flags;
-        if (warp == 0 && s_next < prog.n_steps) issue(s_next, nl + 1);   // stage (nl+1)&1 is free since the last barrier
-        mbar_wait(&mbar[nl & 1], (nl >> 1) & 1);
-        const double* st = lst + (nl & 1) * (KS_TR * PL);
-        // statistics of the previous scored level: one warp folds the partials (round-robin over warps)
-        if (pending >= 0 && warp == (nl % NW)) reduce_pending(pending, pending_par);
-        pending = -1;
+        if (warp == 0 && s_issue < prog.n_steps) {              // keep D-1 levels in flight; the cursor stays warp-uniform
+            if (elect_one()) issue(s_issue, nl_issue);
+            s_issue = next_formed(s_issue);
+            ++nl_issue;
+        }
+        const int u = nl / D, st_i = nl - u * D;
+        mbar_wait(&full[st_i], u & 1);
+        const double* st = lst + st_i * (KS_TR * PL);
         unsigned e_new = 0;
         double tmin = kInf, tsum = 0.0;
         const bool score = (flags & MB_FLAG_SCORE) != 0;
@@ -562,29 +601,46 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
                 mold[k] = mnew;
             }
         }
-        if (score) {
-            tpart[((nl & 1) * 2 + 0) * KS_THREADS + threadIdx.x] = tmin;
-            tpart[((nl & 1) * 2 + 1) * KS_THREADS + threadIdx.x] = tsum;
-            pending = sidx;
-            pending_par = nl & 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st_i]);               // this warp is done with the stage
+        if (score) {                                            // per-warp statistics, fixed order (deterministic)
+            tmin = warp_min(tmin);
+            tsum = warp_sum(tsum);
+            if (lane == 0) {
+                pmin[sidx * NW + warp] = tmin;
+                psum[sidx * NW + warp] = tsum;
+            }
         }
         e_prev = e_cur;
         e_cur = e_new;
-        __syncthreads();            // stage nl&1 and the statistics partials of this level are complete / released
     };
 
-    int s = next_formed(-1), nl = 0;
-    if (s < prog.n_steps && warp == 0) issue(s, 0);
-    while (s < prog.n_steps) {
-        int sn = next_formed(s);
-        level(s, nl, sn, lB, lA, mA, mB);       // even level: own values into lA, maxima into mA (held level nl-2)
-        s = sn; ++nl;
-        if (s >= prog.n_steps) break;
-        sn = next_formed(s);
-        level(s, nl, sn, lA, lB, mB, mA);
-        s = sn; ++nl;
+    if (warp == 0) {                                            // prologue: D-1 levels in flight before the first wait
+        for (int q = 0; q < D - 1 && s_issue < prog.n_steps; ++q) {
+            if (elect_one()) issue(s_issue, nl_issue);
+            s_issue = next_formed(s_issue);
+            ++nl_issue;
+        }
     }
-    if (pending >= 0 && warp == 0) reduce_pending(pending, pending_par);
+    int s = next_formed(-1), nl = 0;
+    while (s < prog.n_steps) {
+        level(s, nl, lB, lA, mA);               // even level: own values into lA, maxima into mA (held level nl-2)
+        s = next_formed(s); ++nl;
+        if (s >= prog.n_steps) break;
+        level(s, nl, lA, lB, mB);
+        s = next_formed(s); ++nl;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+        double mn = pmin[t * NW], sm = psum[t * NW];
+        for (int w = 1; w < NW; ++w) {
+            mn = fmin(mn, pmin[t * NW + w]);
+            sm = __dadd_rn(sm, psum[t * NW + w]);
+        }
+        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+        g.part_min[o] = mn;
+        g.part_sum[o] = sm;
+    }
     // ---- emit the pixels that were ever updated (pAll != 2, mustache.py:774) ----
     if (lvl != 0) {
 #pragma unroll

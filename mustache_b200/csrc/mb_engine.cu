@@ -165,7 +165,6 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.L = (double*)((char*)e->Lb.p + V_GUARD_BYTES);
     g.wl = e->wl;
     g.kh_depth = kh_depth_for(e->prog.rmax);
-    g.dbg_flags = getenv("MB200_DBG") ? atoi(getenv("MB200_DBG")) : 0;
     g.plane_v = e->plane_v;
     g.plane_l = e->plane_l;
     g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
@@ -231,7 +230,7 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     CU(e, cudaGetLastError());
     if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
     e->launches += 2;
-    if (pg.n_scored > 0 && !(g.dbg_flags & 4)) {
+    if (pg.n_scored > 0) {
         ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(pg.n_scored), e->stream>>>(pg, tm, g);
         CU(e, cudaGetLastError());
         e->launches += 1;
@@ -741,13 +740,6 @@ int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair,
     if (!pair) return fail(e, MB200_ERR_ARG, "null output array");
     CU(e, cudaMemcpyAsync(pair, (double*)e->rec_pair.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
-    return MB200_OK;
-}
-
-// development aid: raw bytes of a TMA descriptor (which < 0: the L map, else the V map of that step)
-MB200_API int mb200_debug_tensormap(mb200_engine* e, int which, void* out128) {
-    if (!e || !out128) return MB200_ERR_ARG;
-    memcpy(out128, which < 0 ? (void*)&e->tmaps.l : (void*)&e->tmaps.v[which], 128);
     return MB200_OK;
 }
 

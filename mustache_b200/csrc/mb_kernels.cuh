@@ -76,7 +76,6 @@ struct MbGeom {
     double* L;                      // [n_steps][nblk][n][wl]  DoG formed at each step, diagonals 2..dhi+2 (nullptr: not stored)
     int wl;                         // diagonals per row of L (even)
     int kh_depth;                   // stages of kh_kernel's staging ring
-    int dbg_flags;                  // development switches (0 in production)
     long long plane_v;              // elements between consecutive (step, block) planes of V (>= n*wv, even)
     long long plane_l;              // same for L
     double* part_min;               // [nblk][n_scored][ncta_h]
@@ -369,10 +368,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned box rows)
         tma_load_box3d(vbuf + st * (KH_TR * pv), &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[st]);
     };
-#ifndef MB_DBG_NOTMA
     if (!border && warp == 0 && elect_one())
         for (int s = 0; s < D - 1 && s < prog.n_steps; ++s) issue(s);
-#endif
 
     double gA[KH_K], gB[KH_K];
 #pragma unroll
@@ -387,10 +384,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const int bw = kh_box_width(R);                          // row pitch of this step's staged box
         const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-#ifndef MB_DBG_NOTMA
-            if (warp == 0 && s + D - 1 < prog.n_steps && !(g.dbg_flags & 1) && elect_one()) issue(s + D - 1);
+            if (warp == 0 && s + D - 1 < prog.n_steps && elect_one()) issue(s + D - 1);
             mbar_wait(&full[st], u & 1);
-#endif
         } else {
             __syncthreads();                                     // previous step's readers are done with stage 0
             const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
@@ -409,11 +404,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             }
             __syncthreads();
         }
-#ifdef MB_DBG_NOCONV
-        if (false) {
-#else
         if (chunk_live && row_in) {
-#endif
             conv_slide<KH_K>(vst + lane * bw + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
@@ -430,11 +421,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
             }
         }
-#ifndef MB_DBG_NOSTORE
         if (!(flags & MB_FLAG_RESTART) && row_in && chunk_live) {
-#else
-        if (false) {
-#endif
             // DoG row i, diagonals 2..dhi+2 -> L[s][b][i][d-2]; columns past the image hold the maximum filter's cval 0
             double* lout = g.L + ((size_t)s * g.nblk + b) * g.plane_l + (size_t)i * g.wl;
             double* dst = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF))
@@ -454,12 +441,11 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     };
 
     int s = 0;
-    const int nst = (g.dbg_flags & 1) ? min(prog.n_steps, D - 1) : prog.n_steps;
-    for (; s + 1 < nst; s += 2) {
+    for (; s + 1 < prog.n_steps; s += 2) {
         step(s, gB, gA);
         step(s + 1, gA, gB);
     }
-    if (s < nst) step(s, gB, gA);
+    if (s < prog.n_steps) step(s, gB, gA);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -164,7 +164,6 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.V = (double*)((char*)e->V.p + V_GUARD_BYTES);     // bulk copies may start a few elements before a row
     g.L = (double*)((char*)e->Lb.p + V_GUARD_BYTES);
     g.wl = e->wl;
-    g.kh_depth = kh_depth_for(e->prog.rmax);
     g.plane_v = e->plane_v;
     g.plane_l = e->plane_l;
     g.part_min = (double*)e->part_min.p + (size_t)first_block * ns * e->ncta_h;
@@ -220,7 +219,6 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
                 const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
     const MbProgram& pg = program ? *program : e->prog;
-    g.kh_depth = kh_depth_for(pg.rmax);
     const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
     const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
     kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(pg, g);
@@ -312,6 +310,24 @@ void mb200_destroy(mb200_engine* e) {
 
 const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null engine"; }
 
+// Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping), and for each step the
+// latest earlier step whose box it overwrites.
+static void plan_kh_ring(MbProgram& p) {
+    const int cap = kh_ring_doubles(p.rmax);
+    int cur = 0;
+    for (int s = 0; s < p.n_steps; ++s) {
+        const int size = (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15;
+        if (cur + size > cap) cur = 0;
+        p.stage[s].off = cur;
+        p.stage[s].dep = -1;
+        for (int t = 0; t < s; ++t) {
+            const int tsize = (KH_TR * kh_box_width(p.st[t].radius) + 15) & ~15;
+            if (p.stage[t].off < cur + size && cur < p.stage[t].off + tsize) p.stage[s].dep = t;
+        }
+        cur += size;
+    }
+}
+
 static int parse_program(mb200_engine* e, MbProgram& p, int n_steps, const int32_t* radius, const int32_t* flags,
                          const int32_t* score_id, const int32_t* tap_off, const double* half_taps, int n_taps) {
     if (!e || !radius || !flags || !score_id || !tap_off || !half_taps) return fail(e, MB200_ERR_ARG, "null argument");
@@ -340,6 +356,7 @@ static int parse_program(mb200_engine* e, MbProgram& p, int n_steps, const int32
     }
     if (p.n_scored > 254) return fail(e, MB200_ERR_ARG, "too many scored steps");
     memcpy(p.taps, half_taps, (size_t)n_taps * sizeof(double));
+    plan_kh_ring(p);
     return MB200_OK;
 }
 

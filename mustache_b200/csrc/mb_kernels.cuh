@@ -36,12 +36,20 @@ struct MbStep {
     int score_idx;   // 0-based index among scored steps (valid when MB_FLAG_SCORE)
 };
 
+// kh_kernel stages the axis-0 tile of every step in a byte-granular ring of shared memory: small-radius steps have small
+// boxes, so more of them are in flight.  Placement is computed on the host (mb_engine.cu: plan_kh_ring).
+struct MbStage {
+    int off;         // offset of the step's box in the ring, in doubles (multiple of 16 -> 128-byte aligned)
+    int dep;         // latest earlier step whose box overlaps this one (-1: none): must be released before the copy
+};
+
 struct MbProgram {
     int n_steps;
     int n_scored;
     int rmax;
     int pad;
     MbStep st[MB_MAX_STEPS];
+    MbStage stage[MB_MAX_STEPS];
     int score_id[MB_MAX_STEPS];   // per scored index: octave*12 + i  (reference's scales[o][i])
     double taps[MB_MAX_TAPS];
 };
@@ -75,7 +83,6 @@ struct MbGeom {
     double* V;                      // [n_steps][nblk][n][wv]
     double* L;                      // [n_steps][nblk][n][wl]  DoG formed at each step, diagonals 2..dhi+2 (nullptr: not stored)
     int wl;                         // diagonals per row of L (even)
-    int kh_depth;                   // stages of kh_kernel's staging ring
     long long plane_v;              // elements between consecutive (step, block) planes of V (>= n*wv, even)
     long long plane_l;              // same for L
     double* part_min;               // [nblk][n_scored][ncta_h]
@@ -117,20 +124,23 @@ constexpr int KS_DEPTH = 4;           // levels in flight per CTA
 // on an even column: TMA needs 16-byte aligned box rows), padded to 2 (mod 4) elements so that the dense rows the TMA
 // writes put the 32 lanes (= rows) on 8 different 8-byte bank pairs (2-way conflicts)
 __host__ __device__ inline int kh_box_width(int R) {
-    const int p = KH_TC + 2 * R + 2;
+    const int p = KH_TC + 2 * R + 2;          // + 1 for the even start column, + 1 for the row stagger of kh_kernel
     return (p % 4 == 2) ? p : p + 2;
 }
 __host__ __device__ inline int kh_vbuf_pitch(int rmax) { return kh_box_width(rmax); }
-// ring depth of kh_kernel: as many stages (2..4) as fit in half an SM's shared memory (two CTAs per SM)
-__host__ __device__ inline int kh_depth_for(int rmax) {
-    const size_t stage = (size_t)KH_TR * kh_vbuf_pitch(rmax) * sizeof(double);
-    int d = (int)((112 * 1024 - 64) / stage);
-    return d < 2 ? 2 : (d > 4 ? 4 : d);
+// staging ring of kh_kernel: half an SM's shared memory (two CTAs per SM), at least two of the widest boxes
+constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the slowest warp
+constexpr int KH_XP = KH_K + 1;        // pitch of the per-warp 32 x 8 transpose buffer (odd: lanes index rows)
+__host__ __device__ inline int kh_ring_doubles(int rmax) {
+    const int widest = KH_TR * kh_vbuf_pitch(rmax);
+    const int half_sm = (110 * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP;
+    return half_sm > 2 * widest ? half_sm : 2 * widest;
 }
 __host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
     (void)n_scored;
-    return ((size_t)kh_depth_for(rmax) * KH_TR * kh_vbuf_pitch(rmax) + 8) * sizeof(double);   // stages + 2 x 4 mbarriers
+    // ring + full/empty mbarrier per step + per-warp transpose buffers for the coalesced DoG stores
+    return ((size_t)kh_ring_doubles(rmax) + 2 * MB_MAX_STEPS + (KH_THREADS / 32) * KH_TR * KH_XP) * sizeof(double);
 }
 
 __host__ __device__ inline size_t ks_smem_bytes(int n_scored) {
@@ -327,11 +337,10 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     extern __shared__ __align__(128) double smem[];
     constexpr int NW = KH_THREADS / 32;
     const int rmax = prog.rmax;
-    const int pv = kh_vbuf_pitch(rmax);                         // stage size: the widest box of the chain
-    const int D = g.kh_depth;                                   // ring depth (2..4 stages, as shared memory allows)
-    double* vbuf = smem;                                        // [D][KH_TR][box width of the step]   TMA destination
-    uint64_t* full = reinterpret_cast<uint64_t*>(vbuf + (size_t)D * KH_TR * pv);   // [D] bytes landed
-    uint64_t* empty = full + 4;                                 // [D] every warp is done reading the stage
+    double* vbuf = smem;                                        // byte-granular ring of staged boxes (TMA destination)
+    uint64_t* full = reinterpret_cast<uint64_t*>(vbuf + kh_ring_doubles(rmax));    // [n_steps] bytes landed (used once)
+    uint64_t* empty = full + MB_MAX_STEPS;                      // [n_steps] every warp is done reading the box (used once)
+    double* xbuf = reinterpret_cast<double*>(empty + MB_MAX_STEPS) + (threadIdx.x >> 5) * (KH_TR * KH_XP);   // per warp [32][9]
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -340,36 +349,45 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     const int ilast = min(i0 + KH_TR, g.n) - 1;
     if (js >= g.n || js > ilast + g.dhi + 2) return;    // tile entirely right of the band / of the image
     const int i = i0 + lane;                            // this thread's image row
-    const int c0 = warp * KH_K;
+    // Rows 8-15 and 24-31 of every tile are shifted one column to the right: with the even row pitch of the dense TMA box,
+    // lanes (= rows) r and r+8 would hit the same 8-byte bank pair; the one-column stagger puts them on the odd pairs.
+    // All tiles share the stagger, so they still partition the band.
+    const int stag = (lane >> 3) & 1;
+    const int c0 = warp * KH_K + stag;
     const int jc0 = js + c0;                            // image column of its first pixel
     const bool row_in = i < g.n;
     // tiles whose +/- rmax column halo leaves the image need 'reflect' indexing: generic (slow) staging for those
-    const bool border = (js - rmax < 0) || (js + KH_TC + rmax > g.n);
+    const bool border = (js - rmax < 0) || (js + KH_TC + 1 + rmax > g.n);
 
-    if (threadIdx.x == 0) {
-        for (int d = 0; d < D; ++d) {
-            mbar_init(&full[d], 1);
-            mbar_init(&empty[d], NW);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int t = threadIdx.x; t < prog.n_steps; t += KH_THREADS) {
+        mbar_init(&full[t], 1);
+        mbar_init(&empty[t], NW);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    // any pixel of this warp's 32 x 8 chunk on a diagonal the detector reads (2 .. dhi+2)?
-    const bool chunk_live = (jc0 + KH_K - 1 - i0 >= 2) && (jc0 - (i0 + KH_TR - 1) <= g.dhi + 2) && (jc0 < g.n);
+    // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
+    const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
+                            (js + warp * KH_K < g.n);
 
-    // Producer side (one thread): one TMA box copy per step -- the 32 x (TC + 2R) axis-0 tile of step s into stage s % D,
-    // after every warp released the stage's previous contents (step s - D).
-    auto issue = [&](int s) {
-        const int u = s / D, st = s - u * D;
-        if (u > 0) mbar_wait(&empty[st], (u - 1) & 1);
-        const int R = prog.st[s].radius;
-        const uint32_t bytes = (uint32_t)(KH_TR * kh_box_width(R)) * 8u;
-        mbar_arrive_expect_tx(&full[st], bytes);
-        // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned box rows)
-        tma_load_box3d(vbuf + st * (KH_TR * pv), &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[st]);
+    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
+    // into its slot of the ring, after every warp released the boxes it overlaps.
+    int next_issue = 0;
+    auto issue_ready = [&](int s_now) {
+        while (next_issue < prog.n_steps && next_issue <= s_now + KH_LOOKAHEAD) {
+            const int dep = prog.stage[next_issue].dep;
+            if (dep >= s_now) break;                            // the overlapped box is still ahead of this warp
+            if (elect_one()) {
+                if (dep >= 0) mbar_wait(&empty[dep], 0);
+                const int s = next_issue;
+                const int R = prog.st[s].radius;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
+                // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
+                tma_load_box3d(vbuf + prog.stage[s].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+            }
+            ++next_issue;
+        }
     };
-    if (!border && warp == 0 && elect_one())
-        for (int s = 0; s < D - 1 && s < prog.n_steps; ++s) issue(s);
+    if (!border && warp == 0) issue_ready(0);
 
     double gA[KH_K], gB[KH_K];
 #pragma unroll
@@ -379,17 +397,16 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     auto step = [&](const int s, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
         const int R = prog.st[s].radius;
         const int flags = prog.st[s].flags;
-        const int u = s / D, st = s - u * D;
-        double* vst = vbuf + (border ? 0 : st) * (KH_TR * pv);
+        double* vst = vbuf + (border ? 0 : prog.stage[s].off);
         const int bw = kh_box_width(R);                          // row pitch of this step's staged box
         const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-            if (warp == 0 && s + D - 1 < prog.n_steps && elect_one()) issue(s + D - 1);
-            mbar_wait(&full[st], u & 1);
+            if (warp == 0) issue_ready(s);
+            mbar_wait(&full[s], 0);
         } else {
-            __syncthreads();                                     // previous step's readers are done with stage 0
+            __syncthreads();                                     // previous step's readers are done with the buffer
             const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
-            const int wlen = KH_TC + 2 * R;
+            const int wlen = KH_TC + 1 + 2 * R;
             for (int r = warp; r < KH_TR; r += NW) {
                 const int ii = i0 + r;
                 for (int t = lane; t < wlen; t += 32) {
@@ -410,9 +427,9 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
         }
-        if (!border) {                                           // release the stage: one arrival per warp
+        if (!border) {                                           // release the box: one arrival per warp
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
         if (g.dbgG != nullptr && s == g.dbg_step && b == 0 && row_in) {
 #pragma unroll
@@ -421,21 +438,33 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
             }
         }
-        if (!(flags & MB_FLAG_RESTART) && row_in && chunk_live) {
-            // DoG row i, diagonals 2..dhi+2 -> L[s][b][i][d-2]; columns past the image hold the maximum filter's cval 0
-            double* lout = g.L + ((size_t)s * g.nblk + b) * g.plane_l + (size_t)i * g.wl;
-            double* dst = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF))
-                              ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc + (size_t)i * g.wc : nullptr;
+        if (!(flags & MB_FLAG_RESTART) && chunk_live) {
+            // DoG of the warp's 32 x 8 pixels.  The owner layout (lane = row) would store 32 separate 8-byte pieces per
+            // instruction; a trip through the warp's transpose buffer makes every store instruction write 4 rows x 64
+            // contiguous bytes (whole 32-byte sectors).  Columns past the image hold the maximum filter's cval 0.
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) {
-                const int j = jc0 + k, d = j - i;
-                if (d >= 2 && d <= g.dhi + 2) {
-                    const double l = (j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-                    if (g.L != nullptr) lout[d - 2] = l;
-                    if (dst != nullptr && j < g.n && d >= 4 && d <= g.dhi) dst[d - 4] = l;
-                    if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && j < g.n) g.dbgL[(size_t)i * g.n + j] = l;
+                const int j = jc0 + k;
+                xbuf[lane * KH_XP + k] = (row_in && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+            }
+            __syncwarp();
+            double* lbase = g.L + ((size_t)s * g.nblk + b) * g.plane_l;
+            double* dbase = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF)) ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc : nullptr;
+            const int kk = lane & 7;
+#pragma unroll
+            for (int q = 0; q < KH_TR / 4; ++q) {
+                const int r = 4 * q + (lane >> 3);                       // tile row written by this lane
+                const int ii = i0 + r;
+                const int j = js + warp * KH_K + ((r >> 3) & 1) + kk;    // that row's stagger
+                const int d = j - ii;
+                if (ii < g.n && d >= 2 && d <= g.dhi + 2) {
+                    const double l = xbuf[r * KH_XP + kk];
+                    if (g.L != nullptr) lbase[(size_t)ii * g.wl + (d - 2)] = l;
+                    if (dbase != nullptr && j < g.n && d >= 4 && d <= g.dhi) dbase[(size_t)ii * g.wc + (d - 4)] = l;
+                    if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && j < g.n) g.dbgL[(size_t)ii * g.n + j] = l;
                 }
             }
+            __syncwarp();
         }
         if (!(flags & MB_FLAG_RESTART) && (flags & MB_FLAG_DIFFREF)) ++ndiff;
     };

@@ -271,9 +271,14 @@ kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
 // The V_s rows of the tile are brought in by TMA bulk copies (cp.async.bulk, one per tile row, issued by warp 0) into a
 // two-stage ring guarded by mbarriers, so the copy for step s+1 is in flight while step s is filtered and scored.
 // ---------------------------------------------------------------------------------------------------------------
+// max / min of finite doubles: one compare + select (fmax / fmin add NaN handling that costs ~3x the instructions; the
+// engine rejects non-finite tiles up front, mustache.py:755 would raise on them)
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -594,18 +599,18 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 if (t == 0 && warp == 0) c = 0;                         // clamped columns only feed halo pixels
                 if (t == KS_K + 1 && warp == NW - 1) c = KS_K - 1;
                 const double a1 = (t >= 1 && t <= KS_K) ? lown[t - 1] : st[off_c + c];
-                vm[t] = fmax(fmax(st[off_u + c], a1), st[off_d + c]);
+                vm[t] = dmax(dmax(st[off_u + c], a1), st[off_d + c]);
             }
             const unsigned cand = score ? (mask & e_cur) : 0u;
 #pragma unroll
             for (int k = 0; k < KS_K; ++k) {
                 const unsigned bit = 1u << k;
-                const double mnew = fmax(fmax(vm[k], vm[k + 1]), vm[k + 2]);
+                const double mnew = dmax(dmax(vm[k], vm[k + 1]), vm[k + 2]);
                 const bool en = (lown[k] == mnew);
                 if (en) e_new |= bit;
                 if (score && (mask & bit)) {
                     const double a = fabs(lcur[k]);
-                    tmin = fmin(tmin, a);
+                    tmin = dmin(tmin, a);
                     tsum = __dadd_rn(tsum, a);
                 }
                 // mustache.py:760-765
@@ -649,7 +654,7 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
         double mn = pmin[t * NW], sm = psum[t * NW];
         for (int w = 1; w < NW; ++w) {
-            mn = fmin(mn, pmin[t * NW + w]);
+            mn = dmin(mn, pmin[t * NW + w]);
             sm = __dadd_rn(sm, psum[t * NW + w]);
         }
         const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;

@@ -69,6 +69,11 @@ MB200_API int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* r
 MB200_API int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int64_t ld);
 MB200_API int mb200_upload_dense_dev(mb200_engine* e, int block, const double* tile_dev, int64_t ld);
 MB200_API int mb200_upload_band_host(mb200_engine* e, int block, const double* band, int64_t wsrc);
+/* Uploads are asynchronous on a second stream into the tile slot the kernels are NOT reading (tiles are double
+ * buffered), so the uploads of batch k+1 overlap mb200_run of batch k (the analogue of the reference starting the next
+ * `-p` processes, mustache.py:926-934).  Host buffers of the _dense_/_band_ uploads must stay valid until mb200_run /
+ * mb200_sync; page-locked memory (mb200_host_alloc) makes them true DMA.  Results of batch k stay fetchable until the
+ * next mb200_run. */
 
 /* Runs the whole scale-space loop for all uploaded blocks: mask + fills (mustache.py:699-706), 12 Gaussians per octave
  * (:719-751), DoG (:728,738,754), 3x3 maxima (:740-743,757), extremum test and running best (:760-768), exponential fit

@@ -22,6 +22,13 @@ struct DevBuf {
 struct mb200_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t up_stream = nullptr;     // uploads run here, into the tile slot the compute stream is not reading
+    cudaEvent_t ev_up = nullptr;          // uploads of the pending batch are complete
+    cudaEvent_t ev_run[2] = {nullptr, nullptr};   // the run that read slot k is complete
+    int slot_up = 0;                      // tile slot the next uploads go to
+    int slot_run = 0;                     // tile slot of the last run
+    bool slot_used[2] = {false, false};   // a run has read this slot (uploads into it must wait for ev_run)
+    bool up_dirty = false;                // uploads happened since the last run
     char err[512] = {0};
     MbProgram prog;
     MbProgram dprog;                 // difference-stack chain (diff_mustache): G_2, G_3 of every octave
@@ -73,6 +80,7 @@ int ensure(mb200_engine* e, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return MB200_OK;
     if (b.p) {
         CU(e, cudaStreamSynchronize(e->stream));
+        CU(e, cudaStreamSynchronize(e->up_stream));
         CU(e, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -94,6 +102,33 @@ int use_device(mb200_engine* e) {
 }
 
 constexpr size_t V_GUARD_BYTES = 64 * 1024;   // slack on both sides of the axis-0 scratch for 16-byte-aligned row copies
+
+// Tiles are double-buffered: uploads of the next batch (on up_stream) overlap the kernels of the current one.
+double* raw_slot(const mb200_engine* e, int slot) {
+    return (double*)e->raw.p + (size_t)slot * e->nblocks * e->n * e->wc;
+}
+
+// called by every upload before it touches the upload slot
+int begin_upload(mb200_engine* e) {
+    if (!e->up_dirty && e->slot_used[e->slot_up]) {
+        CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_run[e->slot_up], 0));
+        e->slot_used[e->slot_up] = false;
+    }
+    e->up_dirty = true;
+    return MB200_OK;
+}
+
+// the batch that was just uploaded becomes the one the kernels read; the other slot takes the next uploads
+int adopt_uploads(mb200_engine* e) {
+    if (e->up_dirty) {
+        CU(e, cudaEventRecord(e->ev_up, e->up_stream));
+        CU(e, cudaStreamWaitEvent(e->stream, e->ev_up, 0));
+        e->slot_run = e->slot_up;
+        e->slot_up ^= 1;
+        e->up_dirty = false;
+    }
+    return MB200_OK;
+}
 
 size_t v_bytes_per_block(const mb200_engine* e) {
     return (size_t)e->prog.n_steps * e->plane_v * sizeof(double);
@@ -160,7 +195,7 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.dbg_step = -1;
     g.rec_cap = e->rec_cap;
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
-    g.raw = (const double*)e->raw.p + (size_t)first_block * e->n * e->wc;
+    g.raw = raw_slot(e, e->slot_run) + (size_t)first_block * e->n * e->wc;
     g.V = (double*)((char*)e->V.p + V_GUARD_BYTES);     // bulk copies may start a few elements before a row
     g.L = (double*)((char*)e->Lb.p + V_GUARD_BYTES);
     g.wl = e->wl;
@@ -282,6 +317,10 @@ int mb200_create(int device, mb200_engine** out) {
     e->device = device;
     memset(&e->prog, 0, sizeof(e->prog));
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_up, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_run[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_prep) != cudaSuccess ||
         cudaEventCreate(&e->ev_end) != cudaSuccess) {
         delete e;
@@ -295,6 +334,7 @@ void mb200_destroy(mb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->up_stream) cudaStreamSynchronize(e->up_stream);
     DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
@@ -304,6 +344,10 @@ void mb200_destroy(mb200_engine* e) {
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_prep) cudaEventDestroy(e->ev_prep);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->ev_up) cudaEventDestroy(e->ev_up);
+    for (int k = 0; k < 2; ++k)
+        if (e->ev_run[k]) cudaEventDestroy(e->ev_run[k]);
+    if (e->up_stream) cudaStreamDestroy(e->up_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -415,7 +459,12 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if ((st = set_smem_limits(e))) return st;
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
     const size_t B = nblocks;
-    if ((st = ensure(e, e->raw, B * n * e->wc * sizeof(double)))) return st;
+    CU(e, cudaStreamSynchronize(e->stream));             // a new geometry re-uses every buffer
+    CU(e, cudaStreamSynchronize(e->up_stream));
+    if ((st = ensure(e, e->raw, 2 * B * n * e->wc * sizeof(double)))) return st;
+    e->slot_up = e->slot_run = 0;
+    e->slot_used[0] = e->slot_used[1] = false;
+    e->up_dirty = false;
     if ((st = ensure(e, e->part_min, B * ns * e->ncta_h * sizeof(double)))) return st;
     if ((st = ensure(e, e->part_sum, B * ns * e->ncta_h * sizeof(double)))) return st;
     if ((st = ensure(e, e->rec_count, B * sizeof(unsigned long long)))) return st;
@@ -438,7 +487,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->pass_blocks = (int)std::min<long long>(fit, nblocks);
     if ((st = ensure(e, e->V, (size_t)e->pass_blocks * v_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     if ((st = ensure(e, e->Lb, (size_t)e->pass_blocks * l_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
-    CU(e, cudaMemsetAsync(e->raw.p, 0, B * n * e->wc * sizeof(double), e->stream));
+    CU(e, cudaMemsetAsync(e->raw.p, 0, 2 * B * n * e->wc * sizeof(double), e->stream));
     if ((st = encode_maps(e, e->prog, e->tmaps, true))) return st;
     if ((st = ensure(e, e->d_tmaps, sizeof(MbTensorMaps)))) return st;
     CU(e, cudaMemcpyAsync(e->d_tmaps.p, &e->tmaps, sizeof(MbTensorMaps), cudaMemcpyHostToDevice, e->stream));
@@ -447,7 +496,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
         if ((st = ensure(e, e->d_dtmaps, sizeof(MbTensorMaps)))) return st;
         CU(e, cudaMemcpyAsync(e->d_dtmaps.p, &e->dtmaps, sizeof(MbTensorMaps), cudaMemcpyHostToDevice, e->stream));
     }
-    CU(e, cudaStreamSynchronize(e->stream));      // the host copies may be re-encoded by the next configure
+    CU(e, cudaStreamSynchronize(e->stream));      // the host copies may be re-encoded by the next configure; tiles are zeroed
     e->configured = true;
     e->ran = false;
     e->counts_valid = false;
@@ -460,22 +509,27 @@ int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const
     if (st) return st;
     if (nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(e, MB200_ERR_ARG, "bad COO arguments");
     if ((st = use_device(e))) return st;
-    if (nnz == 0) return MB200_OK;
+    if (nnz == 0) {
+        if ((st = begin_upload(e))) return st;
+        CU(e, cudaMemsetAsync(raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));
+        return MB200_OK;
+    }
     if ((st = ensure(e, e->st_rows, nnz * sizeof(int)))) return st;
     if ((st = ensure(e, e->st_cols, nnz * sizeof(int)))) return st;
     if ((st = ensure(e, e->st_vals, nnz * sizeof(double)))) return st;
-    CU(e, cudaMemcpyAsync(e->st_rows.p, rows, nnz * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaMemcpyAsync(e->st_cols.p, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CU(e, cudaMemcpyAsync(e->st_vals.p, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    if ((st = begin_upload(e))) return st;
+    CU(e, cudaMemcpyAsync(e->st_rows.p, rows, nnz * sizeof(int), cudaMemcpyHostToDevice, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->st_cols.p, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->st_vals.p, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, e->up_stream));
+    double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
+    CU(e, cudaMemsetAsync(rawb, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));   // the slot may hold an older tile
     const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 8);
-    scatter_coo_kernel<<<grid, 256, 0, e->stream>>>((const int*)e->st_rows.p, (const int*)e->st_cols.p,
-                                                    (const double*)e->st_vals.p, nnz, rawb, e->n, e->wc, e->dhi);
+    scatter_coo_kernel<<<grid, 256, 0, e->up_stream>>>((const int*)e->st_rows.p, (const int*)e->st_cols.p,
+                                                       (const double*)e->st_vals.p, nnz, rawb, e->n, e->wc, e->dhi);
     CU(e, cudaGetLastError());
     // the staging buffers are reused by the next upload: keep uploads ordered on the stream (they are) and make
     // sure the host arrays may be released when this call returns
-    CU(e, cudaStreamSynchronize(e->stream));
-    e->ran = false;
+    CU(e, cudaStreamSynchronize(e->up_stream));
     return MB200_OK;
 }
 
@@ -484,11 +538,12 @@ int mb200_upload_band_host(mb200_engine* e, int block, const double* band, int64
     if (st) return st;
     if (!band || wsrc < 1) return fail(e, MB200_ERR_ARG, "bad band arguments");
     if ((st = use_device(e))) return st;
-    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    if ((st = begin_upload(e))) return st;
+    double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
     const size_t w = (size_t)std::min<int64_t>(wsrc, e->wc);
+    if (w < (size_t)e->wc) CU(e, cudaMemsetAsync(rawb, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));
     CU(e, cudaMemcpy2DAsync(rawb, (size_t)e->wc * sizeof(double), band, (size_t)wsrc * sizeof(double), w * sizeof(double),
-                            e->n, cudaMemcpyHostToDevice, e->stream));
-    e->ran = false;
+                            e->n, cudaMemcpyHostToDevice, e->up_stream));
     return MB200_OK;
 }
 
@@ -497,7 +552,8 @@ int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int6
     if (st) return st;
     if (!tile || ld < e->n) return fail(e, MB200_ERR_ARG, "bad dense arguments");
     if ((st = use_device(e))) return st;
-    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
+    if ((st = begin_upload(e))) return st;
+    double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
     // Row i of the band starts at tile[i*ld + i + 4]: a pitched copy with source pitch (ld+1) moves exactly the band.
     // Rows whose band segment would run past the end of the host array are copied one by one, clipped.
     const int64_t total = (int64_t)(e->n - 1) * ld + e->n;                 // elements addressable in the host tile
@@ -505,14 +561,13 @@ int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int6
     safe_rows = std::max<int64_t>(0, std::min<int64_t>(safe_rows, e->n));
     if (safe_rows > 0)
         CU(e, cudaMemcpy2DAsync(rawb, (size_t)e->wc * sizeof(double), tile + 4, (size_t)(ld + 1) * sizeof(double),
-                                (size_t)e->wc * sizeof(double), (size_t)safe_rows, cudaMemcpyHostToDevice, e->stream));
+                                (size_t)e->wc * sizeof(double), (size_t)safe_rows, cudaMemcpyHostToDevice, e->up_stream));
     for (int64_t i = safe_rows; i < e->n; ++i) {
         const int64_t w = std::min<int64_t>(e->wc, e->n - i - 4);
         if (w > 0)
             CU(e, cudaMemcpyAsync(rawb + (size_t)i * e->wc, tile + i * ld + i + 4, (size_t)w * sizeof(double),
-                                  cudaMemcpyHostToDevice, e->stream));
+                                  cudaMemcpyHostToDevice, e->up_stream));
     }
-    e->ran = false;
     return MB200_OK;
 }
 
@@ -521,10 +576,10 @@ int mb200_upload_dense_dev(mb200_engine* e, int block, const double* tile_dev, i
     if (st) return st;
     if (!tile_dev || ld < e->n) return fail(e, MB200_ERR_ARG, "bad dense arguments");
     if ((st = use_device(e))) return st;
-    double* rawb = (double*)e->raw.p + (size_t)block * e->n * e->wc;
-    band_from_dense_kernel<<<148 * 8, 256, 0, e->stream>>>(tile_dev, ld, rawb, e->n, e->wc);
+    if ((st = begin_upload(e))) return st;
+    double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
+    band_from_dense_kernel<<<148 * 8, 256, 0, e->up_stream>>>(tile_dev, ld, rawb, e->n, e->wc);
     CU(e, cudaGetLastError());
-    e->ran = false;
     return MB200_OK;
 }
 
@@ -537,6 +592,7 @@ int mb200_run(mb200_engine* e) {
     e->launches = 0;
     e->counts_valid = false;
     e->ran_diff = false;
+    if ((st = adopt_uploads(e))) return st;
     const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
     while ((int)e->ev_pass.size() < 4 * npass) {
         cudaEvent_t ev;
@@ -547,7 +603,7 @@ int mb200_run(mb200_engine* e) {
     CU(e, cudaMemsetAsync(e->rec_count.p, 0, B * sizeof(unsigned long long), e->stream));
     CU(e, cudaMemsetAsync(e->nz_count.p, 0, B * sizeof(unsigned long long), e->stream));
     CU(e, cudaMemsetAsync(e->nonfinite.p, 0, B * sizeof(int), e->stream));
-    count_mask_kernel<<<dim3(148 * 2, B), 256, 0, e->stream>>>((const double*)e->raw.p, e->n, e->wc,
+    count_mask_kernel<<<dim3(148 * 2, B), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), e->n, e->wc,
                                                                 (unsigned long long*)e->nz_count.p, (int*)e->nonfinite.p);
     CU(e, cudaGetLastError());
     e->launches += 1;
@@ -571,6 +627,8 @@ int mb200_run(mb200_engine* e) {
         e->launches += 2;
     }
     CU(e, cudaEventRecord(e->ev_end, e->stream));
+    CU(e, cudaEventRecord(e->ev_run[e->slot_run], e->stream));
+    e->slot_used[e->slot_run] = true;
     e->ran = true;
     return MB200_OK;
 }
@@ -579,6 +637,7 @@ int mb200_sync(mb200_engine* e) {
     if (!e) return MB200_ERR_ARG;
     int st = use_device(e);
     if (st) return st;
+    CU(e, cudaStreamSynchronize(e->up_stream));
     CU(e, cudaStreamSynchronize(e->stream));
     return MB200_OK;
 }
@@ -679,6 +738,7 @@ int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, d
     const size_t bytes = (size_t)e->n * e->n * sizeof(double);
     if ((st = ensure(e, e->dbgG, bytes))) return st;
     if ((st = ensure(e, e->dbgL, bytes))) return st;
+    if ((st = adopt_uploads(e))) return st;
     CU(e, cudaMemsetAsync(e->dbgG.p, 0, bytes, e->stream));
     CU(e, cudaMemsetAsync(e->dbgL.p, 0, bytes, e->stream));
     MbGeom g = make_geom(e, block, 1);
@@ -717,7 +777,7 @@ int mb200_run_differential(mb200_engine* e) {
     if ((st = ensure(e, e->rec_pair, (size_t)e->nblocks * e->rec_cap * sizeof(double)))) return st;
     if ((st = ensure(e, e->d_score_id, MB_MAX_STEPS * sizeof(int)))) return st;
     CU(e, cudaMemcpyAsync(e->d_score_id.p, e->prog.score_id, MB_MAX_STEPS * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    diff_tile_kernel<<<dim3(148 * 2, npairs), 256, 0, e->stream>>>((const double*)e->raw.p, (double*)e->rawD.p, e->n, e->wc, e->dpx);
+    diff_tile_kernel<<<dim3(148 * 2, npairs), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), (double*)e->rawD.p, e->n, e->wc, e->dpx);
     CU(e, cudaGetLastError());
     CU(e, cudaMemsetAsync(e->dout.p, 0, (size_t)ndiff * npairs * tile * sizeof(double), e->stream));
     // difference stack: same kernels, constant regions are 0 (c = zeros; c[nz] = c1[nz] - c2[nz]), nothing is scored
@@ -733,7 +793,7 @@ int mb200_run_differential(mb200_engine* e) {
         g.dout = (double*)e->dout.p;
         if ((st = launch_pass(e, 0, nb, &g, nullptr, &e->dprog))) return st;
     }
-    diff_stats_kernel<<<dim3(ndiff, npairs), 1024, 0, e->stream>>>((const double*)e->raw.p, (const double*)e->dout.p, e->n, e->wc,
+    diff_stats_kernel<<<dim3(ndiff, npairs), 1024, 0, e->stream>>>(raw_slot(e, e->slot_run), (const double*)e->dout.p, e->n, e->wc,
                                                                   npairs, (double*)e->dmu.p, (double*)e->dsd.p);
     CU(e, cudaGetLastError());
     diff_pair_kernel<<<dim3(32, e->nblocks), 256, 0, e->stream>>>(

@@ -140,10 +140,24 @@ class ScaleSpaceEngine:
         if st:
             raise EngineError(st, "mb200_create(device=%d) failed" % device)
         self.device = int(device)
+        self._pin = {}
         self.program = None
         self.n = self.dpx = self.nblocks = None
 
+    def _pinned(self, name, n, dtype):
+        """Engine-owned page-locked staging array (grow-only) for full-speed device -> host record copies."""
+        buf = self._pin.get(name)
+        if buf is None or buf.array.size < n:
+            if buf is not None:
+                buf.free()
+            buf = PinnedBuffer((max(4096, int(1.25 * n)),), dtype)
+            self._pin[name] = buf
+        return buf.array[:n]
+
     def close(self):
+        for buf in getattr(self, "_pin", {}).values():
+            buf.free()
+        self._pin = {}
         if getattr(self, "h", None):
             self.lib.mb200_destroy(self.h)
             self.h = None
@@ -220,16 +234,21 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_block_counts(self.h, int(block), C.byref(nz), C.byref(nf)))
         return nz.value, nf.value
 
-    def records(self, block, sort=True, pair=False):
-        """Records of every updated pixel, sorted row-major (the order of c[nz] in the reference)."""
+    def records(self, block, sort=True, pair=False, pinned=False):
+        """Records of every updated pixel, sorted row-major (the order of c[nz] in the reference).
+        pinned=True: the arrays are views of engine-owned page-locked buffers, valid until the next records() call."""
         nz, nf = self.counts(block)
         pp = None
         if pair:
             pp = np.empty(nf, np.float64)
             n2 = C.c_int64(0)
             self._chk(self.lib.mb200_fetch_pair(self.h, int(block), nf, _ptr(pp, _f64p), C.byref(n2)))
-        rows, cols = np.empty(nf, np.int32), np.empty(nf, np.int32)
-        v, p, sid = np.empty(nf, np.float64), np.empty(nf, np.float64), np.empty(nf, np.int32)
+        if pinned:
+            rows, cols, sid = (self._pinned(k, nf, np.int32) for k in ("rows", "cols", "sid"))
+            v, p = self._pinned("v", nf, np.float64), self._pinned("p", nf, np.float64)
+        else:
+            rows, cols = np.empty(nf, np.int32), np.empty(nf, np.int32)
+            v, p, sid = np.empty(nf, np.float64), np.empty(nf, np.float64), np.empty(nf, np.int32)
         n_out = C.c_int64(0)
         self._chk(self.lib.mb200_fetch_records(self.h, int(block), nf, _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(v, _f64p),
                                                _ptr(sid, _i32p), _ptr(p, _f64p), C.byref(n_out)))

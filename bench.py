@@ -230,9 +230,9 @@ def main():
 
     def device_step():
         eng.run()
-        if world > 1:
-            recs = [eng.records(b, sort=False) for b in range(B)]
-            gather.all_gather_records(recs, rank, world, torch.device("cuda", local_rank))
+        if world > 1:                        # the path's only collective: candidate records, device to device over NCCL
+            for b in range(B):
+                gather.all_gather_device(eng.records_device(b), world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,9 +283,10 @@ def main():
     def e2e_step():
         eng.run()
         e2e_upload()
-        recs = [eng.records(b, sort=False, pinned=(B == 1)) for b in range(B)]
         if world > 1:
-            gather.all_gather_records(recs, rank, world, torch.device("cuda", local_rank))
+            for b in range(B):
+                gather.all_gather_device(eng.records_device(b), world)
+        recs = [eng.records(b, sort=False, pinned=(B == 1)) for b in range(B)]
         return recs
 
     e2e_upload()

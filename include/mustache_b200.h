@@ -90,6 +90,12 @@ MB200_API int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, 
 MB200_API int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* rows, int32_t* cols, double* v,
                         int32_t* score_id, double* p, int64_t* n_out);
 
+/* Device pointers of a block's record arrays (valid until the next mb200_run / mb200_configure; the engine's stream must
+ * be synchronised -- mb200_block_counts does -- before they are read): lets a multi-GPU caller hand them to NCCL without a
+ * host round trip.  scored_index is the 0-based index among the scoring steps (mb200_fetch_fits maps it to the score id). */
+MB200_API int mb200_records_device(mb200_engine* e, int block, void** rows, void** cols, void** v, void** scored_index,
+                                   void** p, int64_t* capacity);
+
 /* Exponential fit per scored step of a block (loc = min|L|, scale = mean|L| - loc, mustache.py:755): arrays of n_scored. */
 MB200_API int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored);
 

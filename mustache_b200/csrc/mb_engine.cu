@@ -675,6 +675,21 @@ int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* r
     return MB200_OK;
 }
 
+int mb200_records_device(mb200_engine* e, int block, void** rows, void** cols, void** v, void** scored_index, void** p,
+                         int64_t* capacity) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (!e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
+    const size_t o = (size_t)block * e->rec_cap;
+    if (rows) *rows = (int*)e->rec_row.p + o;
+    if (cols) *cols = (int*)e->rec_col.p + o;
+    if (v) *v = (double*)e->rec_v.p + o;
+    if (scored_index) *scored_index = (int*)e->rec_sidx.p + o;
+    if (p) *p = (double*)e->rec_p.p + o;
+    if (capacity) *capacity = e->rec_cap;
+    return MB200_OK;
+}
+
 int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored) {
     int st = check_block(e, block);
     if (st) return st;

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mb200_sync": (C.c_int, [_H]),
     "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
     "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
+    "mb200_records_device": (C.c_int, [_H, C.c_int] + [C.POINTER(C.c_void_p)] * 5 + [_i64p]),
     "mb200_fetch_fits": (C.c_int, [_H, C.c_int, _f64p, _f64p, _i32p, C.c_int, C.POINTER(C.c_int)]),
     "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
     "mb200_last_launches": (C.c_int, [_H, C.POINTER(C.c_int)]),
@@ -261,6 +262,25 @@ class ScaleSpaceEngine:
         out = dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
         if pp is not None:
             out["pair"] = pp
+        return out
+
+    def records_device(self, block):
+        """Record arrays of a block as torch CUDA tensors aliasing the engine's buffers (no copy): dict of
+        rows, cols (int32), v, p (float64), scored_index (int32), each of length n_found; plus nz_count."""
+        import torch
+        nz, nf = self.counts(block)                       # synchronises the engine's stream
+        ptrs = [C.c_void_p() for _ in range(5)]
+        cap = C.c_int64(0)
+        self._chk(self.lib.mb200_records_device(self.h, int(block), *[C.byref(q) for q in ptrs], C.byref(cap)))
+
+        class _Alias:                                     # __cuda_array_interface__ view of engine-owned device memory
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = torch.device("cuda", self.device)
+        out = {}
+        for name, q, ts in zip(("rows", "cols", "v", "scored_index", "p"), ptrs, ("<i4", "<i4", "<f8", "<i4", "<f8")):
+            out[name] = torch.as_tensor(_Alias(q.value, max(nf, 1), ts), device=dev)[:nf]
+        out.update(nz_count=nz, n_found=nf)
         return out
 
     def fits(self, block):

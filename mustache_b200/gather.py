@@ -73,3 +73,26 @@ def split_by_block(gathered):
             rec["pair"] = a[:, len(FIELDS)]
         out[(int(a[0, 0]), int(a[0, 1]))] = rec
     return out
+
+
+def all_gather_device(dev_recs, world):
+    """NCCL gather of one block's records that never leaves the devices: `dev_recs` is ScaleSpaceEngine.records_device()
+    (torch tensors aliasing the engine's buffers).  Counts first, then every field padded to the longest rank.
+    Returns (list of per-rank counts, dict of gathered tensors [world, max_n])."""
+    import torch
+    import torch.distributed as dist
+    dev = dev_recs["v"].device
+    cnt = torch.tensor([dev_recs["n_found"], dev_recs["nz_count"]], dtype=torch.int64, device=dev)
+    cnts = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(cnts, cnt)
+    sizes = cnts[:, 0].tolist()
+    mx = max(max(sizes), 1)
+    out = {}
+    for name in ("rows", "cols", "v", "scored_index", "p"):
+        src = dev_recs[name]
+        pad = torch.zeros(mx, dtype=src.dtype, device=dev)
+        pad[:src.numel()] = src
+        buf = torch.empty((world, mx), dtype=src.dtype, device=dev)
+        dist.all_gather_into_tensor(buf, pad)
+        out[name] = buf
+    return sizes, out

@@ -159,3 +159,46 @@ def test_error_codes(eng):
         eng.records(0)
     assert ei.value.code == -4
 
+
+
+def test_records_device_alias_matches_host_fetch(eng):
+    """records_device() hands NCCL the engine's own buffers (no host round trip): same content as the host fetch."""
+    spec = synth.SYNTH_TILES["n256_o2"]
+    c = synth.make_tile(**spec["gen"])
+    eng.set_octaves(spec["octaves"])
+    eng.configure(256, spec["dpx"], 1)
+    eng.upload_dense(0, c)
+    eng.run()
+    host = eng.records(0, sort=False)
+    dev = eng.records_device(0)
+    assert dev["n_found"] == host["n_found"] and dev["nz_count"] == host["nz_count"]
+    assert np.array_equal(dev["rows"].cpu().numpy(), host["rows"]) and np.array_equal(dev["cols"].cpu().numpy(), host["cols"])
+    assert np.array_equal(dev["v"].cpu().numpy(), host["v"]) and np.array_equal(dev["p"].cpu().numpy(), host["p"])
+    ids = eng.fits(0)["score_id"][dev["scored_index"].cpu().numpy()]
+    assert np.array_equal(ids, host["score_id"])
+
+
+def test_pipelined_uploads_do_not_mix_batches(eng):
+    """Uploads of batch k+1 are issued while batch k may still be running (double-buffered tiles): results of both
+    batches must be those of their own tiles."""
+    a = synth.make_tile(**synth.SYNTH_TILES["n256_o2"]["gen"])
+    b = synth.make_tile(n=256, dpx=100, seed=77, blob_seed=78, nblobs=9, missing=0.2)
+    eng.set_octaves([1.6, 3.2])
+    eng.configure(256, 100, 1)
+    ref = {}
+    for name, t in (("a", a), ("b", b)):
+        eng.upload_dense(0, t)
+        eng.run()
+        ref[name] = eng.records(0)
+    eng.upload_dense(0, a)
+    eng.run()
+    eng.upload_dense(0, b)          # goes to the other slot while the run of `a` is in flight
+    ra = eng.records(0)
+    eng.run()
+    eng.upload_dense(0, a)
+    rb = eng.records(0)
+    eng.run()
+    ra2 = eng.records(0)
+    for got, want in ((ra, ref["a"]), (rb, ref["b"]), (ra2, ref["a"])):
+        assert np.array_equal(got["rows"], want["rows"]) and np.array_equal(got["cols"], want["cols"])
+        assert np.array_equal(got["v"], want["v"]) and np.array_equal(got["p"], want["p"])

@@ -67,9 +67,9 @@ def band_to_coo(band, n=None):
     return i[ok].astype(np.int32), j[ok].astype(np.int32), band[i[ok], k[ok]]
 
 
-def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed=None):
+def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed=None, loop_boost=8.0):
     """Configs 3/4: raw counts ~ Poisson(lam(d)), lam(d) = lam_scale/(d+1) for d >= 1 (30 at d = 0), bias == 1,
-    planted loops adding Poisson(8) in a 3x3 patch.  Returns upper-triangular COO (x, y, count) with |y-x| <= dpx+1,
+    planted loops adding Poisson(loop_boost) in a 3x3 patch.  Returns upper-triangular COO (x, y, count) with |y-x| <= dpx+1,
     i.e. what read_pd() would return for a 3/5-column text file of these counts (mustache.py:254-297)."""
     rng = np.random.default_rng(seed)
     xs, ys, vs = [], [], []
@@ -95,7 +95,7 @@ def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed
             i0 = int(lrng.integers(2, n - d0 - 2))
             for di in (-1, 0, 1):
                 for dj in (-1, 0, 1):
-                    a[i0 + di, i0 + d0 + dj] += lrng.poisson(8)
+                    a[i0 + di, i0 + d0 + dj] += lrng.poisson(loop_boost)
         a = a.tocoo()
         keep = a.data > 0
         x, y, v = a.row[keep].astype(np.int64), a.col[keep].astype(np.int64), a.data[keep].astype(np.float64)

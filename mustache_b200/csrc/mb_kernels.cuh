@@ -308,19 +308,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// K_H (kh_kernel): axis-1 pass of every step + DoG, written to HBM.  grid = (column tiles, row tiles, blocks).
-// Thread (lane = tile row, warp = group of 8 tile columns) produces 8 consecutive outputs along the filter axis; the
-// previous Gaussian of its pixels stays in registers, so L_s = G_{s-1} - G_s costs one subtraction.  No halo: the tiles
-// partition the band, the scoring kernel reads its own halo.  Two CTAs per SM.
-// ---------------------------------------------------------------------------------------------------------------
 // one lane of a converged warp (elect.sync): keeps the TMA operands provably uniform for the compiler
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -240,12 +240,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # 200 ms period: started before the warm-up so that short timed regions are covered
     for _ in range(args.warmup):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     dev_ms, phases = 0.0, {"prep_ms": 0.0, "kv_ms": 0.0, "kh_ms": 0.0, "ks_ms": 0.0, "fin_ms": 0.0}
     t0 = time.perf_counter()
     for _ in range(args.steps):

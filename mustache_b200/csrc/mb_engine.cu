@@ -32,6 +32,7 @@ struct mb200_engine {
     char err[512] = {0};
     MbProgram prog;
     MbProgram dprog;                 // difference-stack chain (diff_mustache): G_2, G_3 of every octave
+    KvPlan kvplan, dkvplan;          // kv_kernel's grouping of the two chains
     bool have_prog = false;
     bool have_dprog = false;
     bool ran_diff = false;
@@ -239,7 +240,9 @@ int set_smem_limits(mb200_engine* e) {
         e->kv_smem_set = kvb;
     }
     if (khb != e->kh_smem_set) {
-        CU(e, cudaFuncSetAttribute(kh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
         e->kh_smem_set = khb;
     }
     const size_t ksb = ks_smem_bytes(e->prog.n_scored);
@@ -256,10 +259,15 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     const MbProgram& pg = program ? *program : e->prog;
     const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
     const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
-    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(pg, g);
+    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
-    kh_kernel<<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    if (g.dout != nullptr)                          // difference stack: only the DIFFREF DoGs are kept
+        kh_kernel<KH_DIFF><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    else if (g.dbgG != nullptr || g.dbgL != nullptr)
+        kh_kernel<KH_DEBUG><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    else
+        kh_kernel<KH_MAIN><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
     CU(e, cudaGetLastError());
     if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
     e->launches += 2;
@@ -372,6 +380,38 @@ static void plan_kh_ring(MbProgram& p) {
     }
 }
 
+// kv_kernel's plan: steps sorted by radius, cut into groups of KV_G (the first group takes the remainder), slots filled
+// from the back, weights transposed per group.
+static int plan_kv(mb200_engine* e, const MbProgram& p, KvPlan& kp) {
+    memset(&kp, 0, sizeof(kp));
+    std::vector<int> order(p.n_steps);
+    for (int s = 0; s < p.n_steps; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.st[a].radius < p.st[b].radius; });
+    kp.rmax = p.rmax;
+    int pos = 0, off = 0;
+    while (pos < p.n_steps) {
+        const int rem = p.n_steps - pos;
+        const int cnt = (rem % KV_G) ? rem % KV_G : KV_G;
+        if (kp.n_groups >= KV_MAX_GROUPS) return fail(e, MB200_ERR_ARG, "too many steps for the axis-0 plan (%d groups)", KV_MAX_GROUPS);
+        KvGroup& gr = kp.grp[kp.n_groups++];
+        gr.n = cnt;
+        gr.rmax = p.st[order[pos + cnt - 1]].radius;
+        gr.tap_off = off;
+        const int need = (gr.rmax + 1) * KV_G;
+        if (off + need > KV_MAX_TAPS_T) return fail(e, MB200_ERR_ARG, "axis-0 plan needs more than %d transposed taps", KV_MAX_TAPS_T);
+        for (int slot = 0; slot < KV_G; ++slot) {
+            const int q = slot - (KV_G - cnt);
+            gr.step[slot] = q >= 0 ? order[pos + q] : -1;
+            gr.R[slot] = q >= 0 ? p.st[order[pos + q]].radius : 0;
+            if (q >= 0)
+                for (int j = 0; j <= gr.R[slot]; ++j) kp.tapsT[off + j * KV_G + slot] = p.taps[p.st[order[pos + q]].tap_off + j];
+        }
+        off += need;
+        pos += cnt;
+    }
+    return MB200_OK;
+}
+
 static int parse_program(mb200_engine* e, MbProgram& p, int n_steps, const int32_t* radius, const int32_t* flags,
                          const int32_t* score_id, const int32_t* tap_off, const double* half_taps, int n_taps) {
     if (!e || !radius || !flags || !score_id || !tap_off || !half_taps) return fail(e, MB200_ERR_ARG, "null argument");
@@ -409,6 +449,7 @@ int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const
     if (!e) return MB200_ERR_ARG;
     int st = parse_program(e, e->prog, n_steps, radius, flags, score_id, tap_off, half_taps, n_taps);
     if (st) return st;
+    if ((st = plan_kv(e, e->prog, e->kvplan))) return st;
     e->have_prog = true;
     e->configured = false;
     return MB200_OK;
@@ -426,6 +467,7 @@ int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, 
         if (flags[s] & MB200_STEP_DIFFREF) ++nd;
     }
     if (nd < 1) return fail(e, MB200_ERR_ARG, "the difference chain needs at least one MB200_STEP_DIFFREF step");
+    if ((st = plan_kv(e, e->dprog, e->dkvplan))) return st;
     e->have_dprog = true;
     e->configured = false;          // the TMA descriptors of the difference chain are built by mb200_configure
     return MB200_OK;

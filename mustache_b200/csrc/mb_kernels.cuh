@@ -54,6 +54,29 @@ struct MbProgram {
     double taps[MB_MAX_TAPS];
 };
 
+// kv_kernel's view of the chain: the steps sorted by radius and cut into groups of KV_G that share their pair sums.
+// Slots are filled from the back: a group with fewer than KV_G steps has dummy slots (step -1, radius 0, weights 0)
+// in front.  tapsT holds the group's weights transposed, tapsT[tap_off + j*KV_G + slot] = weight of `slot` at distance j
+// (0 for j beyond the slot's radius; never read there).
+#define KV_G 6
+#define KV_MAX_GROUPS 16
+#define KV_MAX_TAPS_T 2048
+struct KvGroup {
+    int n;              // real steps in the group
+    int rmax;           // largest radius of the group
+    int tap_off;
+    int pad;
+    int R[KV_G];        // radius per slot, non-decreasing
+    int step[KV_G];     // chain step per slot, -1 = dummy
+};
+struct KvPlan {
+    int n_groups;
+    int rmax;
+    int pad[2];
+    KvGroup grp[KV_MAX_GROUPS];
+    double tapsT[KV_MAX_TAPS_T];
+};
+
 // TMA descriptors (cuTensorMapEncodeTiled, built by the host per batch geometry).  Both scratch arrays are addressed
 // through a skewed 3-D view (x = column index, y = image row, z = step * nblk + block) whose row stride is one element
 // shorter than the band row, so that a rectangular box of the view is a rectangular (i, j) tile of the image:
@@ -101,10 +124,10 @@ struct MbGeom {
 // ---------------------------------------------------------------------------------------------------------------
 // tile shapes
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int KV_TH = 64;      // rows per CTA (axis-0 pass)
+constexpr int KV_TH = 128;     // rows per CTA (axis-0 pass): four 32-row sub-blocks walked one after the other
 constexpr int KV_TW = 32;      // columns per CTA = lanes
-constexpr int KV_K = 8;        // outputs per thread along the filter axis
-constexpr int KV_THREADS = (KV_TH / KV_K) * 32;   // 256
+constexpr int KV_K = 4;        // outputs per thread along the filter axis
+constexpr int KV_THREADS = (32 / KV_K) * 32;      // 256: one 32-row sub-block at a time
 
 constexpr int KH_TR = 32;      // tile rows = lanes (axis-1 pass)
 constexpr int KH_TC = 64;      // tile columns
@@ -136,7 +159,8 @@ __host__ __device__ inline int kh_ring_doubles(int rmax) {
     const int half_sm = (110 * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP;
     return half_sm > 2 * widest ? half_sm : 2 * widest;
 }
-__host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax) * KV_TW * sizeof(double); }
+constexpr int KV_GUARD = 3;
+__host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax + KV_GUARD) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
     (void)n_scored;
     // ring + full/empty mbarrier per step + per-warp transpose buffers for the coalesced DoG stores
@@ -214,13 +238,66 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K_V: axis-0 pass for every step of the chain.  grid = (column tiles, row tiles, blocks)
+// K_V: axis-0 pass for every step of the chain.  grid = (column tiles, row tiles, blocks), two CTAs per SM.
+//
+// Every Gaussian of the chain is an independent convolution of the SAME tile (mustache.py:719,725,734,751 all pass `c`),
+// and in scipy's folded sum  out = x0*w0; for j = R..1: out += (x[-j] + x[j]) * w[j]  the pair sum (x[-j] + x[j]) does
+// not depend on the step.  The steps are therefore processed in groups of KV_G (sorted by radius, mb_engine.cu:
+// plan_kv): a thread owns KV_K consecutive rows of one column, walks j from the group's largest radius down to 1, forms
+// each pair sum once and feeds it to every step of the group whose radius reaches j.  Per step the order of the
+// additions is still j = R..1, so every result is bit-identical to scipy's; the FP64 instruction count per output drops
+// from sum(3R+1) to sum(2R+1) + sum over groups of max R  (2415 -> 1778 for 4 octaves, 532 -> 399 for 2).
+// The walk is split into KV_G segments: in segment a (radii (R[a-1], R[a]]) the steps a..KV_G-1 are active, so the
+// accumulators keep static register names and the only per-tap predicate is the segment end.
 // ---------------------------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ void kv_segment(const double* __restrict__ ctr, const double* __restrict__ tp, const int hiR,
+                                           const int loR, double (&acc)[KV_G][KV_K]) {
+    // taps are handled four at a time from windows loaded once: xl[m] = x[m - jc], xr[m] = x[jc - 3 + m]
+    for (int jc = hiR; jc > loR; jc -= 4) {
+        double xl[KV_K + 3], xr[KV_K + 3];
+#pragma unroll
+        for (int m = 0; m < KV_K + 3; ++m) {
+            xl[m] = ctr[(m - jc) * KV_TW];
+            xr[m] = ctr[(jc - 3 + m) * KV_TW];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = jc - u;
+            if (j > loR) {
+                double t[KV_K];
+#pragma unroll
+                for (int k = 0; k < KV_K; ++k) t[k] = __dadd_rn(xl[k + u], xr[k + 3 - u]);
+#pragma unroll
+                for (int s = A; s < KV_G; ++s) {
+                    const double w = tp[j * KV_G + s];
+#pragma unroll
+                    for (int k = 0; k < KV_K; ++k) acc[s][k] = __dadd_rn(acc[s][k], __dmul_rn(t[k], w));
+                }
+            }
+        }
+    }
+}
+
+template <int A>
+struct KvSegments {
+    static __device__ __forceinline__ void run(const double* __restrict__ ctr, const double* __restrict__ tp,
+                                               const KvGroup& gr, double (&acc)[KV_G][KV_K]) {
+        kv_segment<A>(ctr, tp, gr.R[A], A > 0 ? gr.R[A > 0 ? A - 1 : 0] : 0, acc);   // radii (R[A-1], R[A]]
+        KvSegments<A - 1>::run(ctr, tp, gr, acc);
+    }
+};
+template <>
+struct KvSegments<-1> {
+    static __device__ __forceinline__ void run(const double* __restrict__, const double* __restrict__, const KvGroup&,
+                                               double (&)[KV_G][KV_K]) {}
+};
+
 __global__ void __launch_bounds__(KV_THREADS, 2)
-kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
+kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     extern __shared__ double smem[];
-    double* cs = smem;                              // [(KV_TH + 2 rmax)][KV_TW]
-    const int rmax = prog.rmax;
+    double* cs = smem + KV_GUARD * KV_TW;           // [(KV_TH + 2 rmax)][KV_TW]; the last window of a radius < 3 step
+    const int rmax = plan.rmax;                     //   reaches up to KV_GUARD rows above the tile (loaded, never used)
     const int b = blockIdx.z;
     const int i0 = blockIdx.y * KV_TH;
     const int vhi = g.vlo + g.wv - 1;
@@ -229,37 +306,61 @@ kv_kernel(const __grid_constant__ MbProgram prog, const MbGeom g) {
     const int j0 = jbase + blockIdx.x * KV_TW;
     const int ilast = min(i0 + KV_TH, g.n) - 1;
     if (j0 >= g.n || j0 > ilast + vhi) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = j0 + lane;
 
-    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
-    const int rows = KV_TH + 2 * rmax;
-    for (int e = threadIdx.x; e < rows * KV_TW; e += KV_THREADS) {
-        const int r = e / KV_TW, c = e % KV_TW;
-        const int ii = reflect_idx(i0 - rmax + r, g.n);
-        const int jj = j0 + c;
-        cs[e] = (jj < g.n) ? filled_at(g, rawb, ii, jj) : 0.0;
+    // stage the filled tile (mustache.py:703-706 applied on the fly), 'reflect' rows: one warp per tile row
+    {
+        const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+        const int rows = KV_TH + 2 * rmax;
+#pragma unroll 4
+        for (int r = warp; r < rows; r += KV_THREADS / 32) {
+            // rows past n - 1 + rmax feed no stored output: clamped so that the reflection stays inside the tile
+            const int ii = reflect_idx(min(i0 - rmax + r, g.n - 1 + rmax), g.n);
+            const int d = j - ii;
+            double val = g.fill;                                    // d <= 4, or intra and d >= dpx + 1
+            if (j >= g.n) val = 0.0;                                // never used by a stored output
+            else if (d > 4 && !(g.intra && d >= g.dpx + 1)) val = (d > g.dhi) ? 0.0 : rawb[ii * g.wc + (d - 4)];
+            cs[r * KV_TW + lane] = val;
+        }
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int rb = (threadIdx.x >> 5) * KV_K;
-    const int j = j0 + lane;
-    if (i0 + rb >= g.n) return;
-    const double* ctr = cs + (size_t)(rb + rmax) * KV_TW + lane;
-    const int dmin = j0 - (i0 + rb + KV_K - 1);
-    const int dmax = j0 + KV_TW - 1 - (i0 + rb);
-
-    for (int s = 0; s < prog.n_steps; ++s) {
-        const int R = prog.st[s].radius;
-        const int lo = 2 - R, hi = g.dhi + 2 + R;       // diagonals the axis-1 pass of this step will read
-        if (dmax < lo || dmin > hi) continue;           // warp-uniform
-        double acc[KV_K];
-        conv_slide<KV_K>(ctr, KV_TW, R, prog.taps + prog.st[s].tap_off, acc);
-        double* vout = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
+    for (int sub = 0; sub < KV_TH / 32; ++sub) {
+        const int rb = sub * 32 + warp * KV_K;      // first tile row of this thread's KV_K outputs
+        const int i = i0 + rb;
+        if (i >= g.n) break;                        // warp-uniform
+        const double* ctr = cs + (rb + rmax) * KV_TW + lane;
+        const int dmin_w = j0 - (i + KV_K - 1), dmax_w = j0 + KV_TW - 1 - i;
+        unsigned vmask = 0;                         // outputs inside the image and inside the V storage band
 #pragma unroll
         for (int k = 0; k < KV_K; ++k) {
-            const int i = i0 + rb + k;
-            const int d = j - i;
-            if (i < g.n && j < g.n && d >= lo && d <= hi) vout[(size_t)i * g.wv + (d - g.vlo)] = acc[k];
+            const int d = j - (i + k);
+            if (i + k < g.n && j < g.n && d >= g.vlo && d <= vhi) vmask |= 1u << k;
+        }
+        const long long off0 = (long long)i * g.wv + (j - i - g.vlo);      // output k sits at off0 + k * (wv - 1)
+        for (int gi = 0; gi < plan.n_groups; ++gi) {
+            const KvGroup& gr = plan.grp[gi];
+            if (dmax_w < 2 - gr.rmax || dmin_w > g.dhi + 2 + gr.rmax) continue;     // warp-uniform: nobody reads these
+            const double* tp = plan.tapsT + gr.tap_off;
+            double acc[KV_G][KV_K];
+#pragma unroll
+            for (int k = 0; k < KV_K; ++k) {
+                const double x = ctr[k * KV_TW];
+#pragma unroll
+                for (int s = 0; s < KV_G; ++s) acc[s][k] = __dmul_rn(x, tp[s]);
+            }
+            KvSegments<KV_G - 1>::run(ctr, tp, gr, acc);
+#pragma unroll
+            for (int s = 0; s < KV_G; ++s) {
+                const int step = gr.step[s];
+                if (step >= 0) {
+                    double* vout = g.V + ((size_t)step * g.nblk + b) * g.plane_v + off0;
+#pragma unroll
+                    for (int k = 0; k < KV_K; ++k)
+                        if (vmask & (1u << k)) vout[(long long)k * (g.wv - 1)] = acc[s][k];
+                }
+            }
         }
     }
 }
@@ -324,6 +425,12 @@ __device__ __forceinline__ void tma_load_box3d(void* dst, const CUtensorMap* map
         : "memory");
 }
 
+// MODE: KH_MAIN  DoG of every step -> L (scored by ks_kernel)
+//       KH_DIFF  difference stack of diff_mustache: only the DoGs of MB_FLAG_DIFFREF steps are kept, in dout
+//       KH_DEBUG KH_MAIN plus the dense dumps of mb200_debug_level
+constexpr int KH_MAIN = 0, KH_DIFF = 1, KH_DEBUG = 2;
+
+template <int MODE>
 __global__ void __launch_bounds__(KH_THREADS, 2)
 kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
     extern __shared__ __align__(128) double smem[];
@@ -360,6 +467,36 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
                             (js + warp * KH_K < g.n);
+
+    // Everything the DoG store needs that does not depend on the step.  The owner layout (lane = row) would store 32
+    // separate 8-byte pieces per instruction, so the 32 x 8 DoG chunk of the warp takes a trip through the warp's
+    // transpose buffer: store instruction q writes tile rows 4q..4q+3 (lane>>3 selects the row), 8 columns each.
+    unsigned zmask = 0;                                 // owner side: pixels that hold a DoG (others hold the cval 0)
+#pragma unroll
+    for (int k = 0; k < KH_K; ++k)
+        if (row_in && jc0 + k < g.n) zmask |= 1u << k;
+    const int kk = lane & 7;
+    const int pitch = (MODE == KH_DIFF) ? g.wc : g.wl;          // row length of the destination band
+    const int dlo = (MODE == KH_DIFF) ? 4 : 2;                  // first diagonal it stores
+    const int dhi_st = (MODE == KH_DIFF) ? g.dhi : g.dhi + 2;   // last one
+    unsigned qmask = 0;                                 // writer side: valid (row, column) of store instruction q
+    int qoff0 = 0;                                      // element offset of q = 0; q adds 4*(pitch-1) (+1 for staggered rows)
+    {
+        const int r0 = lane >> 3;
+        const int jw = js + warp * KH_K + kk;
+#pragma unroll
+        for (int q = 0; q < KH_TR / 4; ++q) {
+            const int r = 4 * q + r0;
+            const int ii = i0 + r;
+            const int jj = jw + ((q >> 1) & 1);                 // rows 8-15, 24-31 are staggered
+            const int d = jj - ii;
+            bool ok = ii < g.n && d >= dlo && d <= dhi_st;
+            if (MODE == KH_DIFF) ok = ok && jj < g.n;
+            if (ok) qmask |= 1u << q;
+        }
+        qoff0 = (i0 + r0) * (pitch - 1) + jw - dlo;             // row*pitch + (d - dlo) = row*(pitch-1) + col - dlo
+    }
+    const int qstride = 4 * (pitch - 1);
 
     // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
     // into its slot of the ring, after every warp released the boxes it overlaps.
@@ -423,42 +560,41 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
-        if (g.dbgG != nullptr && s == g.dbg_step && b == 0 && row_in) {
+        if (MODE == KH_DEBUG) {
+            if (g.dbgG != nullptr && s == g.dbg_step && b == 0 && row_in) {
 #pragma unroll
-            for (int k = 0; k < KH_K; ++k) {
-                const int j = jc0 + k;
-                if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
+                for (int k = 0; k < KH_K; ++k) {
+                    const int j = jc0 + k;
+                    if (j < g.n) g.dbgG[(size_t)i * g.n + j] = gnew[k];
+                }
             }
         }
-        if (!(flags & MB_FLAG_RESTART) && chunk_live) {
-            // DoG of the warp's 32 x 8 pixels.  The owner layout (lane = row) would store 32 separate 8-byte pieces per
-            // instruction; a trip through the warp's transpose buffer makes every store instruction write 4 rows x 64
-            // contiguous bytes (whole 32-byte sectors).  Columns past the image hold the maximum filter's cval 0.
+        const bool formed = !(flags & MB_FLAG_RESTART);
+        const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
+        if (keep && chunk_live) {
+            // columns past the image hold the maximum filter's cval 0
 #pragma unroll
-            for (int k = 0; k < KH_K; ++k) {
-                const int j = jc0 + k;
-                xbuf[lane * KH_XP + k] = (row_in && j < g.n) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-            }
+            for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
             __syncwarp();
-            double* lbase = g.L + ((size_t)s * g.nblk + b) * g.plane_l;
-            double* dbase = (g.dout != nullptr && (flags & MB_FLAG_DIFFREF)) ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc : nullptr;
-            const int kk = lane & 7;
+            double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc
+                                            : g.L + ((size_t)s * g.nblk + b) * g.plane_l;
+            dst += qoff0;
 #pragma unroll
             for (int q = 0; q < KH_TR / 4; ++q) {
-                const int r = 4 * q + (lane >> 3);                       // tile row written by this lane
-                const int ii = i0 + r;
-                const int j = js + warp * KH_K + ((r >> 3) & 1) + kk;    // that row's stagger
-                const int d = j - ii;
-                if (ii < g.n && d >= 2 && d <= g.dhi + 2) {
-                    const double l = xbuf[r * KH_XP + kk];
-                    if (g.L != nullptr) lbase[(size_t)ii * g.wl + (d - 2)] = l;
-                    if (dbase != nullptr && j < g.n && d >= 4 && d <= g.dhi) dbase[(size_t)ii * g.wc + (d - 4)] = l;
-                    if (g.dbgL != nullptr && s == g.dbg_step && b == 0 && j < g.n) g.dbgL[(size_t)ii * g.n + j] = l;
+                if (qmask & (1u << q)) {
+                    const double l = xbuf[(4 * q + (lane >> 3)) * KH_XP + kk];
+                    dst[q * qstride + ((q >> 1) & 1)] = l;
+                    if (MODE == KH_DEBUG) {
+                        if (g.dbgL != nullptr && s == g.dbg_step && b == 0) {
+                            const int ii = i0 + 4 * q + (lane >> 3), jj = js + warp * KH_K + kk + ((q >> 1) & 1);
+                            if (jj < g.n) g.dbgL[(size_t)ii * g.n + jj] = l;
+                        }
+                    }
                 }
             }
             __syncwarp();
         }
-        if (!(flags & MB_FLAG_RESTART) && (flags & MB_FLAG_DIFFREF)) ++ndiff;
+        if (MODE == KH_DIFF && keep) ++ndiff;
     };
 
     int s = 0;

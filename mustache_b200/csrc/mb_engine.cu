@@ -42,7 +42,7 @@ struct mb200_engine {
     long long rec_cap = 0;
     int ncta_h = 0;
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
-        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id;
+        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, sm_ticket;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
     bool counts_valid = false;
@@ -213,6 +213,7 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.dbgL = nullptr;
     g.fill = 2.0;                      // mustache.py:703-706
     g.dout = nullptr;
+    g.sm_ticket = (unsigned*)e->sm_ticket.p;
     return g;
 }
 
@@ -346,7 +347,7 @@ void mb200_destroy(mb200_engine* e) {
     DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
-                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps};
+                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps, &e->sm_ticket};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -362,52 +363,67 @@ void mb200_destroy(mb200_engine* e) {
 
 const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null engine"; }
 
-// Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping), and for each step the
-// latest earlier step whose box it overwrites.
+// Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping) for both walking
+// directions, indexed by the position in the walk, and for each position the latest earlier one whose box it overwrites.
 static void plan_kh_ring(MbProgram& p) {
     const int cap = kh_ring_doubles(p.rmax);
-    int cur = 0;
-    for (int s = 0; s < p.n_steps; ++s) {
-        const int size = (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15;
-        if (cur + size > cap) cur = 0;
-        p.stage[s].off = cur;
-        p.stage[s].dep = -1;
-        for (int t = 0; t < s; ++t) {
-            const int tsize = (KH_TR * kh_box_width(p.st[t].radius) + 15) & ~15;
-            if (p.stage[t].off < cur + size && cur < p.stage[t].off + tsize) p.stage[s].dep = t;
+    for (int dir = 0; dir < 2; ++dir) {
+        auto size_at = [&](int pos) {
+            const int s = dir ? p.n_steps - 1 - pos : pos;
+            return (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15;
+        };
+        MbStage* stg = p.stage[dir];
+        int cur = 0;
+        for (int pos = 0; pos < p.n_steps; ++pos) {
+            const int size = size_at(pos);
+            if (cur + size > cap) cur = 0;
+            stg[pos].off = cur;
+            stg[pos].dep = -1;
+            for (int t = 0; t < pos; ++t)
+                if (stg[t].off < cur + size && cur < stg[t].off + size_at(t)) stg[pos].dep = t;
+            cur += size;
         }
-        cur += size;
     }
 }
 
-// kv_kernel's plan: steps sorted by radius, cut into groups of KV_G (the first group takes the remainder), slots filled
-// from the back, weights transposed per group.
+// kv_kernel's plan: steps sorted by radius and cut into groups of 1..KV_GMAX consecutive steps.  A group of n steps
+// with largest radius R costs R*(2n+1) + n FP64 instructions per output (R pair sums shared by the group, every step
+// padded to R taps); the cut minimising the total is found by dynamic programming.
 static int plan_kv(mb200_engine* e, const MbProgram& p, KvPlan& kp) {
     memset(&kp, 0, sizeof(kp));
-    std::vector<int> order(p.n_steps);
-    for (int s = 0; s < p.n_steps; ++s) order[s] = s;
+    const int n = p.n_steps;
+    std::vector<int> order(n);
+    for (int s = 0; s < n; ++s) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.st[a].radius < p.st[b].radius; });
+    std::vector<long long> best(n + 1, 0);
+    std::vector<int> take(n + 1, 1);
+    for (int i = n - 1; i >= 0; --i) {
+        best[i] = -1;
+        for (int c = 1; c <= KV_GMAX && i + c <= n; ++c) {
+            const long long cost = (long long)p.st[order[i + c - 1]].radius * (2 * c + 1) + c + best[i + c];
+            if (best[i] < 0 || cost < best[i]) {
+                best[i] = cost;
+                take[i] = c;
+            }
+        }
+    }
     kp.rmax = p.rmax;
-    int pos = 0, off = 0;
-    while (pos < p.n_steps) {
-        const int rem = p.n_steps - pos;
-        const int cnt = (rem % KV_G) ? rem % KV_G : KV_G;
+    int off = 0;
+    for (int pos = 0; pos < n; pos += take[pos]) {
+        const int cnt = take[pos];
         if (kp.n_groups >= KV_MAX_GROUPS) return fail(e, MB200_ERR_ARG, "too many steps for the axis-0 plan (%d groups)", KV_MAX_GROUPS);
         KvGroup& gr = kp.grp[kp.n_groups++];
         gr.n = cnt;
         gr.rmax = p.st[order[pos + cnt - 1]].radius;
         gr.tap_off = off;
-        const int need = (gr.rmax + 1) * KV_G;
+        const int need = (gr.rmax + 1) * cnt;
         if (off + need > KV_MAX_TAPS_T) return fail(e, MB200_ERR_ARG, "axis-0 plan needs more than %d transposed taps", KV_MAX_TAPS_T);
-        for (int slot = 0; slot < KV_G; ++slot) {
-            const int q = slot - (KV_G - cnt);
-            gr.step[slot] = q >= 0 ? order[pos + q] : -1;
-            gr.R[slot] = q >= 0 ? p.st[order[pos + q]].radius : 0;
-            if (q >= 0)
-                for (int j = 0; j <= gr.R[slot]; ++j) kp.tapsT[off + j * KV_G + slot] = p.taps[p.st[order[pos + q]].tap_off + j];
+        for (int slot = 0; slot < cnt; ++slot) {
+            const MbStep& st = p.st[order[pos + slot]];
+            gr.step[slot] = order[pos + slot];
+            for (int j = 0; j <= st.radius; ++j) kp.tapsT[off + j * cnt + slot] = p.taps[st.tap_off + j];
         }
         off += need;
-        pos += cnt;
     }
     return MB200_OK;
 }
@@ -464,7 +480,10 @@ int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, 
     int nd = 0;
     for (int s = 0; s < n_steps; ++s) {
         if (flags[s] & MB200_STEP_SCORE) return fail(e, MB200_ERR_ARG, "the difference chain never scores");
-        if (flags[s] & MB200_STEP_DIFFREF) ++nd;
+        if (flags[s] & MB200_STEP_DIFFREF) {
+            if (flags[s] & MB200_STEP_RESTART) return fail(e, MB200_ERR_ARG, "step %d: a MB200_STEP_DIFFREF step must form a DoG", s);
+            e->dprog.st[s].score_idx = nd++;         // slot of this step's DoG in dout
+        }
     }
     if (nd < 1) return fail(e, MB200_ERR_ARG, "the difference chain needs at least one MB200_STEP_DIFFREF step");
     if ((st = plan_kv(e, e->dprog, e->dkvplan))) return st;
@@ -519,6 +538,10 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if ((st = ensure(e, e->rec_p, B * e->rec_cap * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_loc, B * ns * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_scale, B * ns * sizeof(double)))) return st;
+    if (!e->sm_ticket.p) {
+        if ((st = ensure(e, e->sm_ticket, MB_MAX_SMS * sizeof(unsigned)))) return st;
+        CU(e, cudaMemsetAsync(e->sm_ticket.p, 0, MB_MAX_SMS * sizeof(unsigned), e->stream));
+    }
     // axis-0 scratch: as many blocks per pass as fit in ~80 % of what is free now (plus what V already holds)
     size_t free_b = 0, total_b = 0;
     CU(e, cudaMemGetInfo(&free_b, &total_b));

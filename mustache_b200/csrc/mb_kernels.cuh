@@ -33,14 +33,17 @@ struct MbStep {
     int radius;
     int tap_off;     // taps[tap_off + j], j = 0..radius, weight at distance j
     int flags;
-    int score_idx;   // 0-based index among scored steps (valid when MB_FLAG_SCORE)
+    int score_idx;   // 0-based index among scored steps (valid when MB_FLAG_SCORE); in the difference chain of
+                     // diff_mustache: slot of this step's DoG in dout (valid when MB_FLAG_DIFFREF)
 };
 
 // kh_kernel stages the axis-0 tile of every step in a byte-granular ring of shared memory: small-radius steps have small
 // boxes, so more of them are in flight.  Placement is computed on the host (mb_engine.cu: plan_kh_ring).
+// A CTA walks the chain upwards (step 0, 1, ...) or downwards (see kh_kernel); the plan is per direction and indexed
+// by the position in the walk.
 struct MbStage {
-    int off;         // offset of the step's box in the ring, in doubles (multiple of 16 -> 128-byte aligned)
-    int dep;         // latest earlier step whose box overlaps this one (-1: none): must be released before the copy
+    int off;         // offset of the box in the ring, in doubles (multiple of 16 -> 128-byte aligned)
+    int dep;         // latest earlier position whose box overlaps this one (-1: none): must be released before the copy
 };
 
 struct MbProgram {
@@ -49,25 +52,24 @@ struct MbProgram {
     int rmax;
     int pad;
     MbStep st[MB_MAX_STEPS];
-    MbStage stage[MB_MAX_STEPS];
+    MbStage stage[2][MB_MAX_STEPS];   // [direction][position in the walk]
     int score_id[MB_MAX_STEPS];   // per scored index: octave*12 + i  (reference's scales[o][i])
     double taps[MB_MAX_TAPS];
 };
 
-// kv_kernel's view of the chain: the steps sorted by radius and cut into groups of KV_G that share their pair sums.
-// Slots are filled from the back: a group with fewer than KV_G steps has dummy slots (step -1, radius 0, weights 0)
-// in front.  tapsT holds the group's weights transposed, tapsT[tap_off + j*KV_G + slot] = weight of `slot` at distance j
-// (0 for j beyond the slot's radius; never read there).
-#define KV_G 6
-#define KV_MAX_GROUPS 16
+// kv_kernel's view of the chain: the steps sorted by radius and cut into groups of up to KV_GMAX that share their pair
+// sums (mb_engine.cu: plan_kv picks the cut that minimises the FP64 work).  Inside a group every step runs over the
+// group's largest radius with its weights zero-padded: tapsT[tap_off + j*n + slot] = weight of `slot` at distance j, 0
+// for j beyond the slot's own radius.  Adding (pair sum) * 0 before a step's first real tap leaves its accumulator
+// unchanged, so the padded taps cost FP64 instructions but not exactness.
+#define KV_GMAX 5
+#define KV_MAX_GROUPS 32
 #define KV_MAX_TAPS_T 2048
 struct KvGroup {
-    int n;              // real steps in the group
+    int n;              // steps in the group (1..KV_GMAX)
     int rmax;           // largest radius of the group
     int tap_off;
-    int pad;
-    int R[KV_G];        // radius per slot, non-decreasing
-    int step[KV_G];     // chain step per slot, -1 = dummy
+    int step[KV_GMAX];  // chain step per slot
 };
 struct KvPlan {
     int n_groups;
@@ -119,7 +121,15 @@ struct MbGeom {
     double* dbgL;                   // dense [n][n]: DoG formed at dbg_step
     double fill;                    // value of the constant regions (2.0; 0.0 for the difference stack of diff_mustache)
     double* dout;                   // [n_diffref][nblk][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
+    unsigned* sm_ticket;            // [MB_MAX_SMS] per-SM arrival counters (never reset: only their parity is used)
 };
+#define MB_MAX_SMS 1024
+
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // tile shapes
@@ -141,7 +151,7 @@ constexpr int KS_THREADS = (KS_TC / KS_K) * 32;   // 256
 constexpr int KS_SR = KS_TR - 2;   // scored rows per CTA
 constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
 constexpr int KS_PITCH = KS_TC + 2;   // 66: box width of the staged DoG tile, == 2 (mod 4)
-constexpr int KS_DEPTH = 4;           // levels in flight per CTA
+constexpr int KS_DEPTH = 5;           // ring stages per CTA: level being scored, the two before it, two in flight
 
 // width of the staged box of a step with radius R: the filter support of the tile plus one element (the box must start
 // on an even column: TMA needs 16-byte aligned box rows), padded to 2 (mod 4) elements so that the dense rows the TMA
@@ -191,50 +201,65 @@ __device__ __forceinline__ double filled_at(const MbGeom& g, const double* __res
 // ---------------------------------------------------------------------------------------------------------------
 // folded symmetric correlation, K outputs per thread, register windows sliding one element per tap
 //   x[q] = ctr[q * stride];  out[k] = x[k]*w0 + sum_{j=R..1} (x[k-j] + x[k+j]) * w[j]   (that order, no FMA)
+// The tap loop is unrolled K times (the window registers rotate with period K).  R is rarely a multiple of K: the
+// first trip enters the unrolled body at tap u0 = (K - R % K) % K (Duff's device) with the windows loaded in the state
+// u0 taps would have left them in, so there is no remainder loop and no padded tap.
 // ---------------------------------------------------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const int stride, const int R,
-                                           const double* __restrict__ tp, double (&acc)[K]) {
+template <int K, int STRIDE>
+__device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const int R, const double* __restrict__ tp,
+                                           double (&acc)[K]) {
+    static_assert(K == 8, "the unrolled body below is written for K = 8");
     double pl[K], pr[K];
     const double w0 = tp[0];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = __dmul_rn(ctr[k * stride], w0);
-#pragma unroll
-    for (int p = 0; p < K; ++p) {
-        pl[p] = ctr[(p - R) * stride];
-        pr[p] = ctr[(p + R) * stride];
+    for (int k = 0; k < K; ++k) acc[k] = __dmul_rn(ctr[k * STRIDE], w0);
+    const int u0 = (K - (R & (K - 1))) & (K - 1);
+    int j = R + u0;                                    // multiple of K; taps j .. j-u0+1 do not exist and are skipped
+    // running pointers: every access of the unrolled body is [pointer + compile-time offset]
+    const double* xl = ctr + (K - j) * STRIDE;         // tap u reloads pl[u] = x[u + K - j]
+    const double* xr = ctr + (j - 1) * STRIDE;         //              and pr[K-1-u] = x[j - u - 1]
+    const double* wj = tp + j;                         // its weight is wj[-u]
+    // window state at the entry point: slot p of pl was reloaded by the skipped taps u < u0 (x[p + K - j]) or still
+    // holds x[p - j]; slot p of pr was reloaded by u = K-1-p < u0 (x[p + j - K]) or still holds x[p + j]
+#define MB_WIN(U0)                                                                                  \
+    _Pragma("unroll") for (int p = 0; p < K; ++p) {                                                 \
+        pl[p] = xl[(p < (U0) ? p : p - K) * STRIDE];                                                \
+        pr[p] = xr[(p + 1 - ((K - 1 - p) < (U0) ? K : 0)) * STRIDE];                                \
     }
-    int j = R;
-    for (; j >= K; j -= K) {
-#pragma unroll
-        for (int u = 0; u < K; ++u) {
-            const double w = tp[j - u];
-            double t[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);
-#pragma unroll
-            for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);
-            pl[u % K] = ctr[(u + K - j) * stride];
-            pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
-        }
+    switch (u0) {
+        case 0: MB_WIN(0) break;
+        case 1: MB_WIN(1) break;
+        case 2: MB_WIN(2) break;
+        case 3: MB_WIN(3) break;
+        case 4: MB_WIN(4) break;
+        case 5: MB_WIN(5) break;
+        case 6: MB_WIN(6) break;
+        default: MB_WIN(7) break;
     }
-#pragma unroll
-    for (int u = 0; u < K - 1; ++u) {
-        if (u < j) {
-            const double w = tp[j - u];
-            double t[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);
-#pragma unroll
-            for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);
-            pl[u % K] = ctr[(u + K - j) * stride];
-            pr[(K - 1 - u) % K] = ctr[(j - u - 1) * stride];
-        }
+#undef MB_WIN
+#define MB_TAP(u)                                                                                              \
+    {                                                                                                          \
+        const double w = wj[-(u)];                                                                             \
+        double t[K];                                                                                           \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);  \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);                               \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);                        \
+        pl[u % K] = xl[(u) * STRIDE];                                                                          \
+        pr[(K - 1 - u) % K] = xr[-(u) * STRIDE];                                                               \
     }
+    switch (u0) {
+        case 0: do { MB_TAP(0)
+        case 1: MB_TAP(1)
+        case 2: MB_TAP(2)
+        case 3: MB_TAP(3)
+        case 4: MB_TAP(4)
+        case 5: MB_TAP(5)
+        case 6: MB_TAP(6)
+        case 7: MB_TAP(7)
+                xl += K * STRIDE; xr -= K * STRIDE; wj -= K;
+                j -= K; } while (j > 0);
+    }
+#undef MB_TAP
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -242,56 +267,63 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
 //
 // Every Gaussian of the chain is an independent convolution of the SAME tile (mustache.py:719,725,734,751 all pass `c`),
 // and in scipy's folded sum  out = x0*w0; for j = R..1: out += (x[-j] + x[j]) * w[j]  the pair sum (x[-j] + x[j]) does
-// not depend on the step.  The steps are therefore processed in groups of KV_G (sorted by radius, mb_engine.cu:
-// plan_kv): a thread owns KV_K consecutive rows of one column, walks j from the group's largest radius down to 1, forms
-// each pair sum once and feeds it to every step of the group whose radius reaches j.  Per step the order of the
-// additions is still j = R..1, so every result is bit-identical to scipy's; the FP64 instruction count per output drops
-// from sum(3R+1) to sum(2R+1) + sum over groups of max R  (2415 -> 1778 for 4 octaves, 532 -> 399 for 2).
-// The walk is split into KV_G segments: in segment a (radii (R[a-1], R[a]]) the steps a..KV_G-1 are active, so the
-// accumulators keep static register names and the only per-tap predicate is the segment end.
+// not depend on the step.  The steps are therefore processed in groups (KvPlan): a thread owns KV_K consecutive rows
+// of one column, walks j from the group's largest radius down to 1, forms each pair sum once and feeds it to every
+// step of the group.  Per step the additions still run j = R..1 (preceded by exact zeros), so every result is
+// bit-identical to scipy's; the FP64 instruction count per output drops from sum(3R+1) = 2415 to 1987 for 4 octaves
+// (532 -> 431 for 2).  The tap loop has no step-dependent control flow: four taps per trip from windows loaded once.
 // ---------------------------------------------------------------------------------------------------------------
-template <int A>
-__device__ __forceinline__ void kv_segment(const double* __restrict__ ctr, const double* __restrict__ tp, const int hiR,
-                                           const int loR, double (&acc)[KV_G][KV_K]) {
-    // taps are handled four at a time from windows loaded once: xl[m] = x[m - jc], xr[m] = x[jc - 3 + m]
-    for (int jc = hiR; jc > loR; jc -= 4) {
+template <int N>
+__device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const double* __restrict__ tp, const int rtop,
+                                         const int* __restrict__ steps, double* __restrict__ vrow, const long long step_stride,
+                                         const int kstride, const unsigned vmask) {
+    double acc[N][KV_K];
+#pragma unroll
+    for (int k = 0; k < KV_K; ++k) {
+        const double x = ctr[k * KV_TW];
+#pragma unroll
+        for (int s = 0; s < N; ++s) acc[s][k] = __dmul_rn(x, tp[s]);
+    }
+    // windows of a trip: xl[m] = x[m - jc], xr[m] = x[jc - 3 + m]; tap j = jc - u pairs xl[k + u] with xr[k + 3 - u].
+    // Running pointers keep every access of the trip at [pointer + compile-time offset].
+    const double* pl = ctr - rtop * KV_TW;
+    const double* pr = ctr + (rtop - 3) * KV_TW;
+    const double* pw = tp + rtop * N;
+    for (int jc = rtop; jc > 0; jc -= 4) {
         double xl[KV_K + 3], xr[KV_K + 3];
 #pragma unroll
         for (int m = 0; m < KV_K + 3; ++m) {
-            xl[m] = ctr[(m - jc) * KV_TW];
-            xr[m] = ctr[(jc - 3 + m) * KV_TW];
+            xl[m] = pl[m * KV_TW];
+            xr[m] = pr[m * KV_TW];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = jc - u;
-            if (j > loR) {
+            if (jc - u > 0) {
                 double t[KV_K];
 #pragma unroll
                 for (int k = 0; k < KV_K; ++k) t[k] = __dadd_rn(xl[k + u], xr[k + 3 - u]);
 #pragma unroll
-                for (int s = A; s < KV_G; ++s) {
-                    const double w = tp[j * KV_G + s];
+                for (int s = 0; s < N; ++s) {
+                    const double w = pw[s - u * N];
 #pragma unroll
                     for (int k = 0; k < KV_K; ++k) acc[s][k] = __dadd_rn(acc[s][k], __dmul_rn(t[k], w));
                 }
             }
         }
+        pl += 4 * KV_TW;
+        pr -= 4 * KV_TW;
+        pw -= 4 * N;
+    }
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+        double* vout = vrow + steps[s] * step_stride;
+#pragma unroll
+        for (int k = 0; k < KV_K; ++k) {
+            if (vmask & (1u << k)) *vout = acc[s][k];
+            vout += kstride;
+        }
     }
 }
-
-template <int A>
-struct KvSegments {
-    static __device__ __forceinline__ void run(const double* __restrict__ ctr, const double* __restrict__ tp,
-                                               const KvGroup& gr, double (&acc)[KV_G][KV_K]) {
-        kv_segment<A>(ctr, tp, gr.R[A], A > 0 ? gr.R[A > 0 ? A - 1 : 0] : 0, acc);   // radii (R[A-1], R[A]]
-        KvSegments<A - 1>::run(ctr, tp, gr, acc);
-    }
-};
-template <>
-struct KvSegments<-1> {
-    static __device__ __forceinline__ void run(const double* __restrict__, const double* __restrict__, const KvGroup&,
-                                               double (&)[KV_G][KV_K]) {}
-};
 
 __global__ void __launch_bounds__(KV_THREADS, 2)
 kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
@@ -326,6 +358,9 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     }
     __syncthreads();
 
+    const long long step_stride = (long long)g.nblk * g.plane_v;
+    double* const vblock = g.V + (long long)b * g.plane_v;
+    const int kstride = g.wv - 1;                   // output k + 1 sits kstride elements after output k
     for (int sub = 0; sub < KV_TH / 32; ++sub) {
         const int rb = sub * 32 + warp * KV_K;      // first tile row of this thread's KV_K outputs
         const int i = i0 + rb;
@@ -338,28 +373,17 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
             const int d = j - (i + k);
             if (i + k < g.n && j < g.n && d >= g.vlo && d <= vhi) vmask |= 1u << k;
         }
-        const long long off0 = (long long)i * g.wv + (j - i - g.vlo);      // output k sits at off0 + k * (wv - 1)
+        double* const vrow = vblock + ((long long)i * g.wv + (j - i - g.vlo));
         for (int gi = 0; gi < plan.n_groups; ++gi) {
             const KvGroup& gr = plan.grp[gi];
             if (dmax_w < 2 - gr.rmax || dmin_w > g.dhi + 2 + gr.rmax) continue;     // warp-uniform: nobody reads these
             const double* tp = plan.tapsT + gr.tap_off;
-            double acc[KV_G][KV_K];
-#pragma unroll
-            for (int k = 0; k < KV_K; ++k) {
-                const double x = ctr[k * KV_TW];
-#pragma unroll
-                for (int s = 0; s < KV_G; ++s) acc[s][k] = __dmul_rn(x, tp[s]);
-            }
-            KvSegments<KV_G - 1>::run(ctr, tp, gr, acc);
-#pragma unroll
-            for (int s = 0; s < KV_G; ++s) {
-                const int step = gr.step[s];
-                if (step >= 0) {
-                    double* vout = g.V + ((size_t)step * g.nblk + b) * g.plane_v + off0;
-#pragma unroll
-                    for (int k = 0; k < KV_K; ++k)
-                        if (vmask & (1u << k)) vout[(long long)k * (g.wv - 1)] = acc[s][k];
-                }
+            switch (gr.n) {
+                case 1: kv_group<1>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 2: kv_group<2>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 3: kv_group<3>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 4: kv_group<4>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                default: kv_group<5>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
             }
         }
     }
@@ -440,6 +464,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     uint64_t* full = reinterpret_cast<uint64_t*>(vbuf + kh_ring_doubles(rmax));    // [n_steps] bytes landed (used once)
     uint64_t* empty = full + MB_MAX_STEPS;                      // [n_steps] every warp is done reading the box (used once)
     double* xbuf = reinterpret_cast<double*>(empty + MB_MAX_STEPS) + (threadIdx.x >> 5) * (KH_TR * KH_XP);   // per warp [32][9]
+    __shared__ unsigned s_ticket;
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -462,8 +487,15 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         mbar_init(&full[t], 1);
         mbar_init(&empty[t], NW);
     }
+    if (threadIdx.x == 0) s_ticket = (MODE == KH_DEBUG) ? 0u : atomicAdd(g.sm_ticket + (sm_id() & (MB_MAX_SMS - 1)), 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    // Every CTA does the same work, so the two CTAs of an SM would run the FP64-dense tap loops and the barrier / store
+    // phases in lockstep, and the small-radius steps (mostly overhead) at the same time.  Every other CTA that arrives
+    // on an SM therefore walks the chain downwards: L_s = G_{s-1} - G_s is formed when its second operand is done,
+    // whichever comes last, so the result is the same bit for bit.
+    const int dir = (int)(s_ticket & 1u);
+    const int n_steps = prog.n_steps;
     // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
                             (js + warp * KH_K < g.n);
@@ -498,20 +530,22 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     }
     const int qstride = 4 * (pitch - 1);
 
-    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
-    // into its slot of the ring, after every warp released the boxes it overlaps.
+    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of the
+    // step at walk position p into its slot of the ring, after every warp released the boxes it overlaps.
+    auto step_at = [&](int p) { return dir ? n_steps - 1 - p : p; };
+    const MbStage* stg = prog.stage[dir];
     int next_issue = 0;
-    auto issue_ready = [&](int s_now) {
-        while (next_issue < prog.n_steps && next_issue <= s_now + KH_LOOKAHEAD) {
-            const int dep = prog.stage[next_issue].dep;
-            if (dep >= s_now) break;                            // the overlapped box is still ahead of this warp
+    auto issue_ready = [&](int p_now) {
+        while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
+            const int dep = stg[next_issue].dep;
+            if (dep >= p_now) break;                            // the overlapped box is still ahead of this warp
             if (elect_one()) {
-                if (dep >= 0) mbar_wait(&empty[dep], 0);
-                const int s = next_issue;
+                if (dep >= 0) mbar_wait(&empty[step_at(dep)], 0);
+                const int s = step_at(next_issue);
                 const int R = prog.st[s].radius;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
                 // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
-                tma_load_box3d(vbuf + prog.stage[s].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+                tma_load_box3d(vbuf + stg[next_issue].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
             }
             ++next_issue;
         }
@@ -521,16 +555,16 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     double gA[KH_K], gB[KH_K];
 #pragma unroll
     for (int k = 0; k < KH_K; ++k) gA[k] = gB[k] = 0.0;
-    int ndiff = 0;
 
-    auto step = [&](const int s, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
+    // walk position p: Gaussian of step s = step_at(p) into gnew; gprev holds the Gaussian of the previous position
+    auto step = [&](const int p, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
+        const int s = step_at(p);
         const int R = prog.st[s].radius;
-        const int flags = prog.st[s].flags;
-        double* vst = vbuf + (border ? 0 : prog.stage[s].off);
+        double* vst = vbuf + (border ? 0 : stg[p].off);
         const int bw = kh_box_width(R);                          // row pitch of this step's staged box
         const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-            if (warp == 0) issue_ready(s);
+            if (warp == 0) issue_ready(p);
             mbar_wait(&full[s], 0);
         } else {
             __syncthreads();                                     // previous step's readers are done with the buffer
@@ -551,7 +585,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             __syncthreads();
         }
         if (chunk_live && row_in) {
-            conv_slide<KH_K>(vst + lane * bw + shift + c0 + R, 1, R, prog.taps + prog.st[s].tap_off, gnew);
+            conv_slide<KH_K, 1>(vst + lane * bw + shift + c0 + R, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
@@ -569,48 +603,65 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 }
             }
         }
+        // the DoG completed now: L_sl = G_{sl-1} - G_sl with sl = s walking up, s + 1 walking down
+        const int sl = dir ? s + 1 : s;
+        if (sl >= n_steps) return;                               // first position of a downward walk
+        const int flags = prog.st[sl].flags;
         const bool formed = !(flags & MB_FLAG_RESTART);
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
         if (keep && chunk_live) {
             // columns past the image hold the maximum filter's cval 0
+            if (dir) {
 #pragma unroll
-            for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gnew[k], gprev[k]) : 0.0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+            }
             __syncwarp();
-            double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)ndiff * g.nblk + b) * g.n * g.wc
-                                            : g.L + ((size_t)s * g.nblk + b) * g.plane_l;
+            double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)prog.st[sl].score_idx * g.nblk + b) * g.n * g.wc
+                                            : g.L + ((size_t)sl * g.nblk + b) * g.plane_l;
             dst += qoff0;
+            const double* xrd = xbuf + (lane >> 3) * KH_XP + kk;
 #pragma unroll
             for (int q = 0; q < KH_TR / 4; ++q) {
                 if (qmask & (1u << q)) {
-                    const double l = xbuf[(4 * q + (lane >> 3)) * KH_XP + kk];
-                    dst[q * qstride + ((q >> 1) & 1)] = l;
+                    const double l = xrd[4 * q * KH_XP];
+                    dst[(q >> 1) & 1] = l;
                     if (MODE == KH_DEBUG) {
-                        if (g.dbgL != nullptr && s == g.dbg_step && b == 0) {
+                        if (g.dbgL != nullptr && sl == g.dbg_step && b == 0) {
                             const int ii = i0 + 4 * q + (lane >> 3), jj = js + warp * KH_K + kk + ((q >> 1) & 1);
                             if (jj < g.n) g.dbgL[(size_t)ii * g.n + jj] = l;
                         }
                     }
                 }
+                dst += qstride;
             }
             __syncwarp();
         }
-        if (MODE == KH_DIFF && keep) ++ndiff;
     };
 
-    int s = 0;
-    for (; s + 1 < prog.n_steps; s += 2) {
-        step(s, gB, gA);
-        step(s + 1, gA, gB);
+    int p = 0;
+    for (; p + 1 < n_steps; p += 2) {
+        step(p, gB, gA);
+        step(p + 1, gA, gB);
     }
-    if (s < prog.n_steps) step(s, gB, gA);
+    if (p < n_steps) step(p, gB, gA);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K_S (ks_kernel): 3x3 maxima, 5-clause extremum test, running best and |L| statistics, streaming the DoG levels from
-// HBM.  grid = (column tiles, row tiles, blocks); tile = 30 x 62 scored pixels + 1-pixel halo; thread (lane = tile row,
-// warp = 8 tile columns) owns 8 pixels for the whole chain and keeps their state in registers (best response, winning
-// level, own value and maxima of the two previous DoGs).  Each level's tile rows arrive by TMA bulk copies into a
-// two-stage ring, prefetched one level ahead.  Everything is exact FP64 comparison; the kernel is HBM/latency bound.
+// K_S (ks_kernel): zero-padded 3x3 maxima, 5-clause extremum test, running best and |L| statistics, streaming the DoG
+// levels from HBM.  grid = (column tiles, row tiles, blocks); tile = 30 x 62 scored pixels + 1-pixel halo; thread (lane =
+// tile row, warp = 8 tile columns) owns 8 pixels for the whole chain and keeps their state in registers (best response,
+// winning level, own value of the previous DoG, "is a 3x3 maximum" bits of the two previous DoGs).  One TMA box per
+// level into a KS_DEPTH-stage ring (full/empty mbarriers), two levels in flight while one is scored.
+//
+// The maximum filters are never materialised.  "L == max3x3(L)" (mustache.py:762-763) is "L >= its 8 neighbours" (the
+// zero padding of mode='constant' is in the staged tile: rows outside the image arrive as zeros from the TMA, columns
+// past it were written as zeros by kh_kernel) -- 8 chained compares per pixel and level.  The two strict clauses
+// "Lc > max3x3(Lp)" and "Lc > max3x3(Ln)" (mustache.py:764-765) only matter for the few pixels that pass the cheap
+// clauses first; for those the 9 values of the next level are already in registers and the 9 of the previous level are
+// still in its ring stage (a stage is released two levels after it was filled).  Everything is exact FP64 comparison.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KS_THREADS, 2)
 ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
@@ -618,7 +669,8 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     constexpr int NW = KS_THREADS / 32;
     constexpr int PL = KS_PITCH;                                // even, == 2 (mod 4)
     constexpr int D = KS_DEPTH;
-    double* lst = smem;                                         // [D][KS_TR][PL]   staged DoG rows
+    constexpr int AHEAD = D - 3;                                // levels in flight beyond the one being scored
+    double* lst = smem;                                         // [D][KS_TR][PL]   staged DoG tiles
     double* pmin = lst + D * KS_TR * PL;                        // [n_scored][NW] per-warp min of |L|
     double* psum = pmin + (size_t)max(prog.n_scored, 1) * NW;   // [n_scored][NW] per-warp sum of |L|
     uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * NW);   // [D]
@@ -648,12 +700,13 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     const bool row_in = (i >= 0) && (i < g.n);
     const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
 
-    // the staged tile is a dense [KS_TR][PL] box; rows outside the image are out of bounds for the TMA and arrive as the
-    // maximum filter's cval 0
+    // the staged tile is a dense [KS_TR][PL] box; the box starts on the even column below tile column 0
     const int x_first = js - 1 - 2;                     // column index (skewed view of L) of tile column 0
-    const int off_c = lane * PL + (x_first & 1) + c0;   // the box starts on the even column below
-    const int off_u = off_c - PL;
-    const int off_d = off_c + PL;
+    const int off_c = lane * PL + (x_first & 1) + c0;
+    // the columns left of tile column 0 / right of column 63 are not staged: the edge warps clamp them (they only feed
+    // the halo pixels, which are never scored)
+    const int cl = (warp == 0) ? 0 : -1;
+    const int cr = (warp == NW - 1) ? KS_K - 1 : KS_K;
 
     if (threadIdx.x == 0) {
         for (int d = 0; d < D; ++d) {
@@ -676,7 +729,8 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         }
     }
 
-    // Producer side (one thread): the DoG tile of step s, the nl-th level of the stream, into stage nl % D
+    // Producer side (one thread): the DoG tile of step s, the nl-th level of the stream, into stage nl % D.  The stage's
+    // previous tile (level nl - D) was released by every warp after it scored level nl - D + 2.
     auto issue = [&](int s, int nl) {
         const int u = nl / D, st = nl - u * D;
         if (u > 0) mbar_wait(&empty[st], (u - 1) & 1);
@@ -689,63 +743,81 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         return s;
     };
 
-    double vbest[KS_K], lA[KS_K], lB[KS_K], mA[KS_K], mB[KS_K];
+    double vbest[KS_K], lA[KS_K], lB[KS_K];
     unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
 #pragma unroll
-    for (int k = 0; k < KS_K; ++k) { vbest[k] = 0.0; lA[k] = lB[k] = mA[k] = mB[k] = 0.0; }
+    for (int k = 0; k < KS_K; ++k) { vbest[k] = 0.0; lA[k] = lB[k] = 0.0; }
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
     int s_issue = next_formed(-1), nl_issue = 0;        // producer cursor (warp 0, uniform)
 
-    // One DoG level.  Register arrays alternate roles between consecutive levels (the loop is unrolled by two): lcur belongs
-    // to the previous level, mold holds the maxima of the level before that and is overwritten with this level's.
-    auto level = [&](const int s, const int nl, const double (&lcur)[KS_K], double (&lown)[KS_K], double (&mold)[KS_K]) {
+    // One DoG level (stream position nl).  lcur holds the own values of level nl-1 (the one being scored), lown receives
+    // those of level nl; the two register arrays swap roles between consecutive levels (the loop is unrolled by two).
+    auto level = [&](const int s, const int nl, const double (&lcur)[KS_K], double (&lown)[KS_K]) {
         const int flags = prog.st[s].flags;
-        if (warp == 0 && s_issue < prog.n_steps) {              // keep D-1 levels in flight; the cursor stays warp-uniform
+        if (warp == 0 && s_issue < prog.n_steps) {              // the cursor stays warp-uniform
             if (elect_one()) issue(s_issue, nl_issue);
             s_issue = next_formed(s_issue);
             ++nl_issue;
         }
         const int u = nl / D, st_i = nl - u * D;
         mbar_wait(&full[st_i], u & 1);
-        const double* st = lst + st_i * (KS_TR * PL);
+        const double* st = lst + st_i * (KS_TR * PL) + off_c;                           // level nl, own pixel 0
+        int sp_i = st_i - 2;
+        if (sp_i < 0) sp_i += D;
+        const double* sp = lst + sp_i * (KS_TR * PL) + off_c;                           // level nl-2, own pixel 0
         unsigned e_new = 0;
         double tmin = kInf, tsum = 0.0;
         const bool score = (flags & MB_FLAG_SCORE) != 0;
         const int sidx = prog.st[s].score_idx;
         if (row_scored) {
-            double vm[KS_K + 2];
-#pragma unroll
-            for (int k = 0; k < KS_K; ++k) lown[k] = st[off_c + k];
-#pragma unroll
-            for (int t = 0; t < KS_K + 2; ++t) {
-                int c = t - 1;                                          // column relative to the first owned pixel
-                if (t == 0 && warp == 0) c = 0;                         // clamped columns only feed halo pixels
-                if (t == KS_K + 1 && warp == NW - 1) c = KS_K - 1;
-                const double a1 = (t >= 1 && t <= KS_K) ? lown[t - 1] : st[off_c + c];
-                vm[t] = dmax(dmax(st[off_u + c], a1), st[off_d + c]);
-            }
-            const unsigned cand = score ? (mask & e_cur) : 0u;
+            double o[KS_K + 2], up[KS_K + 2], dn[KS_K + 2];      // rows i, i-1, i+1, tile columns c0-1 .. c0+8
+            o[0] = st[cl]; up[0] = st[cl - PL]; dn[0] = st[cl + PL];
+            o[KS_K + 1] = st[cr]; up[KS_K + 1] = st[cr - PL]; dn[KS_K + 1] = st[cr + PL];
 #pragma unroll
             for (int k = 0; k < KS_K; ++k) {
-                const unsigned bit = 1u << k;
-                const double mnew = dmax(dmax(vm[k], vm[k + 1]), vm[k + 2]);
-                const bool en = (lown[k] == mnew);
-                if (en) e_new |= bit;
-                if (score && (mask & bit)) {
-                    const double a = fabs(lcur[k]);
-                    tmin = dmin(tmin, a);
-                    tsum = __dadd_rn(tsum, a);
+                o[k + 1] = st[k];
+                up[k + 1] = st[k - PL];
+                dn[k + 1] = st[k + PL];
+            }
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) {
+                const double x = o[k + 1];
+                lown[k] = x;
+                const bool en = (x >= o[k]) && (x >= o[k + 2]) && (x >= up[k]) && (x >= up[k + 1]) && (x >= up[k + 2]) &&
+                                (x >= dn[k]) && (x >= dn[k + 1]) && (x >= dn[k + 2]);
+                if (en) e_new |= 1u << k;
+            }
+            if (score) {
+                const unsigned cand = mask & e_cur & (e_prev | e_new);      // mustache.py:762-763
+#pragma unroll
+                for (int k = 0; k < KS_K; ++k) {
+                    const unsigned bit = 1u << k;
+                    const double x = lcur[k];
+                    if (mask & bit) {                                       // expon.fit over the mask, mustache.py:755
+                        const double a = fabs(x);
+                        tmin = dmin(tmin, a);
+                        tsum = __dadd_rn(tsum, a);
+                    }
+                    if ((cand & bit) && x > vbest[k]) {                     // mustache.py:761
+                        // mustache.py:765  Lc > max3x3(Ln): the next level's 3x3 block is in registers
+                        bool ok = (x > o[k]) && (x > o[k + 1]) && (x > o[k + 2]) && (x > up[k]) && (x > up[k + 1]) &&
+                                  (x > up[k + 2]) && (x > dn[k]) && (x > dn[k + 1]) && (x > dn[k + 2]);
+                        if (ok) {
+                            // mustache.py:764  Lc > max3x3(Lp): the previous level's tile is still staged
+                            const double* q = sp + k;
+                            ok = (x > q[-1]) && (x > q[0]) && (x > q[1]) && (x > q[-PL - 1]) && (x > q[-PL]) && (x > q[-PL + 1]) &&
+                                 (x > q[PL - 1]) && (x > q[PL]) && (x > q[PL + 1]);
+                            if (ok) {
+                                vbest[k] = x;
+                                lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
+                            }
+                        }
+                    }
                 }
-                // mustache.py:760-765
-                if ((cand & bit) && (en || (e_prev & bit)) && lcur[k] > vbest[k] && lcur[k] > mold[k] && lcur[k] > mnew) {
-                    vbest[k] = lcur[k];
-                    lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
-                }
-                mold[k] = mnew;
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st_i]);               // this warp is done with the stage
+        if (nl >= 2 && lane == 0) mbar_arrive(&empty[sp_i]);    // this warp is done with level nl-2
         if (score) {                                            // per-warp statistics, fixed order (deterministic)
             tmin = warp_min(tmin);
             tsum = warp_sum(tsum);
@@ -758,8 +830,8 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         e_cur = e_new;
     };
 
-    if (warp == 0) {                                            // prologue: D-1 levels in flight before the first wait
-        for (int q = 0; q < D - 1 && s_issue < prog.n_steps; ++q) {
+    if (warp == 0) {                                            // prologue: AHEAD levels in flight before the first wait
+        for (int q = 0; q < AHEAD && s_issue < prog.n_steps; ++q) {
             if (elect_one()) issue(s_issue, nl_issue);
             s_issue = next_formed(s_issue);
             ++nl_issue;
@@ -767,10 +839,10 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     }
     int s = next_formed(-1), nl = 0;
     while (s < prog.n_steps) {
-        level(s, nl, lB, lA, mA);               // even level: own values into lA, maxima into mA (held level nl-2)
+        level(s, nl, lB, lA);                   // even level: own values into lA
         s = next_formed(s); ++nl;
         if (s >= prog.n_steps) break;
-        level(s, nl, lA, lB, mB);
+        level(s, nl, lA, lB);
         s = next_formed(s); ++nl;
     }
     __syncthreads();

@@ -7,8 +7,11 @@
 template <int MODE>
 __global__ void __launch_bounds__(256) k(double* out, double a, double b, int iters) {
     double x[16];
+    unsigned y[8];
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = a + threadIdx.x * 1e-9 + i;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = threadIdx.x * 2654435761u + i;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -17,11 +20,20 @@ __global__ void __launch_bounds__(256) k(double* out, double a, double b, int it
             if (MODE == 2) x[i] = __fma_rn(x[i], b, a);
             if (MODE == 3) x[i] = __dadd_rn(x[i], __dmul_rn(__dadd_rn(x[(i + 1) & 15], x[(i + 5) & 15]), b));   // one folded tap
             if (MODE == 4) x[i] = (x[i] > x[(i + 1) & 15]) ? x[i] : x[(i + 1) & 15];
+            if (MODE >= 5) {                 // issue-slot model: 16 DADD + MIX integer instructions per trip
+                x[i] = __dadd_rn(x[i], b);
+                constexpr int MIX = (MODE == 5) ? 4 : (MODE == 6) ? 8 : 16;
+                if (i < MIX) y[i & 7] = (y[i & 7] ^ y[(i + 1) & 7]) + y[(i + 3) & 7];      // LOP3 + IADD
+            }
         }
     }
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += x[i];
+    if (MODE >= 5) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += y[i];
+    }
     if (s == 123.456) out[0] = s;
 }
 
@@ -59,5 +71,8 @@ int main() {
     run<2>("dfma", 1);
     run<3>("tap(dadd,dmul,dadd)", 3);
     run<4>("dsetp+sel(max)", 1);
+    run<5>("16 dadd + 8 int instr per trip (fp64 rate)", 1);
+    run<6>("16 dadd + 16 int instr per trip (fp64 rate)", 1);
+    run<7>("16 dadd + 32 int instr per trip (fp64 rate)", 1);
     return 0;
 }

@@ -151,7 +151,7 @@ constexpr int KS_THREADS = (KS_TC / KS_K) * 32;   // 256
 constexpr int KS_SR = KS_TR - 2;   // scored rows per CTA
 constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
 constexpr int KS_PITCH = KS_TC + 2;   // 66: box width of the staged DoG tile, == 2 (mod 4)
-constexpr int KS_DEPTH = 5;           // ring stages per CTA: level being scored, the two before it, two in flight
+constexpr int KS_DEPTH = 6;           // ring stages per CTA: level being scored, the two before it, three in flight
 
 // width of the staged box of a step with radius R: the filter support of the tile plus one element (the box must start
 // on an even column: TMA needs 16-byte aligned box rows), padded to 2 (mod 4) elements so that the dense rows the TMA
@@ -341,19 +341,31 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = j0 + lane;
 
-    // stage the filled tile (mustache.py:703-706 applied on the fly), 'reflect' rows: one warp per tile row
+    // stage the filled tile (mustache.py:703-706 applied on the fly), 'reflect' rows: one warp per tile row, 16 rows
+    // (= 16 independent loads per thread) in flight at a time
     {
         const double* rawb = g.raw + (size_t)b * g.n * g.wc;
         const int rows = KV_TH + 2 * rmax;
-#pragma unroll 4
-        for (int r = warp; r < rows; r += KV_THREADS / 32) {
-            // rows past n - 1 + rmax feed no stored output: clamped so that the reflection stays inside the tile
-            const int ii = reflect_idx(min(i0 - rmax + r, g.n - 1 + rmax), g.n);
-            const int d = j - ii;
-            double val = g.fill;                                    // d <= 4, or intra and d >= dpx + 1
-            if (j >= g.n) val = 0.0;                                // never used by a stored output
-            else if (d > 4 && !(g.intra && d >= g.dpx + 1)) val = (d > g.dhi) ? 0.0 : rawb[ii * g.wc + (d - 4)];
-            cs[r * KV_TW + lane] = val;
+        constexpr int NWARP = KV_THREADS / 32, BATCH = 16;
+        for (int r0 = warp; r0 < rows; r0 += NWARP * BATCH) {
+            double v[BATCH];
+#pragma unroll
+            for (int q = 0; q < BATCH; ++q) {
+                const int r = r0 + q * NWARP;
+                // rows past n - 1 + rmax feed no stored output: clamped so that the reflection stays inside the tile
+                const int ii = reflect_idx(min(i0 - rmax + min(r, rows - 1), g.n - 1 + rmax), g.n);
+                const int d = j - ii;
+                const bool banded = (j < g.n) && (d > 4) && (d <= g.dhi) && !(g.intra && d >= g.dpx + 1);
+                double val = g.fill;                                // d <= 4, or intra and d >= dpx + 1
+                if (j >= g.n || (d > g.dhi && !(g.intra && d >= g.dpx + 1))) val = 0.0;   // never used by a stored output
+                if (banded) val = rawb[ii * g.wc + (d - 4)];
+                v[q] = val;
+            }
+#pragma unroll
+            for (int q = 0; q < BATCH; ++q) {
+                const int r = r0 + q * NWARP;
+                if (r < rows) cs[r * KV_TW + lane] = v[q];
+            }
         }
     }
     __syncthreads();
@@ -529,6 +541,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         qoff0 = (i0 + r0) * (pitch - 1) + jw - dlo;             // row*pitch + (d - dlo) = row*(pitch-1) + col - dlo
     }
     const int qstride = 4 * (pitch - 1);
+    // warp-uniform: no pixel of the chunk needs a mask (true for all but the tiles on the band / image edges)
+    const bool interior = __all_sync(0xffffffffu, zmask == (1u << KH_K) - 1u && qmask == (1u << (KH_TR / 4)) - 1u);
 
     // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of the
     // step at walk position p into its slot of the ring, after every warp released the boxes it overlaps.
@@ -610,32 +624,46 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const bool formed = !(flags & MB_FLAG_RESTART);
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
         if (keep && chunk_live) {
-            // columns past the image hold the maximum filter's cval 0
-            if (dir) {
-#pragma unroll
-                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gnew[k], gprev[k]) : 0.0;
-            } else {
-#pragma unroll
-                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-            }
-            __syncwarp();
             double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)prog.st[sl].score_idx * g.nblk + b) * g.n * g.wc
                                             : g.L + ((size_t)sl * g.nblk + b) * g.plane_l;
             dst += qoff0;
             const double* xrd = xbuf + (lane >> 3) * KH_XP + kk;
+            if (MODE != KH_DEBUG && interior) {
+                // every pixel of the warp's chunk is inside the image and on a stored diagonal: no masks
+                if (dir) {
 #pragma unroll
-            for (int q = 0; q < KH_TR / 4; ++q) {
-                if (qmask & (1u << q)) {
-                    const double l = xrd[4 * q * KH_XP];
-                    dst[(q >> 1) & 1] = l;
-                    if (MODE == KH_DEBUG) {
-                        if (g.dbgL != nullptr && sl == g.dbg_step && b == 0) {
-                            const int ii = i0 + 4 * q + (lane >> 3), jj = js + warp * KH_K + kk + ((q >> 1) & 1);
-                            if (jj < g.n) g.dbgL[(size_t)ii * g.n + jj] = l;
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gnew[k], gprev[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gprev[k], gnew[k]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < KH_TR / 4; ++q) dst[(long long)q * qstride + ((q >> 1) & 1)] = xrd[4 * q * KH_XP];
+            } else {
+                // columns past the image hold the maximum filter's cval 0
+                if (dir) {
+#pragma unroll
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gnew[k], gprev[k]) : 0.0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < KH_TR / 4; ++q) {
+                    if (qmask & (1u << q)) {
+                        const double l = xrd[4 * q * KH_XP];
+                        dst[(q >> 1) & 1] = l;
+                        if (MODE == KH_DEBUG) {
+                            if (g.dbgL != nullptr && sl == g.dbg_step && b == 0) {
+                                const int ii = i0 + 4 * q + (lane >> 3), jj = js + warp * KH_K + kk + ((q >> 1) & 1);
+                                if (jj < g.n) g.dbgL[(size_t)ii * g.n + jj] = l;
+                            }
                         }
                     }
+                    dst += qstride;
                 }
-                dst += qstride;
             }
             __syncwarp();
         }

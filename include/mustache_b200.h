@@ -121,6 +121,15 @@ MB200_API int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t
 MB200_API int mb200_run_differential(mb200_engine* e);
 MB200_API int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair, int64_t* n_out);
 
+/* The producer of the tile values: per-diagonal z-score normalisation of one chromosome's contact list, the reference's
+ * normalize_sparse(x, y, v, resolution, distance_in_px) (mustache.py:622-686; both its windowed and its global branch).
+ * x, y: bin indices, v: bias-corrected counts, normalised in place (host pointers, nnz entries).  weights (capacity
+ * weights_cap, may be NULL) receives the reference's return value pval_weights, *n_weights its length.  np.mean / np.std
+ * are reproduced bit for bit (numpy's pairwise summation); the 2 Mb box sums are taken left to right, which differs in
+ * the last bits from the BLAS dot product behind np.convolve (whose order depends on the host CPU). */
+MB200_API int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, double* v, int64_t nnz,
+                                     int resolution, int distance_in_px, double* weights, int weights_cap, int* n_weights);
+
 /* Pinned host memory for callers that want full-speed uploads. */
 MB200_API int mb200_host_alloc(void** ptr, int64_t bytes);
 MB200_API int mb200_host_free(void* ptr);

@@ -2,8 +2,10 @@
 // lines each entry point replaces).  Owns one CUDA stream and grow-only device scratch; no torch types anywhere.
 #include "../../include/mustache_b200.h"
 #include "mb_kernels.cuh"
+#include "mb_normalize.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +44,8 @@ struct mb200_engine {
     long long rec_cap = 0;
     int ncta_h = 0;
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
-        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, sm_ticket;
+        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, sm_ticket,
+        nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
     bool counts_valid = false;
@@ -347,7 +350,8 @@ void mb200_destroy(mb200_engine* e) {
     DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
-                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps, &e->sm_ticket};
+                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps, &e->sm_ticket, &e->nz_xs, &e->nz_ds, &e->nz_perm,
+                     &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -897,6 +901,99 @@ int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, double* pair,
     if (!pair) return fail(e, MB200_ERR_ARG, "null output array");
     CU(e, cudaMemcpyAsync(pair, (double*)e->rec_pair.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, double* v, int64_t nnz, int resolution,
+                           int distance_in_px, double* weights, int weights_cap, int* n_weights) {
+    if (!e) return MB200_ERR_ARG;
+    if (n_weights) *n_weights = 0;
+    if (nnz < 0 || (nnz > 0 && (!x || !y || !v)) || resolution < 1 || distance_in_px < 0)
+        return fail(e, MB200_ERR_ARG, "bad arguments to mb200_normalize_sparse");
+    if (nnz == 0) return MB200_OK;
+    int st = use_device(e);
+    if (st) return st;
+    long long n = 0;
+    for (int64_t k = 0; k < nnz; ++k) {
+        if (x[k] < 0 || y[k] < 0) return fail(e, MB200_ERR_ARG, "negative bin index at contact %lld", (long long)k);
+        n = std::max<long long>(n, std::max(x[k], y[k]));
+    }
+    n += 1;                                                                   // mustache.py:623
+    const bool windowed = (n - distance_in_px) * (long long)resolution > 2000000;      // mustache.py:628
+    const long long D = windowed ? (long long)distance_in_px + 2 : std::min<long long>(distance_in_px, n);
+    // stable counting sort by diagonal; contacts the reference's loop never visits go to bucket D
+    std::vector<long long> seg(D + 2, 0);
+    std::vector<int> dd(nnz);
+    for (int64_t k = 0; k < nnz; ++k) {
+        const long long d = std::llabs((long long)y[k] - (long long)x[k]);
+        dd[k] = (int)std::min<long long>(d, D);
+        ++seg[dd[k] + 1];
+    }
+    for (long long d = 0; d <= D; ++d) seg[d + 1] += seg[d];
+    std::vector<long long> cur(seg.begin(), seg.end() - 1), perm(nnz);
+    std::vector<int> xs(nnz), ds(nnz);
+    std::vector<double> vs(nnz);
+    for (int64_t k = 0; k < nnz; ++k) {
+        const long long o = cur[dd[k]]++;
+        perm[o] = k;
+        xs[o] = x[k];
+        ds[o] = dd[k];
+        double val = v[k];
+        if (!windowed && !std::isfinite(val)) val = 0.0;                      // mustache.py:672
+        vs[o] = val;
+    }
+    const long long m = seg[D];                                               // contacts on the visited diagonals
+    if ((st = ensure(e, e->nz_xs, nnz * sizeof(int)))) return st;
+    if ((st = ensure(e, e->nz_ds, nnz * sizeof(int)))) return st;
+    if ((st = ensure(e, e->nz_perm, nnz * sizeof(long long)))) return st;
+    if ((st = ensure(e, e->nz_vs, nnz * sizeof(double)))) return st;
+    if ((st = ensure(e, e->nz_out, nnz * sizeof(double)))) return st;
+    if ((st = ensure(e, e->nz_seg, (D + 2) * sizeof(long long)))) return st;
+    if ((st = ensure(e, e->nz_mean, (D + 1) * sizeof(double)))) return st;
+    if ((st = ensure(e, e->nz_sd, (D + 1) * sizeof(double)))) return st;
+    if ((st = ensure(e, e->nz_w, (D + 1) * sizeof(double)))) return st;
+    cudaStream_t sq = e->stream;
+    CU(e, cudaMemcpyAsync(e->nz_xs.p, xs.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_ds.p, ds.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_perm.p, perm.data(), nnz * sizeof(long long), cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_vs.p, vs.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_seg.p, seg.data(), (D + 2) * sizeof(long long), cudaMemcpyHostToDevice, sq));
+    // pass-through for the contacts no diagonal loop visits: out starts as (cleaned) v in the caller's order
+    std::vector<double> base(nnz);
+    for (int64_t o = 0; o < nnz; ++o) base[perm[o]] = vs[o];
+    CU(e, cudaMemcpyAsync(e->nz_out.p, base.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, sq));
+    if (D > 0) {
+        nz_stats_kernel<<<(unsigned)((D + 63) / 64), 64, 0, sq>>>((const double*)e->nz_vs.p, (const long long*)e->nz_seg.p, (int)D,
+                                                                  (double*)e->nz_mean.p, (double*)e->nz_sd.p);
+        CU(e, cudaGetLastError());
+    }
+    const int grid = (int)std::min<long long>((m + 255) / 256, 148LL * 16);
+    if (windowed && m > 0) {
+        std::vector<double> mean(D), w(D);
+        CU(e, cudaMemcpyAsync(mean.data(), e->nz_mean.p, D * sizeof(double), cudaMemcpyDeviceToHost, sq));
+        CU(e, cudaStreamSynchronize(sq));
+        for (long long d = 0; d < D; ++d) w[d] = 1.0 + std::log(1.0 + mean[d]) / std::log(30.0);     // mustache.py:667-668
+        CU(e, cudaMemcpyAsync(e->nz_w.p, w.data(), D * sizeof(double), cudaMemcpyHostToDevice, sq));
+        if (weights)
+            for (long long d = 0; d < D && d < weights_cap; ++d) weights[d] = w[d];
+        if (n_weights) *n_weights = (int)D;
+        if ((st = ensure(e, e->nz_lines, (size_t)D * n * sizeof(double)))) return st;
+        CU(e, cudaMemsetAsync(e->nz_lines.p, 0, (size_t)D * n * sizeof(double), sq));
+        nz_fill_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_xs.p, (const int*)e->nz_ds.p, (const double*)e->nz_vs.p, m, n,
+                                             (double*)e->nz_lines.p);
+        CU(e, cudaGetLastError());
+        nz_window_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_xs.p, (const int*)e->nz_ds.p, (const long long*)e->nz_perm.p, m, n,
+                                               (int)(2000000 / resolution), (const double*)e->nz_lines.p,
+                                               (const double*)e->nz_mean.p, (const double*)e->nz_sd.p, (const double*)e->nz_w.p,
+                                               (double*)e->nz_out.p);
+        CU(e, cudaGetLastError());
+    } else if (m > 0) {
+        nz_global_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_ds.p, (const long long*)e->nz_perm.p, (const double*)e->nz_vs.p, m,
+                                               (int)D, (const double*)e->nz_mean.p, (const double*)e->nz_sd.p, (double*)e->nz_out.p);
+        CU(e, cudaGetLastError());
+    }
+    CU(e, cudaMemcpyAsync(v, e->nz_out.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, sq));
+    CU(e, cudaStreamSynchronize(sq));
     return MB200_OK;
 }
 

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import postprocess, readers, tiler
 from .mustache import HEADER, _dist_env, _set_octaves, format_row, get_engine, parseBP, resolve_distance
-from .normalize import normalize_sparse
+from .normalize import normalize
 
 _DIFF_KEY = {}
 
@@ -199,7 +199,7 @@ def regulator(f1, f2, norm_method, CHRM_SIZE, outdir, bed1="", bed2="", res=5000
     dpx = tiler.distance_in_px(distance_filter, res)
     n = int(max(max(m[0].max(), m[1].max()) + 1 for m in maps))
     for m in maps:
-        normalize_sparse(m[0], m[1], m[2], res, dpx)
+        normalize(m[0], m[1], m[2], res, dpx, eng=get_engine())
     if verbose:
         print("Loop calling...")
     return call_block_pairs(maps[0], maps[1], n, dpx, octave_values, st, pt, pt2, verbose=verbose, rank=rank, world=world)

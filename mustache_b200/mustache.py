@@ -20,7 +20,7 @@ import time
 import numpy as np
 
 from . import gather, postprocess, readers, tiler
-from .normalize import normalize_sparse
+from .normalize import normalize, normalize_sparse
 
 _ENGINES = {}
 _PROGRAM_KEY = {}
@@ -243,7 +243,7 @@ def regulator(f, norm_method, CHRM_SIZE, outdir, bed="", res=5000, sigma0=1.6, s
         print("Normalizing contact map...")
     dpx = tiler.distance_in_px(distance_in_bp, res)
     n = int(max(max(x), max(y)) + 1)
-    normalize_sparse(x, y, v, res, dpx)
+    normalize(x, y, v, res, dpx, eng=get_engine())
     if verbose:
         print("Loop calling...")
     return call_blocks(np.asarray(x), np.asarray(y), np.asarray(v), n, dpx, octave_values, st, pt, verbose=verbose,

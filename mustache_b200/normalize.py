@@ -1,10 +1,18 @@
 """Per-diagonal z-score normalisation of the sparse contact list (host side, numpy).
 
-Restates mustache.py:622-686 (`normalize_sparse`).  It runs BEFORE the hot path and is listed as the first
-"next" item in SURVEY.md section 8(f); until it moves to the device it is kept numerically identical to the
-reference (same np.convolve calls on the same sequences, same np.mean/np.std element order) because its output
-is the scale-space engine's input and parity is judged on the final loop list.
+`normalize_sparse` restates mustache.py:622-686 in numpy, numerically identical to the reference (same np.convolve
+calls on the same sequences, same np.mean/np.std element order): it is what the parity fixtures were produced with.
+`normalize_sparse_device` is the same function on the GPU (SURVEY.md section 8(f) item 1, C ABI
+mb200_normalize_sparse): np.mean / np.std bit for bit, the 2 Mb box sums to ~1e-13 (np.convolve's BLAS summation order
+is CPU dependent, so no implementation can match it bit for bit on every host).  On bias-corrected maps the two agree
+to ~1e-13 and give the same loops (chr21: 90 loops, FDR within 1e-6).  On raw integer counts (what diff_mustache.py
+feeds for map 1, quirk #13) the reference's z-scores inside windows of identical counts are rounding noise divided by
+rounding noise (val - mean ~ 1e-16, std ~ 1e-8), some of them NaN -> 0 -> off the mask: there the reference's own result
+depends on its BLAS build, and only the numpy path on the same host reproduces it.  The CLI therefore keeps the numpy
+normaliser by default and switches to the device one with MUSTACHE_NORMALIZE=device.
 """
+import ctypes as C
+import os
 import math
 import warnings
 
@@ -64,3 +72,29 @@ def normalize_sparse(x, y, v, resolution, distance_in_px):
                 v[on_diag] = (v[on_diag] - g_mean) / g_std
                 np.nan_to_num(v, copy=False, nan=0, posinf=0, neginf=0)
     return weights
+
+
+def normalize_sparse_device(eng, x, y, v, resolution, distance_in_px):
+    """normalize_sparse(x, y, v, resolution, distance_in_px) on the engine's GPU; `v` is normalised in place."""
+    from .engine import EngineError, _f64p, _i32p
+    xs = np.ascontiguousarray(x, dtype=np.int32)
+    ys = np.ascontiguousarray(y, dtype=np.int32)
+    vv = v if (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous) else np.ascontiguousarray(v, dtype=np.float64)
+    cap = int(distance_in_px) + 2
+    w = np.zeros(cap)
+    nw = C.c_int(0)
+    st = eng.lib.mb200_normalize_sparse(eng.h, xs.ctypes.data_as(_i32p), ys.ctypes.data_as(_i32p), vv.ctypes.data_as(_f64p),
+                                        len(vv), int(resolution), int(distance_in_px), w.ctypes.data_as(_f64p), cap,
+                                        C.byref(nw))
+    if st:
+        raise EngineError(st, eng.lib.mb200_last_error(eng.h).decode())
+    if vv is not v:
+        v[:] = vv
+    return list(w[:nw.value])
+
+
+def normalize(x, y, v, resolution, distance_in_px, eng=None):
+    """What the CLI calls: the numpy normaliser (reference-exact), or the device one when MUSTACHE_NORMALIZE=device."""
+    if os.environ.get("MUSTACHE_NORMALIZE", "host") != "device" or eng is None:
+        return normalize_sparse(x, y, v, resolution, distance_in_px)
+    return normalize_sparse_device(eng, x, y, v, resolution, distance_in_px)

@@ -48,9 +48,28 @@ def contact_bins(n, dpx):
 
 
 def fp64_instr_per_bin(octaves, dedupe=True):
+    """FP64 instructions per contact-bin of the two separable passes: with the reference's arithmetic as it stands
+    (scipy's folded taps, 3R+1 per output and pass), and as executed (the axis-0 pass shares the pair sums inside the
+    groups mb_engine.cu:plan_kv cuts: R*(2n+1)+n per group of n steps with largest radius R)."""
     from mustache_b200 import ladder
     prog = ladder.build_program(octaves, dedupe=dedupe)
-    return sum(2 * (3 * s.radius + 1) for s in prog.steps)
+    radii = sorted(s.radius for s in prog.steps)
+    reference = sum(2 * (3 * r + 1) for r in radii)
+    gmax, n = 5, len(radii)
+    best = [0] * (n + 1)
+    for i in range(n - 1, -1, -1):
+        best[i] = min(radii[i + c - 1] * (2 * c + 1) + c + best[i + c] for c in range(1, gmax + 1) if i + c <= n)
+    executed = best[0] + sum(3 * r + 1 for r in radii)
+    return reference, executed
+
+
+def load_traffic():
+    """DRAM bytes per launch of the three kernels from the committed `ncu --set full` capture of this workload
+    (profiles/traffic_r01.json, written by tools/ncu_summary.py --traffic); None when the capture is for another config."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -305,7 +324,7 @@ def main():
         e2e_ms = float(tt.item())
     wc = min(dpx + 1, n - 1) - 3
     h2d = B * n * wc * 8
-    d2h = int(sum(r["n_found"] for r in recs)) * 28 + B * 20
+    d2h = int(sum(r["n_found"] for r in recs)) * 36 + B * 20      # rows, cols, score id (int32), v, p, sigma (float64) + counters
     n_found = int(sum(r["n_found"] for r in recs))
 
     if rank != 0:
@@ -322,7 +341,19 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    instr = fp64_instr_per_bin(cfg["octaves"]) * bins_rank
+    instr_ref, instr_exec = fp64_instr_per_bin(cfg["octaves"])
+    instr = instr_exec * bins_rank
+    steps_ms = {k: v / args.steps for k, v in phases.items()}
+    # SURVEY 8(d) accounting split by the kernel that moves the bytes: 12 input reads (axis-0 pass), 11 DoG writes
+    # (axis-1 pass), 11 DoG reads (scoring) per octave
+    share = {"kv_kernel": 12 * 8 * n_oct, "kh_kernel": 11 * 8 * n_oct, "ks_kernel": 11 * 8 * n_oct}
+    traffic = load_traffic()
+    tr = (traffic or {}).get(args.config, {})
+    per_kernel = {}
+    for kname, ph in (("kv_kernel", "kv_ms"), ("kh_kernel", "kh_ms"), ("ks_kernel", "ks_ms")):
+        ach = bins_rank * share[kname] / (steps_ms[ph] * 1e-3) / 1e9
+        per_kernel[kname] = {"ms": steps_ms[ph], "algorithmic_bytes_per_bin": share[kname], "achieved": ach,
+                             "frac": ach / peak, "traffic": tr.get(kname)}
     out = {"metric": "contact_bins_per_sec", "value": value, "unit": "contact-bins/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config,
@@ -333,12 +364,18 @@ def main():
            "records_per_step": n_found,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                        "traffic": tr.get(dom), "peak_source": "measured" if peaks else "fallback",
                         "algorithmic_bytes_per_bin": bytes_per_bin, "bins_per_launch": bins_rank,
                         "scope": "whole step (prep + kv_kernel + kh_kernel + ks_kernel + statistics), device time from CUDA events",
                         "dominant_kernel": dom, "dominant_kernel_share": kern[dom] / max(dev_ms, 1e-9),
-                        "fp64": {"instr_per_bin_min": instr / bins_rank, "achieved_instr_per_s": instr / (hot_ms * 1e-3),
-                                 "peak_instr_per_s": FP64_INSTR_PEAK, "frac": instr / (hot_ms * 1e-3) / FP64_INSTR_PEAK}}}
+                        "traffic_note": "dram__bytes_read+write of the dominant kernel per launch, ncu --set full capture "
+                                        "of this command (profiles/)" if tr else "no ncu capture committed for this config",
+                        "kernels": per_kernel,
+                        "fp64": {"instr_per_bin_reference": instr_ref, "instr_per_bin_executed": instr_exec,
+                                 "achieved_instr_per_s": instr / (hot_ms * 1e-3), "peak_instr_per_s": FP64_INSTR_PEAK,
+                                 "frac": instr / (hot_ms * 1e-3) / FP64_INSTR_PEAK,
+                                 "note": "kv_kernel + kh_kernel; an FP64 instruction holds the SM sub-partition's dispatch "
+                                         "for 2 cycles, every other instruction costs ~0.75 more (tools/fp64_peak.cu)"}}}
     if not args.no_cpu_baseline and world == 1:
         val, ms, cores, sample = run_cpu_port(cfg, args.cpu_steps, 0)
         out["cpu_baseline"] = {"value": val, "unit": "contact-bins/s", "cores": cores, "kind": "port", "sample": sample,

@@ -90,6 +90,12 @@ MB200_API int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, 
 MB200_API int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* rows, int32_t* cols, double* v,
                         int32_t* score_id, double* p, int64_t* n_out);
 
+/* Optional: the detection scale (sigma_i, mustache.py:767 `Scales[...] = scales[o][i]`) of every scoring step, in chain
+ * order; call after mb200_set_program.  mb200_fetch_sigma then returns, per record and in the order of
+ * mb200_fetch_records, the value the reference stores in `Scales` (0 when no table was registered). */
+MB200_API int mb200_set_score_sigmas(mb200_engine* e, const double* sigma, int n_scored);
+MB200_API int mb200_fetch_sigma(mb200_engine* e, int block, int64_t capacity, double* sigma, int64_t* n_out);
+
 /* Device pointers of a block's record arrays (valid until the next mb200_run / mb200_configure; the engine's stream must
  * be synchronised -- mb200_block_counts does -- before they are read): lets a multi-GPU caller hand them to NCCL without a
  * host round trip.  scored_index is the 0-based index among the scoring steps (mb200_fetch_fits maps it to the score id). */

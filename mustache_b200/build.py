@@ -40,10 +40,10 @@ def _compile(lib, extra, verbose):
         raise RuntimeError("nvcc failed (%d)" % r.returncode)
 
 
-def build(force=False, verbose=False):
-    if force or needs_build(LIB):
-        _compile(LIB, [], verbose)
-    return LIB
+def build(force=False, verbose=False, lib=LIB, defines=()):
+    if force or needs_build(lib):
+        _compile(lib, ["-D" + d for d in defines], verbose)
+    return lib
 
 
 if __name__ == "__main__":

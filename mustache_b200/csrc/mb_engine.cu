@@ -44,7 +44,7 @@ struct mb200_engine {
     long long rec_cap = 0;
     int ncta_h = 0;
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
-        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, sm_ticket,
+        fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
@@ -54,6 +54,7 @@ struct mb200_engine {
     float t_prep = 0, t_kv = 0, t_kh = 0, t_ks = 0, t_fin = 0, t_total = 0;
     int launches = 0;
     size_t kv_smem_set = 0, kh_smem_set = 0, ks_smem_set = 0;
+    double score_sigma[MB_MAX_STEPS] = {0};   // detection scale per scored index (mb200_set_score_sigmas), 0 if unset
     MbTensorMaps tmaps;              // main chain (host copy)
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
@@ -216,7 +217,6 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.dbgL = nullptr;
     g.fill = 2.0;                      // mustache.py:703-706
     g.dout = nullptr;
-    g.sm_ticket = (unsigned*)e->sm_ticket.p;
     return g;
 }
 
@@ -350,7 +350,7 @@ void mb200_destroy(mb200_engine* e) {
     DevBuf* all[] = {&e->raw, &e->V, &e->Lb, &e->part_min, &e->part_sum, &e->rec_count, &e->nz_count, &e->nonfinite, &e->rec_row,
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
-                     &e->d_score_id, &e->d_tmaps, &e->d_dtmaps, &e->sm_ticket, &e->nz_xs, &e->nz_ds, &e->nz_perm,
+                     &e->d_score_id, &e->d_score_sigma, &e->rec_sid, &e->rec_sigma, &e->d_tmaps, &e->d_dtmaps, &e->nz_xs, &e->nz_ds, &e->nz_perm,
                      &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
@@ -367,26 +367,20 @@ void mb200_destroy(mb200_engine* e) {
 
 const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null engine"; }
 
-// Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping) for both walking
-// directions, indexed by the position in the walk, and for each position the latest earlier one whose box it overwrites.
+// Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping), and for each step the
+// latest earlier step whose box it overwrites.
 static void plan_kh_ring(MbProgram& p) {
     const int cap = kh_ring_doubles(p.rmax);
-    for (int dir = 0; dir < 2; ++dir) {
-        auto size_at = [&](int pos) {
-            const int s = dir ? p.n_steps - 1 - pos : pos;
-            return (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15;
-        };
-        MbStage* stg = p.stage[dir];
-        int cur = 0;
-        for (int pos = 0; pos < p.n_steps; ++pos) {
-            const int size = size_at(pos);
-            if (cur + size > cap) cur = 0;
-            stg[pos].off = cur;
-            stg[pos].dep = -1;
-            for (int t = 0; t < pos; ++t)
-                if (stg[t].off < cur + size && cur < stg[t].off + size_at(t)) stg[pos].dep = t;
-            cur += size;
-        }
+    auto size_of = [&](int s) { return (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15; };
+    int cur = 0;
+    for (int s = 0; s < p.n_steps; ++s) {
+        const int size = size_of(s);
+        if (cur + size > cap) cur = 0;
+        p.stage[s].off = cur;
+        p.stage[s].dep = -1;
+        for (int t = 0; t < s; ++t)
+            if (p.stage[t].off < cur + size && cur < p.stage[t].off + size_of(t)) p.stage[s].dep = t;
+        cur += size;
     }
 }
 
@@ -470,6 +464,7 @@ int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const
     int st = parse_program(e, e->prog, n_steps, radius, flags, score_id, tap_off, half_taps, n_taps);
     if (st) return st;
     if ((st = plan_kv(e, e->prog, e->kvplan))) return st;
+    memset(e->score_sigma, 0, sizeof(e->score_sigma));
     e->have_prog = true;
     e->configured = false;
     return MB200_OK;
@@ -540,12 +535,12 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if ((st = ensure(e, e->rec_sidx, B * e->rec_cap * sizeof(int)))) return st;
     if ((st = ensure(e, e->rec_v, B * e->rec_cap * sizeof(double)))) return st;
     if ((st = ensure(e, e->rec_p, B * e->rec_cap * sizeof(double)))) return st;
+    if ((st = ensure(e, e->rec_sid, B * e->rec_cap * sizeof(int)))) return st;
+    if ((st = ensure(e, e->rec_sigma, B * e->rec_cap * sizeof(double)))) return st;
+    if ((st = ensure(e, e->d_score_id, MB_MAX_STEPS * sizeof(int)))) return st;
+    if ((st = ensure(e, e->d_score_sigma, MB_MAX_STEPS * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_loc, B * ns * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_scale, B * ns * sizeof(double)))) return st;
-    if (!e->sm_ticket.p) {
-        if ((st = ensure(e, e->sm_ticket, MB_MAX_SMS * sizeof(unsigned)))) return st;
-        CU(e, cudaMemsetAsync(e->sm_ticket.p, 0, MB_MAX_SMS * sizeof(unsigned), e->stream));
-    }
     // axis-0 scratch: as many blocks per pass as fit in ~80 % of what is free now (plus what V already holds)
     size_t free_b = 0, total_b = 0;
     CU(e, cudaMemGetInfo(&free_b, &total_b));
@@ -688,10 +683,14 @@ int mb200_run(mb200_engine* e) {
             (const double*)e->part_min.p, (const double*)e->part_sum.p, e->ncta_h, e->prog.n_scored,
             (const unsigned long long*)e->nz_count.p, (double*)e->fit_loc.p, (double*)e->fit_scale.p);
         CU(e, cudaGetLastError());
-        finalise_kernel<<<dim3(64, B), 256, 0, e->stream>>>((const unsigned long long*)e->rec_count.p, e->rec_cap,
-                                                           (const double*)e->rec_v.p, (const int*)e->rec_sidx.p,
-                                                           e->prog.n_scored, (const double*)e->fit_loc.p,
-                                                           (const double*)e->fit_scale.p, (double*)e->rec_p.p);
+        // engine-owned host tables: safe to copy asynchronously (they only change in set_program / set_score_sigmas,
+        // which are not legal while a run is in flight)
+        CU(e, cudaMemcpyAsync(e->d_score_id.p, e->prog.score_id, MB_MAX_STEPS * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        CU(e, cudaMemcpyAsync(e->d_score_sigma.p, e->score_sigma, MB_MAX_STEPS * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        finalise_kernel<<<dim3(64, B), 256, 0, e->stream>>>(
+            (const unsigned long long*)e->rec_count.p, e->rec_cap, (const double*)e->rec_v.p, (const int*)e->rec_sidx.p,
+            e->prog.n_scored, (const double*)e->fit_loc.p, (const double*)e->fit_scale.p, (const int*)e->d_score_id.p,
+            (const double*)e->d_score_sigma.p, (double*)e->rec_p.p, (int*)e->rec_sid.p, (double*)e->rec_sigma.p);
         CU(e, cudaGetLastError());
         e->launches += 2;
     }
@@ -736,11 +735,32 @@ int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* r
     const size_t o = (size_t)block * e->rec_cap;
     CU(e, cudaMemcpyAsync(rows, (int*)e->rec_row.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(cols, (int*)e->rec_col.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaMemcpyAsync(score_id, (int*)e->rec_sidx.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(score_id, (int*)e->rec_sid.p + o, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(v, (double*)e->rec_v.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(p, (double*)e->rec_p.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
-    for (int64_t r = 0; r < m; ++r) score_id[r] = e->prog.score_id[score_id[r]];   // scored index -> octave*12 + i
+    return MB200_OK;
+}
+
+int mb200_set_score_sigmas(mb200_engine* e, const double* sigma, int n_scored) {
+    if (!e || !sigma) return MB200_ERR_ARG;
+    if (!e->have_prog || n_scored != e->prog.n_scored)
+        return fail(e, MB200_ERR_ARG, "mb200_set_score_sigmas: %d values for %d scoring steps", n_scored, e->have_prog ? e->prog.n_scored : -1);
+    memset(e->score_sigma, 0, sizeof(e->score_sigma));
+    memcpy(e->score_sigma, sigma, (size_t)n_scored * sizeof(double));
+    return MB200_OK;
+}
+
+int mb200_fetch_sigma(mb200_engine* e, int block, int64_t capacity, double* sigma, int64_t* n_out) {
+    int64_t nz = 0, nf = 0;
+    int st = mb200_block_counts(e, block, &nz, &nf);
+    if (n_out) *n_out = nf;
+    if (st) return st;
+    const int64_t m = std::min<int64_t>(nf, capacity);
+    if (m <= 0) return MB200_OK;
+    if (!sigma) return fail(e, MB200_ERR_ARG, "null output array");
+    CU(e, cudaMemcpyAsync(sigma, (double*)e->rec_sigma.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
     return MB200_OK;
 }
 
@@ -859,8 +879,6 @@ int mb200_run_differential(mb200_engine* e) {
     if ((st = ensure(e, e->dmu, (size_t)ndiff * npairs * sizeof(double)))) return st;
     if ((st = ensure(e, e->dsd, (size_t)ndiff * npairs * sizeof(double)))) return st;
     if ((st = ensure(e, e->rec_pair, (size_t)e->nblocks * e->rec_cap * sizeof(double)))) return st;
-    if ((st = ensure(e, e->d_score_id, MB_MAX_STEPS * sizeof(int)))) return st;
-    CU(e, cudaMemcpyAsync(e->d_score_id.p, e->prog.score_id, MB_MAX_STEPS * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     diff_tile_kernel<<<dim3(148 * 2, npairs), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), (double*)e->rawD.p, e->n, e->wc, e->dpx);
     CU(e, cudaGetLastError());
     CU(e, cudaMemsetAsync(e->dout.p, 0, (size_t)ndiff * npairs * tile * sizeof(double), e->stream));

@@ -39,11 +39,9 @@ struct MbStep {
 
 // kh_kernel stages the axis-0 tile of every step in a byte-granular ring of shared memory: small-radius steps have small
 // boxes, so more of them are in flight.  Placement is computed on the host (mb_engine.cu: plan_kh_ring).
-// A CTA walks the chain upwards (step 0, 1, ...) or downwards (see kh_kernel); the plan is per direction and indexed
-// by the position in the walk.
 struct MbStage {
-    int off;         // offset of the box in the ring, in doubles (multiple of 16 -> 128-byte aligned)
-    int dep;         // latest earlier position whose box overlaps this one (-1: none): must be released before the copy
+    int off;         // offset of the step's box in the ring, in doubles (multiple of 16 -> 128-byte aligned)
+    int dep;         // latest earlier step whose box overlaps this one (-1: none): must be released before the copy
 };
 
 struct MbProgram {
@@ -52,7 +50,7 @@ struct MbProgram {
     int rmax;
     int pad;
     MbStep st[MB_MAX_STEPS];
-    MbStage stage[2][MB_MAX_STEPS];   // [direction][position in the walk]
+    MbStage stage[MB_MAX_STEPS];
     int score_id[MB_MAX_STEPS];   // per scored index: octave*12 + i  (reference's scales[o][i])
     double taps[MB_MAX_TAPS];
 };
@@ -121,15 +119,7 @@ struct MbGeom {
     double* dbgL;                   // dense [n][n]: DoG formed at dbg_step
     double fill;                    // value of the constant regions (2.0; 0.0 for the difference stack of diff_mustache)
     double* dout;                   // [n_diffref][nblk][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
-    unsigned* sm_ticket;            // [MB_MAX_SMS] per-SM arrival counters (never reset: only their parity is used)
 };
-#define MB_MAX_SMS 1024
-
-__device__ __forceinline__ unsigned sm_id() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
-    return r;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // tile shapes
@@ -140,7 +130,11 @@ constexpr int KV_K = 4;        // outputs per thread along the filter axis
 constexpr int KV_THREADS = (32 / KV_K) * 32;      // 256: one 32-row sub-block at a time
 
 constexpr int KH_TR = 32;      // tile rows = lanes (axis-1 pass)
-constexpr int KH_TC = 64;      // tile columns
+#ifndef MB_KH_TC
+#define MB_KH_TC 64
+#endif
+constexpr int KH_TC = MB_KH_TC; // tile columns (64: two CTAs per SM; 128: one CTA of 16 warps with the whole SM as staging ring)
+constexpr int KH_CTAS = (KH_TC == 64) ? 2 : 1;
 constexpr int KH_K = 8;
 constexpr int KH_THREADS = (KH_TC / KH_K) * 32;   // 256
 
@@ -166,7 +160,7 @@ constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the s
 constexpr int KH_XP = KH_K + 1;        // pitch of the per-warp 32 x 8 transpose buffer (odd: lanes index rows)
 __host__ __device__ inline int kh_ring_doubles(int rmax) {
     const int widest = KH_TR * kh_vbuf_pitch(rmax);
-    const int half_sm = (110 * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP;
+    const int half_sm = ((KH_CTAS == 2 ? 110 : 222) * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP - 2 * MB_MAX_STEPS;
     return half_sm > 2 * widest ? half_sm : 2 * widest;
 }
 constexpr int KV_GUARD = 3;
@@ -467,7 +461,7 @@ __device__ __forceinline__ void tma_load_box3d(void* dst, const CUtensorMap* map
 constexpr int KH_MAIN = 0, KH_DIFF = 1, KH_DEBUG = 2;
 
 template <int MODE>
-__global__ void __launch_bounds__(KH_THREADS, 2)
+__global__ void __launch_bounds__(KH_THREADS, KH_CTAS)
 kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
     extern __shared__ __align__(128) double smem[];
     constexpr int NW = KH_THREADS / 32;
@@ -476,7 +470,6 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     uint64_t* full = reinterpret_cast<uint64_t*>(vbuf + kh_ring_doubles(rmax));    // [n_steps] bytes landed (used once)
     uint64_t* empty = full + MB_MAX_STEPS;                      // [n_steps] every warp is done reading the box (used once)
     double* xbuf = reinterpret_cast<double*>(empty + MB_MAX_STEPS) + (threadIdx.x >> 5) * (KH_TR * KH_XP);   // per warp [32][9]
-    __shared__ unsigned s_ticket;
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -499,14 +492,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         mbar_init(&full[t], 1);
         mbar_init(&empty[t], NW);
     }
-    if (threadIdx.x == 0) s_ticket = (MODE == KH_DEBUG) ? 0u : atomicAdd(g.sm_ticket + (sm_id() & (MB_MAX_SMS - 1)), 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    // Every CTA does the same work, so the two CTAs of an SM would run the FP64-dense tap loops and the barrier / store
-    // phases in lockstep, and the small-radius steps (mostly overhead) at the same time.  Every other CTA that arrives
-    // on an SM therefore walks the chain downwards: L_s = G_{s-1} - G_s is formed when its second operand is done,
-    // whichever comes last, so the result is the same bit for bit.
-    const int dir = (int)(s_ticket & 1u);
     const int n_steps = prog.n_steps;
     // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
@@ -544,18 +531,17 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     // warp-uniform: no pixel of the chunk needs a mask (true for all but the tiles on the band / image edges)
     const bool interior = __all_sync(0xffffffffu, zmask == (1u << KH_K) - 1u && qmask == (1u << (KH_TR / 4)) - 1u);
 
-    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of the
-    // step at walk position p into its slot of the ring, after every warp released the boxes it overlaps.
-    auto step_at = [&](int p) { return dir ? n_steps - 1 - p : p; };
-    const MbStage* stg = prog.stage[dir];
+    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
+    // into its slot of the ring, after every warp released the boxes it overlaps.
+    const MbStage* stg = prog.stage;
     int next_issue = 0;
     auto issue_ready = [&](int p_now) {
         while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
             const int dep = stg[next_issue].dep;
             if (dep >= p_now) break;                            // the overlapped box is still ahead of this warp
             if (elect_one()) {
-                if (dep >= 0) mbar_wait(&empty[step_at(dep)], 0);
-                const int s = step_at(next_issue);
+                if (dep >= 0) mbar_wait(&empty[dep], 0);
+                const int s = next_issue;
                 const int R = prog.st[s].radius;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
                 // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
@@ -570,15 +556,14 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
     for (int k = 0; k < KH_K; ++k) gA[k] = gB[k] = 0.0;
 
-    // walk position p: Gaussian of step s = step_at(p) into gnew; gprev holds the Gaussian of the previous position
-    auto step = [&](const int p, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
-        const int s = step_at(p);
+    // Gaussian of step s into gnew; gprev holds the Gaussian of step s - 1
+    auto step = [&](const int s, const double (&gprev)[KH_K], double (&gnew)[KH_K]) {
         const int R = prog.st[s].radius;
-        double* vst = vbuf + (border ? 0 : stg[p].off);
+        double* vst = vbuf + (border ? 0 : stg[s].off);
         const int bw = kh_box_width(R);                          // row pitch of this step's staged box
         const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-            if (warp == 0) issue_ready(p);
+            if (warp == 0) issue_ready(s);
             mbar_wait(&full[s], 0);
         } else {
             __syncthreads();                                     // previous step's readers are done with the buffer
@@ -617,9 +602,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 }
             }
         }
-        // the DoG completed now: L_sl = G_{sl-1} - G_sl with sl = s walking up, s + 1 walking down
-        const int sl = dir ? s + 1 : s;
-        if (sl >= n_steps) return;                               // first position of a downward walk
+        const int sl = s;                                        // the DoG completed now: L_s = G_{s-1} - G_s
         const int flags = prog.st[sl].flags;
         const bool formed = !(flags & MB_FLAG_RESTART);
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
@@ -630,25 +613,15 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             const double* xrd = xbuf + (lane >> 3) * KH_XP + kk;
             if (MODE != KH_DEBUG && interior) {
                 // every pixel of the warp's chunk is inside the image and on a stored diagonal: no masks
-                if (dir) {
 #pragma unroll
-                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gnew[k], gprev[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gprev[k], gnew[k]);
-                }
+                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gprev[k], gnew[k]);
                 __syncwarp();
 #pragma unroll
                 for (int q = 0; q < KH_TR / 4; ++q) dst[(long long)q * qstride + ((q >> 1) & 1)] = xrd[4 * q * KH_XP];
             } else {
                 // columns past the image hold the maximum filter's cval 0
-                if (dir) {
 #pragma unroll
-                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gnew[k], gprev[k]) : 0.0;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
-                }
+                for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
                 __syncwarp();
 #pragma unroll
                 for (int q = 0; q < KH_TR / 4; ++q) {
@@ -939,10 +912,13 @@ reduce_stats_kernel(const double* __restrict__ part_min, const double* __restric
 }
 
 // p = 1 - expon.cdf(|L|, loc, scale) = 1 - (-expm1(-(x - loc)/scale))   (mustache.py:756); winners have L > 0.
+// Also resolves the scored index of every record to what the caller reads back: the score id (octave*12 + i, the
+// reference's scales[o][i] index) and, when the host registered them, the detection scale sigma itself (mustache.py:767).
 __global__ void __launch_bounds__(256)
 finalise_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const double* __restrict__ rec_v,
                 const int* __restrict__ rec_sidx, int n_scored, const double* __restrict__ fit_loc,
-                const double* __restrict__ fit_scale, double* __restrict__ rec_p) {
+                const double* __restrict__ fit_scale, const int* __restrict__ score_id, const double* __restrict__ score_sigma,
+                double* __restrict__ rec_p, int* __restrict__ rec_sid, double* __restrict__ rec_sigma) {
     const int b = blockIdx.y;
     unsigned long long n = rec_count[b];
     if (n > (unsigned long long)rec_cap) n = rec_cap;
@@ -951,6 +927,8 @@ finalise_kernel(const unsigned long long* __restrict__ rec_count, long long rec_
         const int t = rec_sidx[o];
         const double y = (fabs(rec_v[o]) - fit_loc[(size_t)b * n_scored + t]) / fit_scale[(size_t)b * n_scored + t];
         rec_p[o] = 1.0 - (-expm1(-y));
+        rec_sid[o] = score_id[t];
+        rec_sigma[o] = score_sigma[t];
     }
 }
 

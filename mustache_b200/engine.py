@@ -36,6 +36,8 @@ SIGNATURES = {
     "mb200_sync": (C.c_int, [_H]),
     "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
     "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
+    "mb200_set_score_sigmas": (C.c_int, [_H, _f64p, C.c_int]),
+    "mb200_fetch_sigma": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_records_device": (C.c_int, [_H, C.c_int] + [C.POINTER(C.c_void_p)] * 5 + [_i64p]),
     "mb200_fetch_fits": (C.c_int, [_H, C.c_int, _f64p, _f64p, _i32p, C.c_int, C.POINTER(C.c_int)]),
     "mb200_last_timing": (C.c_int, [_H, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]),
@@ -181,6 +183,9 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_set_program(self.h, len(radius), _ptr(radius, _i32p), _ptr(flags, _i32p), _ptr(sid, _i32p),
                                              _ptr(off, _i32p), _ptr(taps, _f64p), len(taps)))
         self.program = prog
+        sig = np.array([st.score_sigma for st in prog.steps if st.score_id], np.float64)
+        if len(sig):
+            self._chk(self.lib.mb200_set_score_sigmas(self.h, _ptr(sig, _f64p), len(sig)))
 
     def _sigma_lut(self):
         lut = np.zeros(256)
@@ -248,19 +253,20 @@ class ScaleSpaceEngine:
             self._chk(self.lib.mb200_fetch_pair(self.h, int(block), nf, _ptr(pp, _f64p), C.byref(n2)))
         if pinned:
             rows, cols, sid = (self._pinned(k, nf, np.int32) for k in ("rows", "cols", "sid"))
-            v, p = self._pinned("v", nf, np.float64), self._pinned("p", nf, np.float64)
+            v, p, sig = (self._pinned(k, nf, np.float64) for k in ("v", "p", "sigma"))
         else:
             rows, cols = np.empty(nf, np.int32), np.empty(nf, np.int32)
             v, p, sid = np.empty(nf, np.float64), np.empty(nf, np.float64), np.empty(nf, np.int32)
+            sig = np.empty(nf, np.float64)
         n_out = C.c_int64(0)
         self._chk(self.lib.mb200_fetch_records(self.h, int(block), nf, _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(v, _f64p),
                                                _ptr(sid, _i32p), _ptr(p, _f64p), C.byref(n_out)))
+        self._chk(self.lib.mb200_fetch_sigma(self.h, int(block), nf, _ptr(sig, _f64p), C.byref(n_out)))   # resolved on the device
         if sort and nf:
             order = np.lexsort((cols, rows))
-            rows, cols, v, p, sid = rows[order], cols[order], v[order], p[order], sid[order]
+            rows, cols, v, p, sid, sig = rows[order], cols[order], v[order], p[order], sid[order], sig[order]
             if pp is not None:
                 pp = pp[order]
-        sig = self._sigma_lut()[sid] if nf else np.zeros(0)
         out = dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
         if pp is not None:
             out["pair"] = pp

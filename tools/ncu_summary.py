@@ -1,7 +1,12 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read on the CPU box with `ncu -i`): headline metrics per kernel and, for one kernel, the
 instruction / stall-sample split between barrier-delimited phases of the SASS.  Usage:
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-regex]"""
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-regex]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --traffic CONFIG profiles/traffic_r01.json
+(the second form records dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel under CONFIG; bench.py
+reports it as roofline.traffic)"""
+import json
+import os
 import collections
 import csv
 import io
@@ -29,6 +34,20 @@ def main():
     kre = sys.argv[2] if len(sys.argv) > 2 else None
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units = rows[0], rows[1]
+    if kre == "--traffic":
+        cfg, out = sys.argv[3], sys.argv[4]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        acc = {}
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]
+            tot = sum(float(d[m].replace(",", "")) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            acc.setdefault(name, []).append(tot)
+        data = json.load(open(out)) if os.path.exists(out) else {}
+        data[cfg] = {k: sum(v) / len(v) for k, v in acc.items()}
+        json.dump(data, open(out, "w"), indent=1, sort_keys=True)
+        print(json.dumps(data[cfg]))
+        return
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         print("== %s  grid %s block %s" % (d["Kernel Name"].split("(")[0], d.get("Grid Size"), d.get("Block Size")))

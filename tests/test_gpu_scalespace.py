@@ -202,3 +202,29 @@ def test_pipelined_uploads_do_not_mix_batches(eng):
     for got, want in ((ra, ref["a"]), (rb, ref["b"]), (ra2, ref["a"])):
         assert np.array_equal(got["rows"], want["rows"]) and np.array_equal(got["cols"], want["cols"])
         assert np.array_equal(got["v"], want["v"]) and np.array_equal(got["p"], want["p"])
+
+
+@pytest.mark.parametrize("octaves", [(0.5,), (0.7, 1.4, 2.8), (2.3, 4.6), (1.6, 3.2, 6.4)])
+def test_unusual_ladders_match_oracle(eng, octaves):
+    """-sz / -oc other than the defaults: radii 1-2 (the axis-0 windows reach above the tile), one octave (a single
+    chain), three octaves, a sigma0 whose octave tails are not bit-identical to the next octave's heads.  Records against
+    the oracle (numpy restatement of mustache.py:699-772), Gaussians of every step bit-exact."""
+    c = synth.make_tile(n=288, dpx=120, seed=71, blob_seed=72, nblobs=10, missing=0.1)
+    prog = ladder.build_program(list(octaves))
+    eng.set_program(prog)
+    eng.configure(288, 120, 1)
+    eng.upload_dense(0, c)
+    nz, filled = osc.mask_and_fill(c, 120)
+    band = _band_mask(288, 4, 121)
+    for s, st in enumerate(prog.steps):
+        g, _ = eng.debug_level(0, s)
+        assert np.array_equal(g[band], osc.gaussian_level(filled, st.taps)[band]), "step %d radius %d" % (s, st.radius)
+    eng.upload_dense(0, c)
+    eng.run()
+    rec = eng.records(0)
+    ref = osc.scale_space(c, 120, list(octaves))
+    found = ref["p"] != 2
+    assert rec["nz_count"] == ref["nz_count"] and found.sum() > 0
+    assert np.array_equal(rec["rows"], ref["rows"][found]) and np.array_equal(rec["cols"], ref["cols"][found])
+    assert np.array_equal(rec["v"], ref["v"][found]) and np.array_equal(rec["sigma"], ref["scale"][found])
+    assert np.abs(rec["p"] - ref["p"][found]).max() <= P_TOL

@@ -428,6 +428,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrival that tells whether it completed the barrier's phase: the last of the expected arrivals always sees true, an
+// earlier one may too if the last slips in between its two instructions (callers make the follow-up idempotent)
+__device__ __forceinline__ bool mbar_arrive_is_last(uint64_t* bar) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .b64 tok;\n"
+        ".reg .pred P1;\n"
+        "mbarrier.arrive.shared::cta.b64 tok, [%1];\n"
+        "mbarrier.test_wait.shared::cta.b64 P1, [%1], tok;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(done) : "r"(smem_u32(bar)) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -670,12 +684,14 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     constexpr int NW = KS_THREADS / 32;
     constexpr int PL = KS_PITCH;                                // even, == 2 (mod 4)
     constexpr int D = KS_DEPTH;
-    constexpr int AHEAD = D - 3;                                // levels in flight beyond the one being scored
     double* lst = smem;                                         // [D][KS_TR][PL]   staged DoG tiles
     double* pmin = lst + D * KS_TR * PL;                        // [n_scored][NW] per-warp min of |L|
     double* psum = pmin + (size_t)max(prog.n_scored, 1) * NW;   // [n_scored][NW] per-warp sum of |L|
     uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * NW);   // [D]
-    uint64_t* empty = full + D;                                 // [D]
+    uint64_t* empty = full + D;                                 // [D] every warp released the stage's tile
+    __shared__ int stage_lvl[KS_DEPTH];                         // level the stage holds or is loading (claims reloads)
+    __shared__ int lvl_step[MB_MAX_STEPS];                      // chain step of the nl-th DoG of the stream
+    __shared__ int n_levels_s;
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -713,10 +729,16 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         for (int d = 0; d < D; ++d) {
             mbar_init(&full[d], 1);
             mbar_init(&empty[d], NW);
+            stage_lvl[d] = d;
         }
+        int nlev = 0;
+        for (int s = 0; s < prog.n_steps; ++s)
+            if (!(prog.st[s].flags & MB_FLAG_RESTART)) lvl_step[nlev++] = s;            // steps that form a DoG
+        n_levels_s = nlev;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const int n_levels = n_levels_s;
 
     // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
     unsigned mask = 0;
@@ -730,18 +752,13 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         }
     }
 
-    // Producer side (one thread): the DoG tile of step s, the nl-th level of the stream, into stage nl % D.  The stage's
-    // previous tile (level nl - D) was released by every warp after it scored level nl - D + 2.
-    auto issue = [&](int s, int nl) {
-        const int u = nl / D, st = nl - u * D;
-        if (u > 0) mbar_wait(&empty[st], (u - 1) & 1);
+    // Producer side: the DoG tile of the nl-th level of the stream goes into stage nl % D.  A stage is free once every
+    // warp has scored the level two after the one it holds; the warp whose release completes that (the last of the NW
+    // arrivals on the stage's `empty` barrier) issues the stage's next load itself, so nobody ever waits for a free stage.
+    auto issue = [&](int nl) {
+        const int st = nl % D;
         mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
-        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, s * g.nblk + b, &full[st]);
-    };
-    auto next_formed = [&](int s) {                             // next step that forms a DoG
-        ++s;
-        while (s < prog.n_steps && (prog.st[s].flags & MB_FLAG_RESTART)) ++s;
-        return s;
+        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.nblk + b, &full[st]);
     };
 
     double vbest[KS_K], lA[KS_K], lB[KS_K];
@@ -749,17 +766,11 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
     for (int k = 0; k < KS_K; ++k) { vbest[k] = 0.0; lA[k] = lB[k] = 0.0; }
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
-    int s_issue = next_formed(-1), nl_issue = 0;        // producer cursor (warp 0, uniform)
 
     // One DoG level (stream position nl).  lcur holds the own values of level nl-1 (the one being scored), lown receives
     // those of level nl; the two register arrays swap roles between consecutive levels (the loop is unrolled by two).
     auto level = [&](const int s, const int nl, const double (&lcur)[KS_K], double (&lown)[KS_K]) {
         const int flags = prog.st[s].flags;
-        if (warp == 0 && s_issue < prog.n_steps) {              // the cursor stays warp-uniform
-            if (elect_one()) issue(s_issue, nl_issue);
-            s_issue = next_formed(s_issue);
-            ++nl_issue;
-        }
         const int u = nl / D, st_i = nl - u * D;
         mbar_wait(&full[st_i], u & 1);
         const double* st = lst + st_i * (KS_TR * PL) + off_c;                           // level nl, own pixel 0
@@ -818,7 +829,9 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             }
         }
         __syncwarp();
-        if (nl >= 2 && lane == 0) mbar_arrive(&empty[sp_i]);    // this warp is done with level nl-2
+        if (nl >= 2 && lane == 0 && mbar_arrive_is_last(&empty[sp_i])) {     // level nl-2 is released by every warp:
+            if (nl - 2 + D < n_levels && atomicCAS(&stage_lvl[sp_i], nl - 2, nl - 2 + D) == nl - 2) issue(nl - 2 + D);   // reload
+        }
         if (score) {                                            // per-warp statistics, fixed order (deterministic)
             tmin = warp_min(tmin);
             tsum = warp_sum(tsum);
@@ -831,20 +844,11 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         e_cur = e_new;
     };
 
-    if (warp == 0) {                                            // prologue: AHEAD levels in flight before the first wait
-        for (int q = 0; q < AHEAD && s_issue < prog.n_steps; ++q) {
-            if (elect_one()) issue(s_issue, nl_issue);
-            s_issue = next_formed(s_issue);
-            ++nl_issue;
-        }
-    }
-    int s = next_formed(-1), nl = 0;
-    while (s < prog.n_steps) {
-        level(s, nl, lB, lA);                   // even level: own values into lA
-        s = next_formed(s); ++nl;
-        if (s >= prog.n_steps) break;
-        level(s, nl, lA, lB);
-        s = next_formed(s); ++nl;
+    if (threadIdx.x == 0)                                       // prologue: every stage starts loading
+        for (int q = 0; q < D && q < n_levels; ++q) issue(q);
+    for (int nl = 0; nl < n_levels; nl += 2) {
+        level(lvl_step[nl], nl, lB, lA);        // even level: own values into lA
+        if (nl + 1 < n_levels) level(lvl_step[nl + 1], nl + 1, lA, lB);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {

@@ -108,3 +108,24 @@ def test_cli_chr21_with_device_normaliser(tmp_path, monkeypatch):
     out = str(tmp_path / "chr21_out.tsv")
     mm.main(["-f", raw, "-b", kr, "-ch", "21", "-r", "5kb", "-pt", "0.1", "-st", "0.8", "-o", out])
     assert _same_tsv(out, os.path.join(G, "chr21_loops.tsv")) == 90
+
+
+def test_windowed_branch_other_window(eng):
+    """2 kb bins: window of 1000 bins, distance limit 1000 bins, both window ends clipped for most contacts."""
+    rng = np.random.default_rng(11)
+    n, res, dpx = 2500, 2000, 1000
+    m = 120000
+    x = rng.integers(0, n, size=m)
+    d = np.minimum(rng.geometric(0.004, size=m) - 1, dpx + 1)
+    y = x + d
+    ok = y < n
+    x, y = x[ok], y[ok]
+    key = np.unique(x * 100000 + y, return_index=True)[1]
+    x, y = x[key], y[key]
+    v = rng.gamma(1.5, 2.0, size=len(x)) / (1.0 + 0.01 * (y - x))
+    ref = v.copy()
+    w_ref = normalize.normalize_sparse(x, y, ref, res, dpx)
+    got = v.copy()
+    w_got = normalize.normalize_sparse_device(eng, x, y, got, res, dpx)
+    assert w_got == w_ref and len(w_ref) == dpx + 2
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256, CTAS) k(const __grid_constant__ Taps tp, 
         double acc[8];
         for (int r = 0; r < reps; ++r)
             for (int s = 0; s < nr; ++s) {
-                conv_slide<8>(sm + lane * 178 + ((lane >> 3) & 1) + warp * 8 + 56, 1, tp.R[s], tp.w[s], acc);
+                conv_slide<8, 1>(sm + lane * 178 + ((lane >> 3) & 1) + warp * 8 + 56, tp.R[s], tp.w[s], acc);
                 tot += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             }
     } else if (MODE == 2) {     // same, software-pipelined taps

@@ -667,7 +667,7 @@ int mb200_run(mb200_engine* e) {
     CU(e, cudaMemsetAsync(e->rec_count.p, 0, B * sizeof(unsigned long long), e->stream));
     CU(e, cudaMemsetAsync(e->nz_count.p, 0, B * sizeof(unsigned long long), e->stream));
     CU(e, cudaMemsetAsync(e->nonfinite.p, 0, B * sizeof(int), e->stream));
-    count_mask_kernel<<<dim3(148 * 2, B), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), e->n, e->wc,
+    count_mask_kernel<<<dim3(B >= 8 ? 148 * 2 : 148 * 8, B), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), e->n, e->wc,
                                                                 (unsigned long long*)e->nz_count.p, (int*)e->nonfinite.p);
     CU(e, cudaGetLastError());
     e->launches += 1;

@@ -960,21 +960,22 @@ band_from_dense_kernel(const double* __restrict__ c, long long ld, double* __res
     }
 }
 
-// mask size (mustache.py:699-701) and a finiteness check (scipy.stats.expon.fit raises on non-finite data)
+// mask size (mustache.py:699-701) and a finiteness check (scipy.stats.expon.fit raises on non-finite data).
+// grid = (row groups, blocks): a CTA walks whole band rows, so there is no per-element index arithmetic.
 __global__ void __launch_bounds__(256)
 count_mask_kernel(const double* __restrict__ raw, int n, int wc, unsigned long long* __restrict__ nz_count,
                   int* __restrict__ nonfinite) {
     const int b = blockIdx.y;
     const double* rawb = raw + (size_t)b * n * wc;
-    const long long total = (long long)n * wc;
-    unsigned long long cnt = 0;
+    unsigned cnt = 0;
     int bad = 0;
-    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256LL) {
-        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
-        if (i + 4 + k < n) {
-            const double v = rawb[e];
-            if (v != 0.0) ++cnt;
-            if (!isfinite(v)) bad = 1;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const double* row = rawb + (size_t)i * wc;
+        const int w = min(wc, n - 4 - i);                       // columns i+4+k < n
+        for (int k = threadIdx.x; k < w; k += 256) {
+            const double v = row[k];
+            cnt += (v != 0.0);
+            bad |= !isfinite(v);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -982,7 +983,7 @@ count_mask_kernel(const double* __restrict__ raw, int n, int wc, unsigned long l
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (cnt) atomicAdd(nz_count + b, cnt);
+        if (cnt) atomicAdd(nz_count + b, (unsigned long long)cnt);
         if (bad) atomicOr(nonfinite + b, 1);
     }
 }

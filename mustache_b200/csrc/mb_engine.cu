@@ -220,9 +220,12 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     return g;
 }
 
+int kv_tile_rows(const mb200_engine* e) { return e->wv < 1024 ? KV_TH_NARROW : KV_TH_WIDE; }
+
 dim3 kv_grid(const mb200_engine* e, int nblk) {
-    const int span = e->wv + KV_TH - 1;
-    return dim3((span + KV_TW - 1) / KV_TW, (e->n + KV_TH - 1) / KV_TH, nblk);
+    const int th = kv_tile_rows(e);
+    const int span = e->wv + th - 1;
+    return dim3((span + KV_TW - 1) / KV_TW, (e->n + th - 1) / th, nblk);
 }
 
 dim3 kh_grid(const mb200_engine* e, int nblk) {
@@ -236,11 +239,12 @@ dim3 ks_grid(const mb200_engine* e, int nblk) {
 }
 
 int set_smem_limits(mb200_engine* e) {
-    const size_t kvb = kv_smem_bytes(e->prog.rmax), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
+    const size_t kvb = kv_smem_bytes(e->prog.rmax, KV_TH_WIDE), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
     if (kvb > 227 * 1024 || khb > 227 * 1024)
         return fail(e, MB200_ERR_ARG, "radius %d needs %zu / %zu bytes of shared memory (> 227 KB)", e->prog.rmax, kvb, khb);
     if (kvb != e->kv_smem_set) {
-        CU(e, cudaFuncSetAttribute(kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
         e->kv_smem_set = kvb;
     }
     if (khb != e->kh_smem_set) {
@@ -261,9 +265,13 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
                 const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
     const MbProgram& pg = program ? *program : e->prog;
-    const size_t kvb = kv_smem_bytes(pg.rmax), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
+    const int th = kv_tile_rows(e);
+    const size_t kvb = kv_smem_bytes(pg.rmax, th), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
     const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
-    kv_kernel<<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
+    if (th == KV_TH_WIDE)
+        kv_kernel<KV_TH_WIDE><<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
+    else
+        kv_kernel<KV_TH_NARROW><<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
     if (g.dout != nullptr)                          // difference stack: only the DIFFREF DoGs are kept
@@ -687,7 +695,7 @@ int mb200_run(mb200_engine* e) {
         // which are not legal while a run is in flight)
         CU(e, cudaMemcpyAsync(e->d_score_id.p, e->prog.score_id, MB_MAX_STEPS * sizeof(int), cudaMemcpyHostToDevice, e->stream));
         CU(e, cudaMemcpyAsync(e->d_score_sigma.p, e->score_sigma, MB_MAX_STEPS * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        finalise_kernel<<<dim3(64, B), 256, 0, e->stream>>>(
+        finalise_kernel<<<dim3(B >= 8 ? 64 : 148 * 4, B), 256, 0, e->stream>>>(
             (const unsigned long long*)e->rec_count.p, e->rec_cap, (const double*)e->rec_v.p, (const int*)e->rec_sidx.p,
             e->prog.n_scored, (const double*)e->fit_loc.p, (const double*)e->fit_scale.p, (const int*)e->d_score_id.p,
             (const double*)e->d_score_sigma.p, (double*)e->rec_p.p, (int*)e->rec_sid.p, (double*)e->rec_sigma.p);

@@ -124,7 +124,10 @@ struct MbGeom {
 // ---------------------------------------------------------------------------------------------------------------
 // tile shapes
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int KV_TH = 128;     // rows per CTA (axis-0 pass): four 32-row sub-blocks walked one after the other
+// rows per CTA of the axis-0 pass (template parameter TH of kv_kernel), walked as 32-row sub-blocks: 128 amortises the
+// staged +/- rmax halo rows best; 64 wastes less staging on the tiles that straddle the edges of a narrow band (a
+// tile's rows shift the band by one column each)
+constexpr int KV_TH_WIDE = 128, KV_TH_NARROW = 64;
 constexpr int KV_TW = 32;      // columns per CTA = lanes
 constexpr int KV_K = 4;        // outputs per thread along the filter axis
 constexpr int KV_THREADS = (32 / KV_K) * 32;      // 256: one 32-row sub-block at a time
@@ -156,7 +159,7 @@ __host__ __device__ inline int kh_box_width(int R) {
 }
 __host__ __device__ inline int kh_vbuf_pitch(int rmax) { return kh_box_width(rmax); }
 // staging ring of kh_kernel: half an SM's shared memory (two CTAs per SM), at least two of the widest boxes
-constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the slowest warp
+constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the slowest warp (6: no measurable difference)
 constexpr int KH_XP = KH_K + 1;        // pitch of the per-warp 32 x 8 transpose buffer (odd: lanes index rows)
 __host__ __device__ inline int kh_ring_doubles(int rmax) {
     const int widest = KH_TR * kh_vbuf_pitch(rmax);
@@ -164,7 +167,7 @@ __host__ __device__ inline int kh_ring_doubles(int rmax) {
     return half_sm > 2 * widest ? half_sm : 2 * widest;
 }
 constexpr int KV_GUARD = 3;
-__host__ __device__ inline size_t kv_smem_bytes(int rmax) { return (size_t)(KV_TH + 2 * rmax + KV_GUARD) * KV_TW * sizeof(double); }
+__host__ __device__ inline size_t kv_smem_bytes(int rmax, int th) { return (size_t)(th + 2 * rmax + KV_GUARD) * KV_TW * sizeof(double); }
 __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
     (void)n_scored;
     // ring + full/empty mbarrier per step + per-warp transpose buffers for the coalesced DoG stores
@@ -319,6 +322,7 @@ __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const d
     }
 }
 
+template <int KV_TH>
 __global__ void __launch_bounds__(KV_THREADS, 2)
 kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     extern __shared__ double smem[];

@@ -202,10 +202,40 @@ __device__ __forceinline__ double filled_at(const MbGeom& g, const double* __res
 // first trip enters the unrolled body at tap u0 = (K - R % K) % K (Duff's device) with the windows loaded in the state
 // u0 taps would have left them in, so there is no remainder loop and no padded tap.
 // ---------------------------------------------------------------------------------------------------------------
+// Radii below K never complete a trip of the unrolled loop; for them the whole support (K + 2R values) fits in
+// registers and the sum is written out with compile-time indices: no window rotation, no loop, no entry switch.
+template <int R, int K, int STRIDE>
+__device__ __forceinline__ void conv_small(const double* __restrict__ ctr, const double* __restrict__ tp, double (&acc)[K]) {
+    double x[K + 2 * R];
+#pragma unroll
+    for (int q = 0; q < K + 2 * R; ++q) x[q] = ctr[(q - R) * STRIDE];
+    const double w0 = tp[0];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = __dmul_rn(x[k + R], w0);
+#pragma unroll
+    for (int j = R; j >= 1; --j) {
+        const double w = tp[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(x[k + R - j], x[k + R + j]), w));
+    }
+}
+
 template <int K, int STRIDE>
 __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const int R, const double* __restrict__ tp,
                                            double (&acc)[K]) {
     static_assert(K == 8, "the unrolled body below is written for K = 8");
+    if (R < K) {
+        switch (R) {
+            case 1: conv_small<1, K, STRIDE>(ctr, tp, acc); break;
+            case 2: conv_small<2, K, STRIDE>(ctr, tp, acc); break;
+            case 3: conv_small<3, K, STRIDE>(ctr, tp, acc); break;
+            case 4: conv_small<4, K, STRIDE>(ctr, tp, acc); break;
+            case 5: conv_small<5, K, STRIDE>(ctr, tp, acc); break;
+            case 6: conv_small<6, K, STRIDE>(ctr, tp, acc); break;
+            default: conv_small<7, K, STRIDE>(ctr, tp, acc); break;
+        }
+        return;
+    }
     double pl[K], pr[K];
     const double w0 = tp[0];
 #pragma unroll

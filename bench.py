@@ -7,7 +7,7 @@ One JSON line on stdout (rank 0).  A "step" = one pass of the hot path (mask/fil
 DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over one synthetic batch:
   N=1 default workload = BASELINE.json configs[1]: synthetic 10k x 10k dense band (dpx 5000), 4 octaves x 12 sigma.
   N>1: every rank runs the same-shaped tile with its own seed (weak scaling); the only collective is the NCCL
-  all_gather of the candidate records before BH-FDR, inside the timed step.
+  gather of the candidate records to the rank that runs BH-FDR, inside the timed step.
 `value`  : contact-bins/s with the tile already resident in HBM, device time from CUDA events on the engine's stream.
 `e2e`    : same metric through the public API with the HOST tile: pinned host -> device copy of the band, all kernels,
            device -> host read of the records, per step, wall clock around synchronised calls.
@@ -212,7 +212,7 @@ def main():
     bytes_per_bin = BYTES_PER_BIN_PER_OCTAVE * n_oct
     config = {"workload": cfg["workload"], "n": cfg["n"], "dpx": cfg["dpx"], "octaves": cfg["octaves"],
               "blocks_per_gpu": cfg["blocks"], "l2": "inputs larger than L2 (band tile + axis-0 scratch >> 126 MB)",
-              "parallelism": "blocks sharded one set per GPU, NCCL all_gather of records only" if world > 1 else "single GPU"}
+              "parallelism": "blocks sharded one set per GPU, NCCL gather of the records to rank 0 only" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -251,7 +251,7 @@ def main():
         eng.run()
         if world > 1:                        # the path's only collective: candidate records, device to device over NCCL
             for b in range(B):
-                gather.all_gather_device(eng.records_device(b), world)
+                gather.gather_device_to_root(eng.records_device(b), world, rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -304,7 +304,7 @@ def main():
         e2e_upload()
         if world > 1:
             for b in range(B):
-                gather.all_gather_device(eng.records_device(b), world)
+                gather.gather_device_to_root(eng.records_device(b), world, rank)
         recs = [eng.records(b, sort=False, pinned=(B == 1)) for b in range(B)]
         return recs
 

@@ -83,16 +83,51 @@ def all_gather_device(dev_recs, world):
     import torch.distributed as dist
     dev = dev_recs["v"].device
     cnt = torch.tensor([dev_recs["n_found"], dev_recs["nz_count"]], dtype=torch.int64, device=dev)
-    cnts = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    cnts = torch.empty(world * 2, dtype=torch.int64, device=dev)        # flat: gloo only takes 1-D outputs here
     dist.all_gather_into_tensor(cnts, cnt)
-    sizes = cnts[:, 0].tolist()
+    sizes = cnts.view(world, 2)[:, 0].tolist()
     mx = max(max(sizes), 1)
     out = {}
     for name in ("rows", "cols", "v", "scored_index", "p"):
         src = dev_recs[name]
         pad = torch.zeros(mx, dtype=src.dtype, device=dev)
         pad[:src.numel()] = src
-        buf = torch.empty((world, mx), dtype=src.dtype, device=dev)
+        buf = torch.empty(world * mx, dtype=src.dtype, device=dev)
         dist.all_gather_into_tensor(buf, pad)
-        out[name] = buf
+        out[name] = buf.view(world, mx)
     return sizes, out
+
+
+_DEV_FIELDS = ("rows", "cols", "v", "scored_index", "p")
+
+
+def gather_device_to_root(dev_recs, world, rank, root=0):
+    """The candidate gather as the path needs it: only the rank that runs BH-FDR receives.  One collective of counts,
+    then ONE dist.gather of a byte buffer holding all five fields of the block (each padded to the longest rank), so the
+    cost is one launch plus the root's ingest instead of five all_gathers that every rank pays for.
+    Returns (sizes, {field: tensor [world, max_n]}) on the root, (sizes, None) elsewhere."""
+    import torch
+    import torch.distributed as dist
+    dev = dev_recs["v"].device
+    cnt = torch.tensor([dev_recs["n_found"], dev_recs["nz_count"]], dtype=torch.int64, device=dev)
+    cnts = torch.empty(world * 2, dtype=torch.int64, device=dev)        # flat: gloo only takes 1-D outputs here
+    dist.all_gather_into_tensor(cnts, cnt)
+    sizes = cnts.view(world, 2)[:, 0].tolist()
+    mx = max(max(sizes), 1)
+    widths = [dev_recs[name].element_size() for name in _DEV_FIELDS]
+    buf = torch.zeros(mx * sum(widths), dtype=torch.uint8, device=dev)
+    off = 0
+    for name, w in zip(_DEV_FIELDS, widths):
+        src = dev_recs[name]
+        buf[off:off + src.numel() * w] = src.contiguous().view(torch.uint8)
+        off += mx * w
+    outs = [torch.empty_like(buf) for _ in range(world)] if rank == root else None
+    dist.gather(buf, outs, dst=root)
+    if rank != root:
+        return sizes, None
+    stacked = torch.stack(outs)                                  # [world, mx * 28]
+    fields, off = {}, 0
+    for name, w in zip(_DEV_FIELDS, widths):
+        fields[name] = stacked[:, off:off + mx * w].contiguous().view(dev_recs[name].dtype).view(world, mx)
+        off += mx * w
+    return sizes, fields

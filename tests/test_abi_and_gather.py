@@ -84,7 +84,16 @@ def _gather_worker(rank, world, port, q):
                          pair=rng.random(m), nz_count=1000 + b))
         ids.append(b)
     got = gather.all_gather_records(recs, rank, world, torch.device("cpu"), block_ids=ids, with_pair=True)
-    q.put((rank, got, gather.pack_records(recs, 0, ids, with_pair=True)))
+    # the device-resident variants on CPU tensors: same collectives, gloo instead of NCCL
+    r0 = recs[0]
+    dev = dict(rows=torch.from_numpy(r0["rows"]), cols=torch.from_numpy(r0["cols"]), v=torch.from_numpy(r0["v"]),
+               scored_index=torch.from_numpy(r0["score_id"]), p=torch.from_numpy(r0["p"]), n_found=len(r0["rows"]),
+               nz_count=r0["nz_count"])
+    s_all, f_all = gather.all_gather_device(dev, world)
+    s_root, f_root = gather.gather_device_to_root(dev, world, rank)
+    ok = s_all == s_root and ((rank != 0 and f_root is None) or
+                              all(torch.equal(f_all[k][w, :s_all[w]], f_root[k][w, :s_all[w]]) for k in f_all for w in range(world)))
+    q.put((rank, got, gather.pack_records(recs, 0, ids, with_pair=True), ok))
     dist.destroy_process_group()
 
 
@@ -102,8 +111,9 @@ def test_gather_world_size_2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     full = np.concatenate([res[0][2], res[1][2]], axis=0)
-    for rank, got, _ in res:
+    for rank, got, _, root_gather_ok in res:
         assert np.array_equal(got, full)            # every rank sees every record, rank order, bit-exact
+        assert root_gather_ok                       # gather-to-root of a block == the all_gather of the same block
     by = gather.split_by_block(full)
     assert sorted(k[1] for k in by) == [0, 1, 2, 4]  # block 3 had no records
     r4 = by[(0, 4)]

@@ -15,9 +15,10 @@
 // into shared memory.  Axis-0 results are stored as V[step][block][i][j-i-vlo] for diagonals [vlo, vlo+wv), vlo = 2-rmax.
 //
 // Arithmetic: scipy's NI_Correlate1D symmetric branch,  out = x[0]*w[0]; for j=-R..-1: out += (x[j]+x[-j])*w[j],
-// with separate multiply and add (__dmul_rn/__dadd_rn are never contracted into FMA).  Each thread produces K = 8
-// consecutive outputs along the filter axis and keeps the two K-wide input windows in registers, sliding them by one
-// element per tap, so a tap costs 2 shared-memory loads + 1 constant load for 24 FP64 instructions.
+// with separate multiply and add (__dmul_rn/__dadd_rn are never contracted into FMA).  An FP64 instruction holds a
+// sub-partition's dispatch for two cycles and every other instruction costs most of a cycle on top (tools/fp64_peak.cu),
+// so the tap loops are written for the fewest instructions around the FP64 ones: register windows instead of reloads,
+// running pointers with compile-time offsets, no remainder loops.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
@@ -430,11 +431,11 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K_H: axis-1 pass, DoG chain, 3x3 maxima, extremum test, per-level statistics.  grid = (col tiles, row tiles, blocks)
-// Thread (lane = tile row, warp = group of 8 tile columns) owns 8 pixels for the whole chain and keeps their state
-// (previous Gaussian, best response, winning level, the maxima of the two previous DoGs) in registers; one CTA per SM.
-// The V_s rows of the tile are brought in by TMA bulk copies (cp.async.bulk, one per tile row, issued by warp 0) into a
-// two-stage ring guarded by mbarriers, so the copy for step s+1 is in flight while step s is filtered and scored.
+// K_H: axis-1 pass and DoG chain, written to HBM for K_S.  grid = (col tiles, row tiles, blocks), two CTAs per SM.
+// Thread (lane = tile row, warp = group of 8 tile columns) owns 8 pixels for the whole chain and keeps the previous
+// Gaussian in registers.  The axis-0 tile of every step arrives as ONE 3-D TMA box (cp.async.bulk.tensor through the
+// skewed tensor map, issued by an elected lane of warp 0) in a byte-granular shared-memory ring with a full / empty
+// mbarrier per step, up to KH_LOOKAHEAD steps ahead; tiles whose halo leaves the image take a generic staging path.
 // ---------------------------------------------------------------------------------------------------------------
 // max / min of finite doubles: one compare + select (fmax / fmin add NaN handling that costs ~3x the instructions; the
 // engine rejects non-finite tiles up front, mustache.py:755 would raise on them)

@@ -110,3 +110,23 @@ def test_mask_pixels_last_write_wins():
     xc = np.array([3, 3, 5, 0]); yc = np.array([9, 9, 8, 2]); vc = np.array([1.0, 7.0, 2.0, 4.0])
     r, c, v = tiler.block_mask_pixels(xc, yc, vc, 100)
     assert list(r) == [3] and list(c) == [9] and list(v) == [7.0]       # (5,8): d=3 < 4; (0,2): d=2
+
+
+@pytest.mark.parametrize("seed,n,dpx,missing,st,pt", [(101, 240, 90, 0.05, 0.6, 0.3), (102, 260, 300, 0.25, 0.4, 0.5),
+                                                      (103, 224, 70, 0.0, 0.88, 0.2), (104, 300, 120, 0.4, 0.3, 0.8)])
+def test_sparse_postprocess_equals_dense_oracle(seed, n, dpx, missing, st, pt):
+    """Seeded tiles the reference never saw (sparse masks, band wider than the tile, loose and tight thresholds): the
+    product's sparse post-processing must return exactly what the dense restatement of mustache.py:774-850 returns
+    from the same per-pixel state (coordinates, FDR and scale bit for bit; candidates near the tile border exercise the
+    negative-slice quirk of the sparsity windows)."""
+    c = synth.make_tile(n=n, dpx=dpx, seed=seed, blob_seed=seed + 50, nblobs=14, missing=missing)
+    res = osc.scale_space(c, dpx, [1.6, 3.2], use_scipy=True)
+    assert not res["skipped"] and res["nz_count"] >= 10000
+    nz, filled = osc.mask_and_fill(c, dpx)
+    ref = opost.loops_dense(filled, nz, res["p"], res["scale"], 7, dpx, st, pt)
+    found = res["p"] != 2
+    mr, mc = res["rows"], res["cols"]
+    loops, _ = postprocess.call_loops(n, dpx, 7, mr, mc, c[mr, mc], mr[found], mc[found], res["p"][found],
+                                      res["scale"][found], st=st, pt=pt)
+    key = lambda l: (l[0], l[1])
+    assert len(ref) > 0 and sorted(map(tuple, loops), key=key) == sorted(map(tuple, ref), key=key)

@@ -26,8 +26,22 @@ def _nan_to(value, fallback):
     return fallback if math.isnan(value) else value
 
 
+def _by_diagonal(dist, ndiag):
+    """Index lists of the contacts on diagonals 0..ndiag-1, each in the order a boolean mask `dist == d` selects them
+    (ascending position), from ONE stable sort instead of ndiag passes over all contacts."""
+    order = np.argsort(dist, kind="stable")
+    bounds = np.searchsorted(dist[order], np.arange(ndiag + 1), side="left")
+    return [order[bounds[d]:bounds[d + 1]] for d in range(ndiag)]
+
+
 def normalize_sparse(x, y, v, resolution, distance_in_px):
-    """In-place normalisation of `v`; returns the per-diagonal weights list the reference also returns (unused)."""
+    """In-place normalisation of `v`; returns the per-diagonal weights list the reference also returns (unused).
+
+    Same arithmetic on the same arrays in the same order as mustache.py:622-686 (bit-identical output, pinned by
+    tests/test_host_pipeline.py against a dump of the reference); only the selection of a diagonal's contacts differs:
+    the reference builds `distances == d` for every d (O(nnz * dpx), 80 % of its 3 s on chr21), here one stable sort."""
+    x = np.asarray(x)
+    y = np.asarray(y)
     n = max(max(x), max(y)) + 1
     weights = []
     dist = np.abs(y - x)
@@ -35,8 +49,7 @@ def normalize_sparse(x, y, v, resolution, distance_in_px):
         warnings.simplefilter("ignore", category=RuntimeWarning)
         if (n - distance_in_px) * resolution > LOCAL_WINDOW_BP:
             box = np.ones(int(LOCAL_WINDOW_BP / resolution))
-            for d in range(2 + distance_in_px):
-                on_diag = dist == d
+            for d, on_diag in enumerate(_by_diagonal(dist, 2 + distance_in_px)):
                 rows = x[on_diag]
                 line = np.zeros(n - d)
                 line[rows] = v[on_diag] + 0.001                       # mustache.py:635
@@ -65,8 +78,7 @@ def normalize_sparse(x, y, v, resolution, distance_in_px):
                 v[on_diag] = line[rows]
         else:
             np.nan_to_num(v, copy=False, neginf=0, posinf=0, nan=0)
-            for d in range(min(distance_in_px, n)):                   # mustache.py:674-675 (not 2+dpx)
-                on_diag = dist == d
+            for on_diag in _by_diagonal(dist, min(distance_in_px, n)):    # mustache.py:674-675 (not 2+dpx)
                 g_std = _nan_to(np.std(v[on_diag]), 1)
                 g_mean = _nan_to(np.mean(v[on_diag]), 0)
                 v[on_diag] = (v[on_diag] - g_mean) / g_std

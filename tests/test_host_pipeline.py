@@ -130,3 +130,26 @@ def test_sparse_postprocess_equals_dense_oracle(seed, n, dpx, missing, st, pt):
                                       res["scale"][found], st=st, pt=pt)
     key = lambda l: (l[0], l[1])
     assert len(ref) > 0 and sorted(map(tuple, loops), key=key) == sorted(map(tuple, ref), key=key)
+
+
+def test_normaliser_equals_literal_restatement(chr21):
+    """mustache_b200.normalize selects each diagonal's contacts from one stable sort; the literal restatement in
+    oracle/normalize.py builds `distances == d` per diagonal like mustache.py:632-633.  Same bits, both branches,
+    unsorted input, empty diagonals, contacts beyond the visited diagonals."""
+    from oracle import normalize as onorm
+    rng = np.random.default_rng(17)
+    n, dpx = 3000, 400
+    x = rng.integers(0, n - 450, size=9000)
+    d = rng.integers(0, dpx + 30, size=9000)
+    d[d == 33] = 34                                   # an empty diagonal
+    y = x + d
+    key = np.unique(x * 100000 + y, return_index=True)[1]
+    key = key[rng.permutation(len(key))]              # unsorted
+    x, y = x[key], y[key]
+    v = rng.gamma(2.0, 3.0, size=len(x))
+    for res in (5000, 500):                           # windowed branch / global branch ((n - dpx) * res <= 2 Mb)
+        a, b = v.copy(), v.copy()
+        wa = normalize.normalize_sparse(x, y, a, res, dpx)
+        wb = onorm.normalize_sparse(x, y, b, res, dpx)
+        assert wa == wb and np.array_equal(a, b)
+        assert not np.array_equal(a, v)

@@ -242,7 +242,7 @@ def regulator(f, norm_method, CHRM_SIZE, outdir, bed="", res=5000, sigma0=1.6, s
     if verbose:
         print("Normalizing contact map...")
     dpx = tiler.distance_in_px(distance_in_bp, res)
-    n = int(max(max(x), max(y)) + 1)
+    n = int(max(np.max(x), np.max(y)) + 1)
     normalize(x, y, v, res, dpx, eng=get_engine())
     if verbose:
         print("Loop calling...")

@@ -42,7 +42,7 @@ def normalize_sparse(x, y, v, resolution, distance_in_px):
     the reference builds `distances == d` for every d (O(nnz * dpx), 80 % of its 3 s on chr21), here one stable sort."""
     x = np.asarray(x)
     y = np.asarray(y)
-    n = max(max(x), max(y)) + 1
+    n = int(max(x.max(), y.max())) + 1                               # mustache.py:623
     weights = []
     dist = np.abs(y - x)
     with warnings.catch_warnings():

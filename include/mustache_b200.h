@@ -136,6 +136,11 @@ MB200_API int mb200_fetch_pair(mb200_engine* e, int block, int64_t capacity, dou
 MB200_API int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, double* v, int64_t nnz,
                                      int resolution, int distance_in_px, double* weights, int weights_cap, int* n_weights);
 
+/* Host-only inspection of the axis-0 kernel's plan (no engine, no device): the group every chain step is assigned to
+ * (steps of a group share the folded pair sums x[-j] + x[j], which do not depend on the Gaussian) and the FP64
+ * instructions per output pixel the plan costs, sum over groups of R_group*(2n+1)+n.  Either output may be NULL. */
+MB200_API int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, int64_t* fp64_per_output);
+
 /* Pinned host memory for callers that want full-speed uploads. */
 MB200_API int mb200_host_alloc(void** ptr, int64_t bytes);
 MB200_API int mb200_host_free(void* ptr);

@@ -1023,6 +1023,33 @@ int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, 
     return MB200_OK;
 }
 
+int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, int64_t* fp64_per_output) {
+    if (!radius || n_steps < 1 || n_steps > MB_MAX_STEPS) return MB200_ERR_ARG;
+    static MbProgram p;                      // host-only helper, no engine: large structs stay off the stack
+    static KvPlan kp;
+    memset(&p, 0, sizeof(p));
+    p.n_steps = n_steps;
+    int off = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        if (radius[s] < 1 || off + radius[s] + 1 > MB_MAX_TAPS) return MB200_ERR_ARG;
+        p.st[s].radius = radius[s];
+        p.st[s].tap_off = off;
+        off += radius[s] + 1;
+        p.rmax = std::max(p.rmax, (int)radius[s]);
+    }
+    int st = plan_kv(nullptr, p, kp);
+    if (st) return st;
+    long long cost = 0;
+    for (int gi = 0; gi < kp.n_groups; ++gi) {
+        const KvGroup& gr = kp.grp[gi];
+        cost += (long long)gr.rmax * (2 * gr.n + 1) + gr.n;
+        for (int slot = 0; slot < gr.n; ++slot)
+            if (group_of_step) group_of_step[gr.step[slot]] = gi;
+    }
+    if (fp64_per_output) *fp64_per_output = cost;
+    return MB200_OK;
+}
+
 int mb200_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return MB200_ERR_ARG;
     return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MB200_OK : MB200_ERR_NOMEM;

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mb200_fetch_pair": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_normalize_sparse": (C.c_int, [_H, _i32p, _i32p, _f64p, C.c_int64, C.c_int, C.c_int, _f64p, C.c_int,
                                          C.POINTER(C.c_int)]),
+    "mb200_kv_plan": (C.c_int, [C.c_int, _i32p, _i32p, _i64p]),
     "mb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "mb200_host_free": (C.c_int, [C.c_void_p]),
     "mb200_scale_space_dense": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _i32p, _i32p,

@@ -119,3 +119,27 @@ def test_gather_world_size_2_gloo():
     r4 = by[(0, 4)]
     assert r4["n_found"] == 11 and r4["nz_count"] == 1004 and "pair" in r4
     assert (np.diff(r4["rows"].astype(np.int64) * 4096 + r4["cols"]) >= 0).all()    # row-major within a block
+
+
+def test_kv_plan_is_a_partition_with_the_optimal_cost():
+    """The axis-0 kernel's grouping (host-only entry point, runs without a GPU): every step in exactly one group of at
+    most 5, groups ordered by radius, and the cost equals the dynamic programme bench.py restates for the roofline."""
+    import bench
+    from mustache_b200 import engine, ladder
+    lib = engine.load_library()
+    for octs in ([1.6, 3.2], [1.6, 3.2, 6.4, 12.8], [0.7, 1.4, 2.8], [2.3]):
+        prog = ladder.build_program(octs)
+        radius = np.array([s.radius for s in prog.steps], np.int32)
+        grp = np.full(len(radius), -1, np.int32)
+        cost = C.c_int64(0)
+        st = lib.mb200_kv_plan(len(radius), radius.ctypes.data_as(engine._i32p), grp.ctypes.data_as(engine._i32p), C.byref(cost))
+        assert st == 0 and (grp >= 0).all()
+        sizes = np.bincount(grp)
+        assert sizes.min() >= 1 and sizes.max() <= 5
+        by_radius = [sorted(radius[grp == g]) for g in range(len(sizes))]
+        assert all(a[-1] <= b[0] for a, b in zip(by_radius, by_radius[1:]))          # groups are contiguous in radius
+        assert cost.value == sum(r[-1] * (2 * len(r) + 1) + len(r) for r in by_radius)
+        ref_instr, exec_instr = bench.fp64_instr_per_bin(octs)
+        assert exec_instr == cost.value + int(sum(3 * r + 1 for r in radius))        # axis-0 plan + axis-1 pass
+        assert cost.value < sum(3 * r + 1 for r in radius)                            # sharing always pays
+    assert lib.mb200_kv_plan(0, None, None, None) != 0

@@ -66,6 +66,8 @@ MB200_API int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nb
  *  _band_host  : band layout [n][wsrc], element (i, k) = tile[i][i+4+k]  (host pointer) */
 MB200_API int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const int32_t* cols, const double* vals,
                           int64_t nnz);
+MB200_API int mb200_upload_coo_dev(mb200_engine* e, int block, const int32_t* rows_dev, const int32_t* cols_dev,
+                                   const double* vals_dev, int64_t nnz);   /* same, device pointers, complete before the call */
 MB200_API int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int64_t ld);
 MB200_API int mb200_upload_dense_dev(mb200_engine* e, int block, const double* tile_dev, int64_t ld);
 MB200_API int mb200_upload_band_host(mb200_engine* e, int block, const double* band, int64_t wsrc);
@@ -89,6 +91,24 @@ MB200_API int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, 
  * capacity, in which case only `capacity` are written). */
 MB200_API int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* rows, int32_t* cols, double* v,
                         int32_t* score_id, double* p, int64_t* n_out);
+
+/* Whole-batch forms (the reference collects every block's loops in one Manager().list(), mustache.py:913-914, 959).
+ * mb200_batch_counts: nz_count / n_found of every block (arrays of nblocks; no error for over-capacity blocks, so that a
+ * caller can size a retry).  mb200_pack_records: packs the records of all blocks contiguously on the device, block b at
+ * [offsets[b], offsets[b+1]) (offsets: nblocks + 1 entries); mb200_fetch_packed copies them to the host with one copy per
+ * field (sigma / pair may be NULL); mb200_packed_device hands out the device arrays (for an NCCL gather without a host
+ * round trip; valid until the next mb200_run / mb200_configure). */
+MB200_API int mb200_batch_counts(mb200_engine* e, int64_t* nz_count, int64_t* n_found);
+MB200_API int mb200_pack_records(mb200_engine* e, int64_t* offsets, int64_t* total);
+MB200_API int mb200_fetch_packed(mb200_engine* e, int64_t capacity, int32_t* rows, int32_t* cols, double* v, int32_t* score_id,
+                                 double* p, double* sigma, double* pair);
+MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, void** v, void** score_id, void** scored_index,
+                                  void** p, void** sigma, void** pair);
+
+/* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The
+ * reference's analogue is `-p`, the number of block processes alive at a time (mustache.py:931-934).  Takes effect at the
+ * next mb200_configure. */
+MB200_API int mb200_set_pass_limit(mb200_engine* e, int max_blocks);
 
 /* Optional: the detection scale (sigma_i, mustache.py:767 `Scales[...] = scales[o][i]`) of every scoring step, in chain
  * order; call after mb200_set_program.  mb200_fetch_sigma then returns, per record and in the order of

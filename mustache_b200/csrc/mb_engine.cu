@@ -59,6 +59,12 @@ struct mb200_engine {
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
     long long plane_v = 0, plane_l = 0;
+    int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
+    int ndiff = 0;                   // MB_FLAG_DIFFREF steps of the difference chain
+    // packed view of the batch's records (mb200_pack_records): block b occupies [pk_off[b], pk_off[b+1])
+    DevBuf pk_row, pk_col, pk_v, pk_sid, pk_p, pk_sigma, pk_pair, pk_sidx, pk_offsets;
+    std::vector<long long> pk_off;
+    bool packed = false;
 };
 
 namespace {
@@ -217,6 +223,7 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.dbgL = nullptr;
     g.fill = 2.0;                      // mustache.py:703-706
     g.dout = nullptr;
+    g.ndiff = e->ndiff;
     return g;
 }
 
@@ -359,7 +366,8 @@ void mb200_destroy(mb200_engine* e) {
                      &e->rec_col, &e->rec_v, &e->rec_sidx, &e->rec_p, &e->fit_loc, &e->fit_scale, &e->st_rows, &e->st_cols,
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
                      &e->d_score_id, &e->d_score_sigma, &e->rec_sid, &e->rec_sigma, &e->d_tmaps, &e->d_dtmaps, &e->nz_xs, &e->nz_ds, &e->nz_perm,
-                     &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines};
+                     &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines,
+                     &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -494,6 +502,7 @@ int mb200_set_diff_program(mb200_engine* e, int n_steps, const int32_t* radius, 
     }
     if (nd < 1) return fail(e, MB200_ERR_ARG, "the difference chain needs at least one MB200_STEP_DIFFREF step");
     if ((st = plan_kv(e, e->dprog, e->dkvplan))) return st;
+    e->ndiff = nd;
     e->have_dprog = true;
     e->configured = false;          // the TMA descriptors of the difference chain are built by mb200_configure
     return MB200_OK;
@@ -549,6 +558,16 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if ((st = ensure(e, e->d_score_sigma, MB_MAX_STEPS * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_loc, B * ns * sizeof(double)))) return st;
     if ((st = ensure(e, e->fit_scale, B * ns * sizeof(double)))) return st;
+    if (e->have_dprog && nblocks % 2 == 0 && e->dprog.rmax <= e->prog.rmax) {
+        // differential batches (blocks 2k / 2k+1 = the two maps of pair k): difference tile, its kept DoGs, norm.fit and
+        // pPair per record -- allocated here so that the scratch below is sized from what is really left
+        const size_t tile = (size_t)n * e->wc, np = B / 2;
+        if ((st = ensure(e, e->rawD, np * tile * sizeof(double)))) return st;
+        if ((st = ensure(e, e->dout, (size_t)e->ndiff * np * tile * sizeof(double)))) return st;
+        if ((st = ensure(e, e->dmu, (size_t)e->ndiff * np * sizeof(double)))) return st;
+        if ((st = ensure(e, e->dsd, (size_t)e->ndiff * np * sizeof(double)))) return st;
+        if ((st = ensure(e, e->rec_pair, B * e->rec_cap * sizeof(double)))) return st;
+    }
     // axis-0 scratch: as many blocks per pass as fit in ~80 % of what is free now (plus what V already holds)
     size_t free_b = 0, total_b = 0;
     CU(e, cudaMemGetInfo(&free_b, &total_b));
@@ -557,6 +576,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     long long fit = (long long)(budget / per_block);
     if (fit < 1) return fail(e, MB200_ERR_NOMEM, "axis-0 scratch for one block needs %zu bytes, %zu available", per_block, budget);
     e->pass_blocks = (int)std::min<long long>(fit, nblocks);
+    if (e->pass_limit > 0) e->pass_blocks = std::min(e->pass_blocks, e->pass_limit);
     if ((st = ensure(e, e->V, (size_t)e->pass_blocks * v_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     if ((st = ensure(e, e->Lb, (size_t)e->pass_blocks * l_bytes_per_block(e) + 2 * V_GUARD_BYTES))) return st;
     CU(e, cudaMemsetAsync(e->raw.p, 0, 2 * B * n * e->wc * sizeof(double), e->stream));
@@ -572,6 +592,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->configured = true;
     e->ran = false;
     e->counts_valid = false;
+    e->packed = false;
     return MB200_OK;
 }
 
@@ -599,9 +620,25 @@ int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const
     scatter_coo_kernel<<<grid, 256, 0, e->up_stream>>>((const int*)e->st_rows.p, (const int*)e->st_cols.p,
                                                        (const double*)e->st_vals.p, nnz, rawb, e->n, e->wc, e->dhi);
     CU(e, cudaGetLastError());
-    // the staging buffers are reused by the next upload: keep uploads ordered on the stream (they are) and make
-    // sure the host arrays may be released when this call returns
-    CU(e, cudaStreamSynchronize(e->up_stream));
+    // The staging buffers are reused by the next upload; uploads are ordered on up_stream, so the scatter above has read
+    // them before the next copies land.  The host arrays are pageable (numpy): cudaMemcpyAsync returns once they have been
+    // staged, so they may be released when this call returns; no stream synchronisation per block.
+    return MB200_OK;
+}
+
+int mb200_upload_coo_dev(mb200_engine* e, int block, const int32_t* rows_dev, const int32_t* cols_dev, const double* vals_dev,
+                         int64_t nnz) {
+    int st = check_block(e, block);
+    if (st) return st;
+    if (nnz < 0 || (nnz > 0 && (!rows_dev || !cols_dev || !vals_dev))) return fail(e, MB200_ERR_ARG, "bad COO arguments");
+    if ((st = use_device(e))) return st;
+    if ((st = begin_upload(e))) return st;
+    double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
+    CU(e, cudaMemsetAsync(rawb, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));
+    if (nnz == 0) return MB200_OK;
+    const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 8);
+    scatter_coo_kernel<<<grid, 256, 0, e->up_stream>>>(rows_dev, cols_dev, vals_dev, nnz, rawb, e->n, e->wc, e->dhi);
+    CU(e, cudaGetLastError());
     return MB200_OK;
 }
 
@@ -664,6 +701,7 @@ int mb200_run(mb200_engine* e) {
     e->launches = 0;
     e->counts_valid = false;
     e->ran_diff = false;
+    e->packed = false;
     if ((st = adopt_uploads(e))) return st;
     const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
     while ((int)e->ev_pass.size() < 4 * npass) {
@@ -747,6 +785,110 @@ int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* r
     CU(e, cudaMemcpyAsync(v, (double*)e->rec_v.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(p, (double*)e->rec_p.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_set_pass_limit(mb200_engine* e, int max_blocks) {
+    if (!e || max_blocks < 0) return MB200_ERR_ARG;
+    e->pass_limit = max_blocks;
+    e->configured = false;
+    return MB200_OK;
+}
+
+// Packs the records of every block of the batch into contiguous arrays (block b at [offsets[b], offsets[b+1])), on the
+// device: one kernel, so that a batch is fetched (or handed to NCCL) with one copy per field instead of one per block.
+int mb200_pack_records(mb200_engine* e, int64_t* offsets, int64_t* total) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured) return fail(e, MB200_ERR_ARG, "mb200_configure has not been called");
+    int st = use_device(e);
+    if (st) return st;
+    if ((st = refresh_counts(e))) return st;
+    const int B = e->nblocks;
+    e->pk_off.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+        if (e->h_nonfinite[b]) return fail(e, MB200_ERR_NONFINITE, "block %d holds non-finite values", b);
+        if ((long long)e->h_rec[b] > e->rec_cap)
+            return fail(e, MB200_ERR_CAPACITY, "block %d produced %llu records, capacity %lld", b, e->h_rec[b], e->rec_cap);
+        e->pk_off[b + 1] = e->pk_off[b] + (long long)e->h_rec[b];
+    }
+    const long long tot = e->pk_off[B];
+    if (offsets)
+        for (int b = 0; b <= B; ++b) offsets[b] = e->pk_off[b];
+    if (total) *total = tot;
+    if (!e->packed && tot > 0) {
+        const size_t m = (size_t)tot;
+        if ((st = ensure(e, e->pk_row, m * sizeof(int)))) return st;
+        if ((st = ensure(e, e->pk_col, m * sizeof(int)))) return st;
+        if ((st = ensure(e, e->pk_sid, m * sizeof(int)))) return st;
+        if ((st = ensure(e, e->pk_sidx, m * sizeof(int)))) return st;
+        if ((st = ensure(e, e->pk_v, m * sizeof(double)))) return st;
+        if ((st = ensure(e, e->pk_p, m * sizeof(double)))) return st;
+        if ((st = ensure(e, e->pk_sigma, m * sizeof(double)))) return st;
+        if (e->ran_diff && (st = ensure(e, e->pk_pair, m * sizeof(double)))) return st;
+        if ((st = ensure(e, e->pk_offsets, (size_t)(B + 1) * sizeof(long long)))) return st;
+        CU(e, cudaMemcpyAsync(e->pk_offsets.p, e->pk_off.data(), (size_t)(B + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+        const long long avg = tot / B + 1;
+        const int gx = (int)std::max<long long>(1, std::min<long long>((avg + 255) / 256, B >= 8 ? 32 : 148 * 4));
+        pack_records_kernel<<<dim3(gx, B), 256, 0, e->stream>>>(
+            (const long long*)e->pk_offsets.p, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, (const double*)e->rec_v.p,
+            (const int*)e->rec_sid.p, (const int*)e->rec_sidx.p, (const double*)e->rec_p.p, (const double*)e->rec_sigma.p,
+            e->ran_diff ? (const double*)e->rec_pair.p : nullptr, (int*)e->pk_row.p, (int*)e->pk_col.p, (double*)e->pk_v.p,
+            (int*)e->pk_sid.p, (int*)e->pk_sidx.p, (double*)e->pk_p.p, (double*)e->pk_sigma.p, (double*)e->pk_pair.p);
+        CU(e, cudaGetLastError());
+        e->launches += 1;
+    }
+    e->packed = true;
+    return MB200_OK;
+}
+
+int mb200_packed_device(mb200_engine* e, void** rows, void** cols, void** v, void** score_id, void** scored_index, void** p,
+                        void** sigma, void** pair) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->packed) return fail(e, MB200_ERR_ARG, "mb200_pack_records has not been called for this batch");
+    if (rows) *rows = e->pk_row.p;
+    if (cols) *cols = e->pk_col.p;
+    if (v) *v = e->pk_v.p;
+    if (score_id) *score_id = e->pk_sid.p;
+    if (scored_index) *scored_index = e->pk_sidx.p;
+    if (p) *p = e->pk_p.p;
+    if (sigma) *sigma = e->pk_sigma.p;
+    if (pair) *pair = e->ran_diff ? e->pk_pair.p : nullptr;
+    return MB200_OK;
+}
+
+int mb200_fetch_packed(mb200_engine* e, int64_t capacity, int32_t* rows, int32_t* cols, double* v, int32_t* score_id, double* p,
+                       double* sigma, double* pair) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->packed) return fail(e, MB200_ERR_ARG, "mb200_pack_records has not been called for this batch");
+    int st = use_device(e);
+    if (st) return st;
+    const long long tot = e->pk_off.back();
+    if (tot > capacity) return fail(e, MB200_ERR_CAPACITY, "%lld records, caller capacity %lld", tot, (long long)capacity);
+    if (pair && !e->ran_diff) return fail(e, MB200_ERR_ARG, "mb200_run_differential has not been called for this batch");
+    if (tot > 0) {
+        const size_t m = (size_t)tot;
+        if (rows) CU(e, cudaMemcpyAsync(rows, e->pk_row.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (cols) CU(e, cudaMemcpyAsync(cols, e->pk_col.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (score_id) CU(e, cudaMemcpyAsync(score_id, e->pk_sid.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (v) CU(e, cudaMemcpyAsync(v, e->pk_v.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (p) CU(e, cudaMemcpyAsync(p, e->pk_p.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (sigma) CU(e, cudaMemcpyAsync(sigma, e->pk_sigma.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (pair) CU(e, cudaMemcpyAsync(pair, e->pk_pair.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_batch_counts(mb200_engine* e, int64_t* nz_count, int64_t* n_found) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured) return fail(e, MB200_ERR_ARG, "mb200_configure has not been called");
+    int st = use_device(e);
+    if (st) return st;
+    if ((st = refresh_counts(e))) return st;
+    for (int b = 0; b < e->nblocks; ++b) {
+        if (nz_count) nz_count[b] = (int64_t)e->h_nz[b];
+        if (n_found) n_found[b] = (int64_t)e->h_rec[b];
+    }
     return MB200_OK;
 }
 
@@ -882,6 +1024,7 @@ int mb200_run_differential(mb200_engine* e) {
     for (int t = 0; t < e->prog.n_scored; ++t) oct_max = std::max(oct_max, e->prog.score_id[t] / 12);
     if (oct_max >= ndiff) return fail(e, MB200_ERR_ARG, "difference chain has %d octaves, main chain scores octave %d", ndiff, oct_max);
     const size_t tile = (size_t)e->n * e->wc;
+    if (ndiff != e->ndiff) return fail(e, MB200_ERR_ARG, "difference chain changed after mb200_configure");
     if ((st = ensure(e, e->rawD, (size_t)npairs * tile * sizeof(double)))) return st;
     if ((st = ensure(e, e->dout, (size_t)ndiff * npairs * tile * sizeof(double)))) return st;
     if ((st = ensure(e, e->dmu, (size_t)ndiff * npairs * sizeof(double)))) return st;
@@ -890,7 +1033,8 @@ int mb200_run_differential(mb200_engine* e) {
     diff_tile_kernel<<<dim3(148 * 2, npairs), 256, 0, e->stream>>>(raw_slot(e, e->slot_run), (double*)e->rawD.p, e->n, e->wc, e->dpx);
     CU(e, cudaGetLastError());
     CU(e, cudaMemsetAsync(e->dout.p, 0, (size_t)ndiff * npairs * tile * sizeof(double), e->stream));
-    // difference stack: same kernels, constant regions are 0 (c = zeros; c[nz] = c1[nz] - c2[nz]), nothing is scored
+    // difference stack: same kernels, constant regions are 0 (c = zeros; c[nz] = c1[nz] - c2[nz]), nothing is scored.
+    // dout is [pair][octave][n][wc], so every pass of pass_blocks pairs writes its own slice.
     for (int first = 0; first < npairs; first += e->pass_blocks) {
         const int nb = std::min(e->pass_blocks, npairs - first);
         MbGeom g = make_geom(e, 0, nb);
@@ -898,9 +1042,7 @@ int mb200_run_differential(mb200_engine* e) {
         g.fill = 0.0;
         g.rec_cap = 0;
         g.L = nullptr;                      // nothing is scored on the difference stack: its DoGs go to dout only
-        // dout is indexed [ndiff][nblk of the pass]; with several passes each pass writes its own slice per octave
-        if (npairs > e->pass_blocks) return fail(e, MB200_ERR_NOMEM, "differential batch does not fit one pass (%d pairs > %d)", npairs, e->pass_blocks);
-        g.dout = (double*)e->dout.p;
+        g.dout = (double*)e->dout.p + (size_t)first * ndiff * tile;
         if ((st = launch_pass(e, 0, nb, &g, nullptr, &e->dprog))) return st;
     }
     diff_stats_kernel<<<dim3(ndiff, npairs), 1024, 0, e->stream>>>(raw_slot(e, e->slot_run), (const double*)e->dout.p, e->n, e->wc,
@@ -909,9 +1051,10 @@ int mb200_run_differential(mb200_engine* e) {
     diff_pair_kernel<<<dim3(32, e->nblocks), 256, 0, e->stream>>>(
         (const unsigned long long*)e->rec_count.p, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p,
         (const int*)e->rec_sidx.p, (const int*)e->d_score_id.p, (const double*)e->dout.p, (const double*)e->dmu.p,
-        (const double*)e->dsd.p, e->n, e->wc, npairs, (double*)e->rec_pair.p);
+        (const double*)e->dsd.p, e->n, e->wc, ndiff, (double*)e->rec_pair.p);
     CU(e, cudaGetLastError());
     e->launches += 3;
+    CU(e, cudaEventRecord(e->ev_run[e->slot_run], e->stream));   // the difference kernels read the tile slot too
     e->ran_diff = true;
     return MB200_OK;
 }

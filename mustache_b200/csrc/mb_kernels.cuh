@@ -119,7 +119,8 @@ struct MbGeom {
     double* dbgG;                   // dense [n][n] (block 0 of the pass) or nullptr
     double* dbgL;                   // dense [n][n]: DoG formed at dbg_step
     double fill;                    // value of the constant regions (2.0; 0.0 for the difference stack of diff_mustache)
-    double* dout;                   // [n_diffref][nblk][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
+    double* dout;                   // [nblk][ndiff][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
+    int ndiff;                      // MB_FLAG_DIFFREF steps of the difference chain (octaves)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -656,7 +657,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const bool formed = !(flags & MB_FLAG_RESTART);
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
         if (keep && chunk_live) {
-            double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)prog.st[sl].score_idx * g.nblk + b) * g.n * g.wc
+            double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)b * g.ndiff + prog.st[sl].score_idx) * g.n * g.wc
                                             : g.L + ((size_t)sl * g.nblk + b) * g.plane_l;
             dst += qoff0;
             const double* xrd = xbuf + (lane >> 3) * KH_XP + kk;
@@ -971,6 +972,28 @@ finalise_kernel(const unsigned long long* __restrict__ rec_count, long long rec_
     }
 }
 
+// Records of the batch packed block after block (mb200_pack_records): grid = (x, blocks).
+__global__ void __launch_bounds__(256)
+pack_records_kernel(const long long* __restrict__ offsets, long long rec_cap, const int* __restrict__ row, const int* __restrict__ col,
+                    const double* __restrict__ v, const int* __restrict__ sid, const int* __restrict__ sidx,
+                    const double* __restrict__ p, const double* __restrict__ sigma, const double* __restrict__ pair,
+                    int* __restrict__ orow, int* __restrict__ ocol, double* __restrict__ ov, int* __restrict__ osid,
+                    int* __restrict__ osidx, double* __restrict__ op, double* __restrict__ osigma, double* __restrict__ opair) {
+    const int b = blockIdx.y;
+    const long long o0 = offsets[b], m = offsets[b + 1] - o0;
+    const size_t s0 = (size_t)b * rec_cap;
+    for (long long r = blockIdx.x * 256LL + threadIdx.x; r < m; r += (long long)gridDim.x * 256LL) {
+        orow[o0 + r] = row[s0 + r];
+        ocol[o0 + r] = col[s0 + r];
+        ov[o0 + r] = v[s0 + r];
+        osid[o0 + r] = sid[s0 + r];
+        osidx[o0 + r] = sidx[s0 + r];
+        op[o0 + r] = p[s0 + r];
+        osigma[o0 + r] = sigma[s0 + r];
+        if (pair != nullptr) opair[o0 + r] = pair[s0 + r];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tile preparation
 // ---------------------------------------------------------------------------------------------------------------
@@ -1066,7 +1089,7 @@ diff_stats_kernel(const double* __restrict__ raw, const double* __restrict__ dou
     const int o = blockIdx.x, pr = blockIdx.y;
     const double* r1 = raw + (size_t)(2 * pr) * n * wc;
     const double* r2 = raw + (size_t)(2 * pr + 1) * n * wc;
-    const double* dd = dout + ((size_t)o * npairs + pr) * n * wc;
+    const double* dd = dout + ((size_t)pr * gridDim.x + o) * n * wc;
     const long long total = (long long)n * wc;
     double s = 0.0, cnt = 0.0;
     for (long long e = threadIdx.x; e < total; e += 1024) {
@@ -1083,8 +1106,8 @@ diff_stats_kernel(const double* __restrict__ raw, const double* __restrict__ dou
     }
     const double ss = block_sum_1024(q, sh);
     if (threadIdx.x == 0) {
-        mu[(size_t)o * npairs + pr] = mean;
-        sd[(size_t)o * npairs + pr] = sqrt(ss / num);
+        mu[(size_t)pr * gridDim.x + o] = mean;
+        sd[(size_t)pr * gridDim.x + o] = sqrt(ss / num);
     }
 }
 
@@ -1093,7 +1116,7 @@ __global__ void __launch_bounds__(256)
 diff_pair_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const int* __restrict__ rec_row,
                  const int* __restrict__ rec_col, const int* __restrict__ rec_sidx,
                  const int* __restrict__ score_id, const double* __restrict__ dout, const double* __restrict__ mu,
-                 const double* __restrict__ sd, int n, int wc, int npairs, double* __restrict__ rec_pair) {
+                 const double* __restrict__ sd, int n, int wc, int ndiff, double* __restrict__ rec_pair) {
     const int b = blockIdx.y, pr = b >> 1;
     unsigned long long m = rec_count[b];
     if (m > (unsigned long long)rec_cap) m = rec_cap;
@@ -1101,8 +1124,8 @@ diff_pair_kernel(const unsigned long long* __restrict__ rec_count, long long rec
         const size_t o = (size_t)b * rec_cap + r;
         const int oct = score_id[rec_sidx[o]] / 12;                 // score id = octave*12 + i
         const int i = rec_row[o], j = rec_col[o];
-        const double x = dout[((size_t)oct * npairs + pr) * n * wc + (size_t)i * wc + (j - i - 4)];
-        double p = normcdf((x - mu[(size_t)oct * npairs + pr]) / sd[(size_t)oct * npairs + pr]);
+        const double x = dout[((size_t)pr * ndiff + oct) * n * wc + (size_t)i * wc + (j - i - 4)];
+        double p = normcdf((x - mu[(size_t)pr * ndiff + oct]) / sd[(size_t)pr * ndiff + oct]);
         if (!isfinite(p)) p = 1.0;                                  // np.nan_to_num(..., nan=1, posinf=1, neginf=1)
         if (p > 0.5) p = 1.0 - p;
         rec_pair[o] = 2.0 * p;

@@ -107,68 +107,57 @@ def diff_mustache(c1, c2, chromosome, chromosome2, res, start, end, mask_size, d
     return select_differential(n, distance_in_px, start, masks, recs, st, pt, pt2)
 
 
-def call_block_pairs(xyv1, xyv2, n, dpx, octave_values, st, pt, pt2, verbose=True, rank=0, world=1):
-    """Tile both normalised maps, run this rank's block pairs in one batch, gather, select.  Returns tagged loops
-    [[x, y, fdr, scale, tag]], tag 1/2/3/4 = loops1 / diffloops1 / loops2 / diffloops2 (diff_mustache.py:704-715)."""
-    from . import gather
-    chunk, start, end = tiler.block_geometry(n, dpx)
-    nb = len(start)
-    mine = [b for b in range(nb) if b % world == rank]
+def _pair_calls(dpx, st, pt, pt2):
+    """Selection of one block pair where it was computed (diff_mustache.py:428-569): calls carry the tag of the output
+    they belong to, 1/2/3/4 = loops1 / diffloops1 / loops2 / diffloops2 (diff_mustache.py:704-715)."""
+    def fn(task, recs, chunk, start):
+        out = []
+        for tag, loops in zip((1, 2, 3, 4), select_differential(chunk, dpx, start, task.maps, recs, st, pt, pt2)):
+            out += [[l[0], l[1], l[2], l[3], tag] for l in loops]
+        return out
+    return fn
+
+
+def call_chromosome_pairs(preps, n_chrom, dpx, octave_values, st, pt, pt2, verbose=True, rank=0, world=1, owners=None):
+    """Block pool of the differential run: preps = {chromosome index: dict(maps=[(x, y, v) map 1, (x, y, v) map 2], n)}
+    for the chromosomes this rank read.  Both tiles of a block pair stay on one GPU (the difference stack needs them and
+    their common mask).  Rank 0 receives {chromosome index: [[x, y, fdr, scale, tag]]}."""
+    from . import blockrun
     eng = get_engine()
     _set_octaves_diff(eng, octave_values)
-    masks = {}
+    return blockrun.shard_and_call(preps, n_chrom, dpx, 2, eng, _pair_calls(dpx, st, pt, pt2), rank=rank, world=world,
+                                   verbose=verbose, owners=owners, width=5)
 
-    def block_masks(b):
-        out = []
-        for (x, y, v) in (xyv1, xyv2):
-            xc, yc, vc = tiler.block_coo(x, y, v, start[b], end[b])
-            out.append(tiler.block_mask_pixels(xc, yc, vc, chunk))
-        return out
 
-    recs = {}
-    if mine:
-        eng.configure(chunk, dpx, 2 * len(mine))
-        for k, b in enumerate(mine):
-            if verbose:
-                print("Starting block ", b + 1, "/", nb, "...", sep="")
-            masks[b] = block_masks(b)
-            eng.upload_coo(2 * k, *masks[b][0])
-            eng.upload_coo(2 * k + 1, *masks[b][1])
-        eng.run_differential()
-        for k, b in enumerate(mine):
-            recs[b] = [eng.records(2 * k, pair=True), eng.records(2 * k + 1, pair=True)]
-    if world > 1:
-        import torch
-        dev = torch.device("cuda", eng.device) if torch.cuda.is_available() else torch.device("cpu")
-        flat = [recs[b][w] for b in mine for w in (0, 1)]
-        ids = [2 * b + w for b in mine for w in (0, 1)]
-        by = gather.split_by_block(gather.all_gather_records(flat, rank, world, dev, block_ids=ids, with_pair=True))
-        if rank != 0:
-            return []
-        lut = eng._sigma_lut()
-        recs = {}
-        for b in range(nb):
-            masks.setdefault(b, block_masks(b))
-            pair_recs = []
-            for w in (0, 1):
-                r = by.get((0, 2 * b + w))
-                if r is None:
-                    r = dict(rows=np.zeros(0, np.int32), cols=np.zeros(0, np.int32), v=np.zeros(0), p=np.zeros(0),
-                             score_id=np.zeros(0, np.int32), pair=np.zeros(0), nz_count=len(masks[b][w][0]))
-                r["sigma"] = lut[r["score_id"]]
-                pair_recs.append(r)
-            recs[b] = pair_recs
-    out = []
-    for b in range(nb):
-        ms = tiler.block_mask_size(b, start, end, dpx)
-        res4 = select_differential(chunk, dpx, start[b], masks[b], recs[b], st, pt, pt2)
-        for tag, loops in zip((1, 2, 3, 4), res4):
-            for loop in loops:
-                if tiler.keep_after_overlap(loop, start[b], ms):
-                    out.append([loop[0], loop[1], loop[2], loop[3], tag])
-        if verbose:
-            print("Block", b + 1, "done.")
-    return out
+def call_block_pairs(xyv1, xyv2, n, dpx, octave_values, st, pt, pt2, verbose=True, rank=0, world=1):
+    """Two normalised maps of one chromosome (held by rank 0).  Returns tagged loops [[x, y, fdr, scale, tag]] on rank 0."""
+    preps = {0: dict(maps=[tuple(np.asarray(a) for a in xyv1), tuple(np.asarray(a) for a in xyv2)], n=int(n))} if rank == 0 else {}
+    out = call_chromosome_pairs(preps, 1, dpx, octave_values, st, pt, pt2, verbose=verbose, rank=rank, world=world, owners=[0])
+    return [[l[0], l[1], l[2], l[3], int(l[4])] for l in out.get(0, [])]
+
+
+def prepare_pair(f1, f2, norm_method, CHRM_SIZE, res, distance_filter, bias1, bias2, chromosome, chromosome2, verbose=True):
+    """Read and normalise both maps of one chromosome (diff_mustache.py:602-635)."""
+    if verbose:
+        print("Reading contact map...")
+    maps = []
+    for f, b in ((f1, bias1), (f2, bias2)):
+        if f.endswith(".hic"):
+            got = readers.read_hic(f, norm_method, CHRM_SIZE, distance_filter, chromosome, chromosome2, res)
+        elif f.endswith(".cool") or f.endswith(".mcool"):
+            got = readers.read_cool(f, distance_filter, chromosome, chromosome2, norm_method, res)
+        else:
+            got = readers.read_text(f, distance_filter, b, chromosome, res)
+        if got is None or len(got[2]) == 0:
+            return None
+        maps.append([np.asarray(a) for a in got])
+    if verbose:
+        print("Normalizing contact map...")
+    dpx = tiler.distance_in_px(distance_filter, res)
+    n = int(max(max(m[0].max(), m[1].max()) + 1 for m in maps))
+    for m in maps:
+        normalize(m[0], m[1], m[2], res, dpx, eng=get_engine())
+    return dict(maps=[tuple(m) for m in maps], n=n)
 
 
 def regulator(f1, f2, norm_method, CHRM_SIZE, outdir, bed1="", bed2="", res=5000, sigma0=1.6, s=10, pt=0.1, pt2=0.1,
@@ -181,28 +170,16 @@ def regulator(f1, f2, norm_method, CHRM_SIZE, outdir, bed1="", bed2="", res=5000
         raise FileNotFoundError
     octave_values = [sigma0 * (2 ** i) for i in range(octaves)]
     rank, world = _dist_env()
-    if verbose:
-        print("Reading contact map...")
-    maps = []
-    for f, b in ((f1, bias1), (f2, bias2)):
-        if f.endswith(".hic"):
-            got = readers.read_hic(f, norm_method, CHRM_SIZE, distance_filter, chromosome, chromosome2, res)
-        elif f.endswith(".cool") or f.endswith(".mcool"):
-            got = readers.read_cool(f, distance_filter, chromosome, chromosome2, norm_method, res)
-        else:
-            got = readers.read_text(f, distance_filter, b, chromosome, res)
-        if got is None or len(got[2]) == 0:
-            return []
-        maps.append([np.asarray(a) for a in got])
-    if verbose:
-        print("Normalizing contact map...")
-    dpx = tiler.distance_in_px(distance_filter, res)
-    n = int(max(max(m[0].max(), m[1].max()) + 1 for m in maps))
-    for m in maps:
-        normalize(m[0], m[1], m[2], res, dpx, eng=get_engine())
+    preps = {}
+    if rank == 0:
+        prep = prepare_pair(f1, f2, norm_method, CHRM_SIZE, res, distance_filter, bias1, bias2, chromosome, chromosome2, verbose)
+        if prep is not None:
+            preps[0] = prep
     if verbose:
         print("Loop calling...")
-    return call_block_pairs(maps[0], maps[1], n, dpx, octave_values, st, pt, pt2, verbose=verbose, rank=rank, world=world)
+    dpx = tiler.distance_in_px(distance_filter, res)
+    out = call_chromosome_pairs(preps, 1, dpx, octave_values, st, pt, pt2, verbose=verbose, rank=rank, world=world, owners=[0])
+    return [[l[0], l[1], l[2], l[3], int(l[4])] for l in out.get(0, [])]
 
 
 def parse_args(args):

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mb200_set_program": (C.c_int, [_H, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int]),
     "mb200_configure": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mb200_upload_coo_host": (C.c_int, [_H, C.c_int, _i32p, _i32p, _f64p, C.c_int64]),
+    "mb200_upload_coo_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mb200_upload_dense_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "mb200_upload_dense_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "mb200_upload_band_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
@@ -36,6 +37,11 @@ SIGNATURES = {
     "mb200_sync": (C.c_int, [_H]),
     "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
     "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
+    "mb200_batch_counts": (C.c_int, [_H, _i64p, _i64p]),
+    "mb200_pack_records": (C.c_int, [_H, _i64p, _i64p]),
+    "mb200_fetch_packed": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _f64p, _f64p]),
+    "mb200_packed_device": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 8),
+    "mb200_set_pass_limit": (C.c_int, [_H, C.c_int]),
     "mb200_set_score_sigmas": (C.c_int, [_H, _f64p, C.c_int]),
     "mb200_fetch_sigma": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_records_device": (C.c_int, [_H, C.c_int] + [C.POINTER(C.c_void_p)] * 5 + [_i64p]),
@@ -147,6 +153,7 @@ class ScaleSpaceEngine:
             raise EngineError(st, "mb200_create(device=%d) failed" % device)
         self.device = int(device)
         self._pin = {}
+        self._keep = []
         self.program = None
         self.n = self.dpx = self.nblocks = None
 
@@ -213,6 +220,17 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_upload_coo_host(self.h, int(block), _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(vals, _f64p),
                                                  len(vals)))
 
+    def upload_coo_dev(self, block, rows, cols, vals):
+        """Block-local COO already on the engine's device (torch tensors: int32, int32, float64), complete on their stream."""
+        assert rows.is_cuda and rows.dtype.itemsize == 4 and vals.dtype.itemsize == 8 and rows.is_contiguous()
+        self._keep.append((rows, cols, vals))                 # the scatter runs asynchronously: keep the tensors alive
+        self._chk(self.lib.mb200_upload_coo_dev(self.h, int(block), C.c_void_p(rows.data_ptr()), C.c_void_p(cols.data_ptr()),
+                                                C.c_void_p(vals.data_ptr()), int(vals.numel())))
+
+    def set_pass_limit(self, max_blocks):
+        """At most this many blocks per pass of the kernels (0 = whatever fits); next configure()."""
+        self._chk(self.lib.mb200_set_pass_limit(self.h, int(max_blocks)))
+
     def upload_dense(self, block, tile):
         """tile: C-contiguous float64 numpy array (n x n) or anything with .data_ptr() on the engine's device."""
         if hasattr(tile, "data_ptr"):
@@ -237,6 +255,7 @@ class ScaleSpaceEngine:
 
     def sync(self):
         self._chk(self.lib.mb200_sync(self.h))
+        self._keep = []
 
     def counts(self, block):
         nz, nf = C.c_int64(0), C.c_int64(0)
@@ -271,6 +290,77 @@ class ScaleSpaceEngine:
         out = dict(rows=rows, cols=cols, v=v, p=p, score_id=sid, sigma=sig, nz_count=nz, n_found=nf)
         if pp is not None:
             out["pair"] = pp
+        return out
+
+    def batch_counts(self):
+        nz, nf = np.zeros(self.nblocks, np.int64), np.zeros(self.nblocks, np.int64)
+        self._chk(self.lib.mb200_batch_counts(self.h, _ptr(nz, _i64p), _ptr(nf, _i64p)))
+        self._keep = []                                       # the run has completed: device inputs may be released
+        return nz, nf
+
+    def pack(self):
+        """Pack the batch's records block after block on the device; returns the offsets array (nblocks + 1)."""
+        off = np.zeros(self.nblocks + 1, np.int64)
+        tot = C.c_int64(0)
+        self._chk(self.lib.mb200_pack_records(self.h, _ptr(off, _i64p), C.byref(tot)))
+        return off
+
+    def records_batch(self, sort=True, pair=False, pinned=True):
+        """Records of every block of the batch with ONE device -> host copy per field (page-locked staging).
+        Returns a list of per-block dicts like records(); with pinned=True the arrays are views of engine-owned buffers
+        that stay valid until the next records_batch() call (sort=True copies them)."""
+        off = self.pack()
+        tot = int(off[-1])
+        nz, _ = self.batch_counts()
+        if pinned:
+            rows, cols, sid = (self._pinned("b_" + k, tot, np.int32) for k in ("rows", "cols", "sid"))
+            v, p, sig = (self._pinned("b_" + k, tot, np.float64) for k in ("v", "p", "sigma"))
+            pp = self._pinned("b_pair", tot, np.float64) if pair else None
+        else:
+            rows, cols, sid = (np.empty(tot, np.int32) for _ in range(3))
+            v, p, sig = (np.empty(tot, np.float64) for _ in range(3))
+            pp = np.empty(tot, np.float64) if pair else None
+        self._chk(self.lib.mb200_fetch_packed(self.h, tot, _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(v, _f64p), _ptr(sid, _i32p),
+                                              _ptr(p, _f64p), _ptr(sig, _f64p), _ptr(pp, _f64p) if pair else None))
+        if sort and tot:
+            blk = np.repeat(np.arange(self.nblocks), np.diff(off))
+            order = np.lexsort((cols, rows, blk))
+            rows, cols, v, p, sid, sig = rows[order], cols[order], v[order], p[order], sid[order], sig[order]
+            if pair:
+                pp = pp[order]
+        out = []
+        for b in range(self.nblocks):
+            a, z = int(off[b]), int(off[b + 1])
+            r = dict(rows=rows[a:z], cols=cols[a:z], v=v[a:z], p=p[a:z], score_id=sid[a:z], sigma=sig[a:z],
+                     nz_count=int(nz[b]), n_found=z - a)
+            if pair:
+                r["pair"] = pp[a:z]
+            out.append(r)
+        return out
+
+    def packed_device(self):
+        """The packed record arrays as torch CUDA tensors aliasing the engine's buffers (no copy), plus offsets and the
+        per-block mask sizes: what the multi-GPU gather hands to NCCL."""
+        import torch
+        off = self.pack()
+        tot = int(off[-1])
+        nz, _ = self.batch_counts()
+        self.sync()
+        ptrs = [C.c_void_p() for _ in range(8)]
+        self._chk(self.lib.mb200_packed_device(self.h, *[C.byref(q) for q in ptrs]))
+
+        class _Alias:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = torch.device("cuda", self.device)
+        out = {}
+        names = ("rows", "cols", "v", "score_id", "scored_index", "p", "sigma", "pair")
+        for name, q, ts in zip(names, ptrs, ("<i4", "<i4", "<f8", "<i4", "<i4", "<f8", "<f8", "<f8")):
+            if q.value and tot:
+                out[name] = torch.as_tensor(_Alias(q.value, tot, ts), device=dev)
+            elif name != "pair":
+                out[name] = torch.empty(0, dtype=torch.int32 if ts == "<i4" else torch.float64, device=dev)
+        out.update(offsets=off, nz_count=nz)
         return out
 
     def records_device(self, block):

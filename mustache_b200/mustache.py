@@ -8,9 +8,9 @@ Same names, argument meaning and output as the reference (ay-lab/mustache v1.3.3
   process_block / mustache     mustache.py:945-960, 697-850   scale-space loop on the engine, post-processing on the host
 The hot path has no CPU fallback: without the CUDA library or a GPU these functions raise.
 
-Multi-GPU: when launched under torchrun (WORLD_SIZE > 1) the blocks of a chromosome are sharded round-robin over the
-ranks (blocks are independent, mustache.py:697-850), candidate records are all-gathered (the path's only collective)
-and rank 0 post-processes and writes the TSV.
+Multi-GPU: when launched under torchrun (WORLD_SIZE > 1) every chromosome is read and normalised by one owner rank, the
+blocks of all chromosomes are spread evenly over the ranks (blocks are independent, mustache.py:697-850; sharding.py),
+each rank post-processes what it computed and rank 0 gathers the calls and writes the TSV.
 """
 import argparse
 import os
@@ -19,7 +19,7 @@ import time
 
 import numpy as np
 
-from . import gather, postprocess, readers, tiler
+from . import postprocess, readers, sharding, tiler
 from .normalize import normalize, normalize_sparse
 
 _ENGINES = {}
@@ -154,100 +154,78 @@ def _dist_env():
     return rank, world
 
 
-def call_blocks(x, y, v, n, distance_in_px, octave_values, st, pt, verbose=True, rank=0, world=1, device=None,
-                timings=None):
-    """Tile a normalised chromosome, run every block of this rank's shard through the engine in one batch, gather
-    the records, post-process per block.  Returns the de-duplicated loop list (rank 0; other ranks get [])."""
-    chunk, start, end = tiler.block_geometry(n, distance_in_px)
-    nb = len(start)
-    mine = [b for b in range(nb) if b % world == rank]
-    masks = {}
-    t0 = time.time()
+def _block_calls(dpx, st, pt):
+    """Post-processing of one block where it was computed (mustache.py:774-850)."""
+    def fn(task, recs, chunk, start):
+        return _loops_from_records(chunk, dpx, start, task.maps[0], recs[0], st, pt)
+    return fn
+
+
+def call_chromosomes(preps, n_chrom, distance_in_px, octave_values, st, pt, verbose=True, rank=0, world=1, owners=None,
+                     timings=None):
+    """The block pool of `n_chrom` chromosomes: preps = {chromosome index: dict(maps=[(x, y, v)], n=bins)} for the
+    chromosomes this rank read and normalised.  Every block runs on exactly one rank (sharding.balanced_assignment),
+    is post-processed there, and rank 0 receives {chromosome index: de-duplicated loop list}."""
+    from . import blockrun
     eng = get_engine()
     _set_octaves(eng, octave_values)
-    recs = []
-    if mine:
-        eng.configure(chunk, distance_in_px, len(mine))
-        for k, b in enumerate(mine):
-            if verbose:
-                print("Starting block ", b + 1, "/", nb, "...", sep="")
-            xc, yc, vc = tiler.block_coo(x, y, v, start[b], end[b])
-            masks[b] = tiler.block_mask_pixels(xc, yc, vc, chunk)
-            eng.upload_coo(k, *masks[b])
-        eng.run()
-        recs = [eng.records(k) for k in range(len(mine))]
-        if timings is not None:
-            timings.append(eng.timing())
-    if world > 1:
-        import torch
-        dev = torch.device("cuda", eng.device) if torch.cuda.is_available() else torch.device("cpu")
-        packed = gather.all_gather_records(recs, rank, world, dev, block_ids=mine)
-        by_block = gather.split_by_block(packed)
-        if rank != 0:
-            return []
-        lut = eng._sigma_lut()
-        all_recs = {}
-        for b in range(nb):
-            r = by_block.get((0, b))
-            if r is not None:
-                r["sigma"] = lut[r["score_id"]]
-            all_recs[b] = r
-        # rank 0 needs every block's mask pixels for the post-processing
-        for b in range(nb):
-            if b not in masks:
-                xc, yc, vc = tiler.block_coo(x, y, v, start[b], end[b])
-                masks[b] = tiler.block_mask_pixels(xc, yc, vc, chunk)
+    return blockrun.shard_and_call(preps, n_chrom, distance_in_px, 1, eng, _block_calls(distance_in_px, st, pt), rank=rank,
+                                   world=world, verbose=verbose, owners=owners, timings=timings, width=4)
+
+
+def call_blocks(x, y, v, n, distance_in_px, octave_values, st, pt, verbose=True, rank=0, world=1, device=None,
+                timings=None):
+    """One normalised chromosome (held by rank 0; what other ranks pass is ignored): tile it, run every block on some
+    rank, post-process, return the de-duplicated loop list (rank 0; other ranks get [])."""
+    preps = {0: dict(maps=[(np.asarray(x), np.asarray(y), np.asarray(v))], n=int(n))} if rank == 0 else {}
+    out = call_chromosomes(preps, 1, distance_in_px, octave_values, st, pt, verbose=verbose, rank=rank, world=world,
+                           owners=[0], timings=timings)
+    return out.get(0, [])
+
+
+def prepare_chromosome(f, norm_method, CHRM_SIZE, res, distance_filter, bias, chromosome, chromosome2, verbose=True):
+    """Read and normalise one chromosome (mustache.py:877-895): returns dict(maps=[(x, y, v)], n=bins) or None."""
+    if verbose:
+        print("Reading contact map...")
+    if f.endswith(".hic"):
+        got = readers.read_hic(f, norm_method, CHRM_SIZE, distance_filter, chromosome, chromosome2, res)
+    elif f.endswith(".cool") or f.endswith(".mcool"):
+        got = readers.read_cool(f, distance_filter, chromosome, chromosome2, norm_method, res)
     else:
-        all_recs = dict(zip(mine, recs))
-    out = []
-    for b in range(nb):
-        rec = all_recs.get(b)
-        if rec is None:
-            if len(masks[b][0]) >= 50:
-                rec = dict(rows=np.zeros(0, np.int32), cols=np.zeros(0, np.int32), p=np.zeros(0), sigma=np.zeros(0),
-                           nz_count=len(masks[b][0]))
-        loops = _loops_from_records(chunk, distance_in_px, start[b], masks[b], rec, st, pt)
-        process_block(b, start, end, distance_in_px, loops, out)
-        if verbose:
-            print("Block", b + 1, "done.")
-    if timings is not None:
-        timings.append({"host_s": time.time() - t0})
-    return out
+        got = readers.read_text(f, distance_filter, bias, chromosome, res)
+    if got is None:
+        return None
+    x, y, v = got
+    if len(v) == 0:
+        return None
+    if verbose:
+        print("Normalizing contact map...")
+    dpx = tiler.distance_in_px(distance_filter, res)
+    n = int(max(np.max(x), np.max(y)) + 1)
+    normalize(x, y, v, res, dpx, eng=get_engine())      # in place
+    return dict(maps=[(np.asarray(x), np.asarray(y), np.asarray(v))], n=n)
 
 
 def regulator(f, norm_method, CHRM_SIZE, outdir, bed="", res=5000, sigma0=1.6, s=10, pt=0.1, st=0.88, octaves=2,
               verbose=True, nprocesses=4, distance_filter=2000000, bias=False, chromosome="n", chromosome2=None):
-    """mustache.py:853-942 with the block fan-out on the GPU.  Returns [[x, y, fdr, scale], ...] in bin units."""
+    """mustache.py:853-942 with the block fan-out on the GPU(s).  Returns [[x, y, fdr, scale], ...] in bin units."""
     if not chromosome2 or chromosome2 == "n":
         chromosome2 = chromosome
     if chromosome != chromosome2:
         print("Interchromosomal analysis is only supported for .hic and .cool input formats.")
         raise FileNotFoundError
     octave_values = [sigma0 * (2 ** i) for i in range(octaves)]
-    distance_in_bp = distance_filter
     rank, world = _dist_env()
-    if verbose:
-        print("Reading contact map...")
-    if f.endswith(".hic"):
-        got = readers.read_hic(f, norm_method, CHRM_SIZE, distance_in_bp, chromosome, chromosome2, res)
-    elif f.endswith(".cool") or f.endswith(".mcool"):
-        got = readers.read_cool(f, distance_in_bp, chromosome, chromosome2, norm_method, res)
-    else:
-        got = readers.read_text(f, distance_in_bp, bias, chromosome, res)
-    if got is None:
-        return []
-    x, y, v = got
-    if len(v) == 0:
-        return []
-    if verbose:
-        print("Normalizing contact map...")
-    dpx = tiler.distance_in_px(distance_in_bp, res)
-    n = int(max(np.max(x), np.max(y)) + 1)
-    normalize(x, y, v, res, dpx, eng=get_engine())
+    preps = {}
+    if rank == 0:                      # one reader per chromosome; the blocks are spread over all ranks afterwards
+        prep = prepare_chromosome(f, norm_method, CHRM_SIZE, res, distance_filter, bias, chromosome, chromosome2, verbose)
+        if prep is not None:
+            preps[0] = prep
     if verbose:
         print("Loop calling...")
-    return call_blocks(np.asarray(x), np.asarray(y), np.asarray(v), n, dpx, octave_values, st, pt, verbose=verbose,
-                       rank=rank, world=world)
+    dpx = tiler.distance_in_px(distance_filter, res)
+    out = call_chromosomes(preps, 1, dpx, octave_values, st, pt, verbose=verbose, rank=rank, world=world, owners=[0])
+    return out.get(0, [])
 
 
 def resolve_distance(dist_arg, res, cap=10000):
@@ -320,31 +298,55 @@ def main(argv=None):
         import pandas as pd
         csz = pd.read_csv(args.chrSize_file, header=None, sep="\t")
         chr_sizes = {"chr" + str(csz.iloc[i, 0]).replace("chr", ""): csz.iloc[i, 1] for i in range(csz.shape[0])}
-    for i, (chromosome, chromosome2) in enumerate(zip(chr_list, chr_list2)):
-        CHRM_SIZE = chr_sizes["chr" + str(chromosome).replace("chr", "")] if chr_sizes else False
-        biasf = False
-        if args.biasfile:
-            if os.path.exists(args.biasfile):
-                biasf = args.biasfile
-            else:
-                print("Error: Couldn't find specified bias file")
-                return
-        o = regulator(f, args.norm_method, CHRM_SIZE, args.outdir, bed=args.bed, res=res, sigma0=args.s_z, s=args.s,
-                      verbose=args.verbose and not quiet, pt=args.pt, st=args.st, distance_filter=distFilter,
-                      nprocesses=args.nprocesses, bias=biasf, chromosome=chromosome, chromosome2=chromosome2,
-                      octaves=args.octaves)
+    biasf = False
+    if args.biasfile:
+        if os.path.exists(args.biasfile):
+            biasf = args.biasfile
+        else:
+            print("Error: Couldn't find specified bias file")
+            return
+    for c1, c2 in zip(chr_list, chr_list2):
+        if c1 != c2:
+            print("Interchromosomal analysis is only supported for .hic and .cool input formats.")
+            raise FileNotFoundError
+    octave_values = [args.s_z * (2 ** k) for k in range(args.octaves)]
+    dpx = tiler.distance_in_px(distFilter, res)
+    verbose = args.verbose and not quiet
+    # The reference walks the chromosomes one after the other (mustache.py:1057).  Here a round of chromosomes is read
+    # and normalised by their owner ranks, and the blocks of the whole round form one pool spread over all GPUs.
+    per_round = max(8, 2 * world)
+    wrote_header = False
+    for r0 in range(0, len(chr_list), per_round):
+        names = chr_list[r0:r0 + per_round]
+        sizes = [chr_sizes["chr" + str(c).replace("chr", "")] for c in names] if chr_sizes else None
+        owners = sharding.chromosome_owners(len(names), world, sizes)
+        preps = {}
+        for k, chromosome in enumerate(names):
+            if owners[k] != rank:
+                continue
+            CHRM_SIZE = sizes[k] if sizes else False
+            prep = prepare_chromosome(f, args.norm_method, CHRM_SIZE, res, distFilter, biasf, chromosome, chromosome, verbose)
+            if prep is not None:
+                preps[k] = prep
+        if verbose:
+            print("Loop calling...")
+        found = call_chromosomes(preps, len(names), dpx, octave_values, args.st, args.pt, verbose=verbose, rank=rank,
+                                 world=world, owners=owners)
         if quiet:
             continue
-        if i == 0:
-            with open(args.outdir, "w") as out_file:
-                out_file.write(HEADER)
-        print("{0} loops found for chrmosome={1}, fdr<{2} in {3}sec".format(len(o), chromosome, args.pt,
-                                                                            "%.2f" % (time.time() - start_time)))
-        if o:
-            with open(args.outdir, "a") as out_file:
-                for loop in o:
-                    out_file.write(format_row(chromosome, chromosome2, loop, res))
-        start_time = time.time()
+        for k, chromosome in enumerate(names):
+            o = found.get(k, [])
+            if not wrote_header:
+                with open(args.outdir, "w") as out_file:
+                    out_file.write(HEADER)
+                wrote_header = True
+            print("{0} loops found for chrmosome={1}, fdr<{2} in {3}sec".format(len(o), chromosome, args.pt,
+                                                                                "%.2f" % (time.time() - start_time)))
+            if o:
+                with open(args.outdir, "a") as out_file:
+                    for loop in o:
+                        out_file.write(format_row(chromosome, chromosome, loop, res))
+            start_time = time.time()
 
 
 if __name__ == "__main__":

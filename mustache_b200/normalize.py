@@ -107,6 +107,7 @@ def normalize_sparse_device(eng, x, y, v, resolution, distance_in_px):
 
 def normalize(x, y, v, resolution, distance_in_px, eng=None):
     """What the CLI calls: the numpy normaliser (reference-exact), or the device one when MUSTACHE_NORMALIZE=device."""
-    if os.environ.get("MUSTACHE_NORMALIZE", "host") != "device" or eng is None:
+    integer_counts = np.asarray(v).dtype.kind in "iu"        # z-scores truncate into the integer array: numpy path only
+    if os.environ.get("MUSTACHE_NORMALIZE", "host") != "device" or eng is None or integer_counts:
         return normalize_sparse(x, y, v, resolution, distance_in_px)
     return normalize_sparse_device(eng, x, y, v, resolution, distance_in_px)

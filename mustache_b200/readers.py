@@ -70,7 +70,9 @@ def read_text(path, distance_in_bp, bias_path, chromosome, res):
     """mustache.py:254-297 (`read_pd`): 5-column (chr pos chr pos count) or 3-column (pos pos count) text.
 
     Returns upper-triangular COO (x, y, value) in bin units: |pos1-pos2| <= (distance/res + 1)*res, divided by both
-    biases (in that order), non-positive values dropped.
+    biases (in that order), non-positive values dropped.  The value column keeps the dtype pandas inferred, as in the
+    reference: integer counts without a bias file stay int64, and normalize_sparse then writes its z-scores into that
+    integer array, truncating them (mustache.py:668, 683) -- part of the reference's observable behaviour.
     """
     import pandas as pd
     sep = guess_separator(path)
@@ -83,9 +85,9 @@ def read_text(path, distance_in_bp, bias_path, chromosome, res):
             print("Could't read any interaction for this chromosome!")
             return None
         df = df[_chromosome_rows(df[2], chromosome)]
-        a, b, val = df[1].to_numpy(), df[3].to_numpy(), df[4].to_numpy(dtype=np.float64)
+        a, b, val = df[1].to_numpy(), df[3].to_numpy(), df[4].to_numpy()
     elif df.shape[1] == 3:
-        a, b, val = df[0].to_numpy(), df[1].to_numpy(), df[2].to_numpy(dtype=np.float64)
+        a, b, val = df[0].to_numpy(), df[1].to_numpy(), df[2].to_numpy()
     else:
         raise ValueError("expected a 3- or 5-column contact file, got %d columns" % df.shape[1])
     near = np.abs(a - b) <= limit

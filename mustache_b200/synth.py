@@ -100,3 +100,94 @@ def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed
         keep = a.data > 0
         x, y, v = a.row[keep].astype(np.int64), a.col[keep].astype(np.int64), a.data[keep].astype(np.float64)
     return x, y, v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 4 / 5: whole synthetic chromosomes as raw count maps
+# ------------------------------------------------------------------------------------------------------------------
+def _plant_loops(band, n, dpx, nloops, rng, boost, sign=+1):
+    """Adds (or with sign=-1 re-draws and removes) Poisson(boost) counts in a 3x3 patch around `nloops` random centres."""
+    d0 = rng.integers(12, dpx - 4, size=nloops)
+    i0 = (rng.random(nloops) * (n - d0 - 4)).astype(np.int64) + 2
+    inc = rng.poisson(boost, size=(nloops, 3, 3))
+    for a, di in enumerate((-1, 0, 1)):
+        for b, dj in enumerate((-1, 0, 1)):
+            np.add.at(band, (i0 + di, d0 + dj - di), sign * inc[:, a, b])
+    return i0, d0
+
+
+def poisson_band(n, dpx, lam_scale, seed, chunk_rows=2048):
+    """Raw counts in band layout [n][dpx + 2] (column = j - i, 0 .. dpx+1): Poisson(30) on the diagonal,
+    Poisson(lam_scale / (d + 1)) at distance d >= 1; cells past the chromosome end are 0."""
+    w = dpx + 2
+    lam = np.empty(w)
+    lam[0] = 30.0
+    lam[1:] = lam_scale / (np.arange(1, w) + 1.0)
+    rng = np.random.default_rng(seed)
+    band = np.empty((n, w), dtype=np.int32)
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        band[r0:r1] = rng.poisson(lam[None, :], size=(r1 - r0, w))
+    return band
+
+
+def _clip_band(band, n):
+    w = band.shape[1]
+    tail = min(n, w)
+    i = np.arange(n - tail, n)[:, None]
+    band[n - tail:][(i + np.arange(w)[None, :]) >= n] = 0
+    return band
+
+
+def band_counts_to_coo(band):
+    """Row-major upper-triangular COO (x, y, count) of a count band: the line order of the text files we write."""
+    i, k = np.nonzero(band)
+    return i.astype(np.int64), (i + k).astype(np.int64), band[i, k].astype(np.int64)
+
+
+def synthetic_chromosome(n, dpx, lam_scale, seed, nloops, loop_seed=None, loop_boost=8.0):
+    """One synthetic chromosome of configs 3 / 4: Poisson background + `nloops` planted 3x3 loops; COO of raw counts."""
+    band = poisson_band(n, dpx, lam_scale, seed)
+    if nloops:
+        _plant_loops(band, n, dpx, nloops, np.random.default_rng(seed + 1 if loop_seed is None else loop_seed), loop_boost)
+    return band_counts_to_coo(_clip_band(band, n))
+
+
+# name -> (n bins, resolution, dpx, lam_scale, background seed, loops, loop seed)
+CONFIG3 = dict(n=50000, res=1000, dpx=2000, lam_scale=4.0, seed=2001, nloops=2000, loop_seed=2002)
+# same geometry as config 3 (1 kb, N 4000, dpx 2000) but dense enough near the diagonal for loops to survive the
+# reference's sparsity filter (mustache.py:800-811 needs >= 60 % non-zero pixels in a (4s+1)^2 window): config 3 as
+# SURVEY defines it yields 0 loops in the reference
+CONFIG3D = dict(n=12000, res=1000, dpx=2000, lam_scale=60.0, seed=2101, nloops=1500, loop_seed=2102)
+CONFIG4 = {"s%d" % (k + 1): dict(n=10000 * (k + 1), res=5000, dpx=400, lam_scale=18.0, seed=3000 + k, nloops=40 * (k + 1),
+                                 loop_seed=3100 + k) for k in range(8)}
+CONFIG5 = dict(n=20000, res=5000, dpx=400, lam_scale=18.0, seed=4001, loop_seed=4002, thin_seed=4003, nloops=300, ndelete=100,
+               nadd=100, keep_prob=0.6)
+
+
+def config5_maps(n=20000, dpx=400, lam_scale=18.0, seed=4001, loop_seed=4002, thin_seed=4003, nloops=300, ndelete=100,
+                 nadd=100, keep_prob=0.6, loop_boost=8.0, **_):
+    """Config 5: map A = background + `nloops` loops; map B = binomial(keep_prob) thinning of map A without its last
+    `ndelete` loops, plus `nadd` loops of its own.  Returns two COO triples of raw counts."""
+    base = poisson_band(n, dpx, lam_scale, seed)
+    lrng = np.random.default_rng(loop_seed)
+    common = base.copy()
+    _plant_loops(common, n, dpx, nloops - ndelete, lrng, loop_boost)
+    a = common.copy()
+    _plant_loops(a, n, dpx, ndelete, lrng, loop_boost)
+    trng = np.random.default_rng(thin_seed)
+    b = trng.binomial(common, keep_prob).astype(np.int32)
+    _plant_loops(b, n, dpx, nadd, trng, loop_boost)
+    return band_counts_to_coo(_clip_band(a, n)), band_counts_to_coo(_clip_band(b, n))
+
+
+def write_contact_text(path, chrom, x, y, counts, res, mode="w"):
+    """5-column contact text (chr pos chr pos count) in the style of the reference's bundled data/chr21_5kb.RAWobserved:
+    counts written as '3.0', so that read_pd (mustache.py:254-297) yields float64 values as it does for that file."""
+    name = str(chrom)
+    with open(path, mode) as f:
+        step = 1 << 20
+        for s in range(0, len(x), step):
+            xs, ys, cs = x[s:s + step] * res, y[s:s + step] * res, counts[s:s + step]
+            f.write("".join([name + "\t%d\t" % a + name + "\t%d\t%d.0\n" % (b, c) for a, b, c in zip(xs.tolist(), ys.tolist(), cs.tolist())]))
+    return path

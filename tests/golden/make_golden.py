@@ -193,6 +193,166 @@ def make_diffcli():
         print(suf, len(body))
 
 
+def _sorted_body(path):
+    lines = open(path).read().splitlines()
+    return lines[0], sorted(lines[1:], key=lambda s: (s.split("\t")[0], int(s.split("\t")[1]), int(s.split("\t")[4])))
+
+
+def _res_arg(res):
+    return "%dkb" % (res // 1000)
+
+
+def make_cfg3():
+    """BASELINE configs[2]: synthetic 50k-bin chromosome at 1 kb through the reference CLI, plus the
+    mustache() dumps of two of its 4000 x 4000 blocks (replaying regulator()'s tiling in-process)."""
+    import math
+    import time
+    from mustache_b200 import synth as gen
+    spec = gen.CONFIG3
+    tmp = "/tmp/_golden_cfg3"
+    os.makedirs(tmp, exist_ok=True)
+    x, y, c = gen.synthetic_chromosome(**{k: v for k, v in spec.items() if k != "res"})
+    path = gen.write_contact_text(os.path.join(tmp, "cfg3.txt"), "chrS", x, y, c, spec["res"])
+    out = os.path.join(tmp, "out.tsv")
+    t0 = time.time()
+    rr.run_cli(["-f", path, "-ch", "chrS", "-r", _res_arg(spec["res"]), "-pt", "0.1", "-st", "0.8", "-p", "8", "-o", out])
+    print("cfg3 reference CLI: %.1f s" % (time.time() - t0))
+    head, body = _sorted_body(out)
+    with open(os.path.join(HERE, "cfg3_loops.tsv"), "w") as f:
+        f.write("\n".join([head] + body) + "\n")
+    print("cfg3:", len(body), "loops")
+    # block dumps
+    m = rr.load_module("mustache")
+    hooks = rr.bh_hooks()
+    res, dpx = spec["res"], spec["dpx"]
+    xx, yy, vv = m.read_pd(path, 2000000, False, "chrS", res)
+    xx, yy = np.asarray(xx), np.asarray(yy)
+    m.normalize_sparse(xx, yy, vv, res, dpx)
+    n = max(max(xx), max(yy)) + 1
+    chunk = max(2 * dpx, 2000)
+    outz = dict(n=n, dpx=dpx, nnz=len(vv), v_sum=np.float64(vv.sum()))
+    for b in CFG3_DUMP_BLOCKS:
+        s0 = b * (chunk - dpx)
+        sel = (xx >= s0) & (xx < s0 + chunk) & (yy >= s0) & (yy < s0 + chunk)
+        cc = np.zeros((chunk, chunk))
+        cc[xx[sel] - s0, yy[sel] - s0] = vv[sel]
+        d = Dump()
+        hooks.append(d)
+        loops = m.mustache(cc, "chrS", "chrS", res, [], s0, s0 + chunk, -1, dpx, [1.6, 3.2], 0.8, 0.1)
+        hooks.remove(d)
+        outz["b%d_loops" % b] = _loops_arr(loops)
+        _pack("b%d_" % b, d.items[0], outz)
+        print("cfg3 block", b, "mask", d.items[0]["nz_count"], "found", len(d.items[0]["p"]), "loops", len(loops))
+    np.savez_compressed(os.path.join(HERE, "cfg3_blocks.npz"), **outz)
+
+
+CFG3_DUMP_BLOCKS = (0, 11)
+
+
+def make_cfg3d():
+    """Denser 1 kb chromosome (same block geometry as config 3): the reference CLI finds loops here."""
+    import time
+    from mustache_b200 import synth as gen
+    spec = gen.CONFIG3D
+    tmp = "/tmp/_golden_cfg3d"
+    os.makedirs(tmp, exist_ok=True)
+    x, y, c = gen.synthetic_chromosome(**{k: v for k, v in spec.items() if k != "res"})
+    path = gen.write_contact_text(os.path.join(tmp, "cfg3d.txt"), "chrT", x, y, c, spec["res"])
+    out = os.path.join(tmp, "out.tsv")
+    t0 = time.time()
+    rr.run_cli(["-f", path, "-ch", "chrT", "-r", _res_arg(spec["res"]), "-pt", "0.1", "-st", "0.8", "-p", "8", "-o", out])
+    head, body = _sorted_body(out)
+    with open(os.path.join(HERE, "cfg3d_loops.tsv"), "w") as f:
+        f.write("\n".join([head] + body) + "\n")
+    print("cfg3d:", len(body), "loops, %.1f s" % (time.time() - t0))
+
+
+def make_cfg4():
+    """BASELINE configs[3]: the 8 synthetic chromosomes (10k..80k bins at 5 kb), reference CLI per chromosome."""
+    import time
+    from mustache_b200 import synth as gen
+    tmp = "/tmp/_golden_cfg4"
+    os.makedirs(tmp, exist_ok=True)
+    rows, head = [], None
+    for name, spec in gen.CONFIG4.items():
+        x, y, c = gen.synthetic_chromosome(**{k: v for k, v in spec.items() if k != "res"})
+        path = gen.write_contact_text(os.path.join(tmp, name + ".txt"), name, x, y, c, spec["res"])
+        out = os.path.join(tmp, name + ".tsv")
+        t0 = time.time()
+        rr.run_cli(["-f", path, "-ch", name, "-r", _res_arg(spec["res"]), "-pt", "0.1", "-st", "0.8", "-p", "8", "-o", out])
+        head, body = _sorted_body(out)
+        rows += body
+        print("cfg4", name, len(body), "loops, %.1f s" % (time.time() - t0), flush=True)
+    with open(os.path.join(HERE, "cfg4_loops.tsv"), "w") as f:
+        f.write("\n".join([head] + rows) + "\n")
+
+
+def make_cfg5():
+    """BASELINE configs[4]: differential CLI on two synthetic 20k-bin maps, -pt 0.05 -pt2 0.1."""
+    from mustache_b200 import synth as gen
+    spec = gen.CONFIG5
+    tmp = "/tmp/_golden_cfg5"
+    os.makedirs(tmp, exist_ok=True)
+    A, B = gen.config5_maps(**spec)
+    fa = gen.write_contact_text(os.path.join(tmp, "mapA.txt"), "chrD", *A, spec["res"])
+    fb = gen.write_contact_text(os.path.join(tmp, "mapB.txt"), "chrD", *B, spec["res"])
+    outp = os.path.join(tmp, "out")
+    rr.run_cli(["-f1", fa, "-f2", fb, "-ch", "chrD", "-r", _res_arg(spec["res"]), "-pt", "0.05", "-pt2", "0.1", "-st", "0.8",
+                "-p", "8", "-o", outp], which="diff_mustache")
+    for suf in ("loop1", "loop2", "diffloop1", "diffloop2"):
+        head, body = _sorted_body(outp + "." + suf)
+        with open(os.path.join(HERE, "cfg5_%s.tsv" % suf), "w") as f:
+            f.write("\n".join([head] + body) + "\n")
+        print("cfg5", suf, len(body))
+
+
+class _FitSpy:
+    """Stands in for `expon` inside the reference module: records every fit() result, forwards everything else."""
+
+    def __init__(self, real):
+        self._real, self.fits = real, []
+
+    def fit(self, *a, **k):
+        r = self._real.fit(*a, **k)
+        self.fits.append(r)
+        return r
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
+def make_cfg2():
+    """BASELINE configs[1] at full size: the 10k x 10k dense band, 4 octaves, through the reference's mustache() once
+    (about 10 minutes and 13 GB on one core).  Commits the 36 exponential fits, a digest of the sorted records and a
+    sample of the p-values -- the records themselves (1.3 M) are too large for a fixture."""
+    import time
+    from mustache_b200 import synth as gen
+    m = rr.load_module("mustache")
+    hooks = rr.bh_hooks()
+    n, dpx, octs = 10000, 5000, [1.6, 3.2, 6.4, 12.8]
+    cc = gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=1001, blob_seed=1002, nblobs=200), n)
+    spy = _FitSpy(m.expon)
+    m.expon = spy
+    d = Dump()
+    hooks.append(d)
+    t0 = time.time()
+    loops = m.mustache(cc, "1", "1", 2000, [], 0, n, -1, dpx, octs, 0.88, 0.1)
+    hooks.remove(d)
+    m.expon = spy._real
+    print("cfg2 reference mustache(): %.1f s" % (time.time() - t0))
+    it = d.items[0]
+    h = hashlib.sha256()
+    for k in ("rows", "cols", "v", "scale"):
+        h.update(np.ascontiguousarray(it[k]).tobytes())
+    step = 997
+    np.savez_compressed(os.path.join(HERE, "cfg2_tile.npz"), fits=np.array(spy.fits, dtype=np.float64),
+                        n_found=len(it["p"]), nz_count=it["nz_count"], digest=np.frombuffer(h.digest(), np.uint8),
+                        sample_step=step, sample_rows=it["rows"][::step], sample_cols=it["cols"][::step],
+                        sample_v=it["v"][::step], sample_scale=it["scale"][::step], sample_p=it["p"][::step],
+                        p_sum=np.float64(it["p"].sum()), loops=_loops_arr(loops))
+    print("cfg2: mask", it["nz_count"], "found", len(it["p"]), "loops", len(loops), "fits", len(spy.fits))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["input", "cli", "blocks", "synth", "diff", "diffcli"]
     for w in what:

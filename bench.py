@@ -1,22 +1,31 @@
 #!/usr/bin/env python3
 """Benchmark of the scale-space hot path (BASELINE.json metric: contact-bins/sec through the full scale-space).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3s|chr]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5|chr|3s]
 
 One JSON line on stdout (rank 0).  A "step" = one pass of the hot path (mask/fills, every Gaussian of every octave,
-DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over one synthetic batch:
-  N=1 default workload = BASELINE.json configs[1]: synthetic 10k x 10k dense band (dpx 5000), 4 octaves x 12 sigma.
-  N>1: every rank runs the same-shaped tile with its own seed (weak scaling); the only collective is the NCCL
-  gather of the candidate records to the rank that runs BH-FDR, inside the timed step.
-`value`  : contact-bins/s with the tile already resident in HBM, device time from CUDA events on the engine's stream.
-`e2e`    : same metric through the public API with the HOST tile: pinned host -> device copy of the band, all kernels,
-           device -> host read of the records, per step, wall clock around synchronised calls.
-`--impl reference` times the reference's CPU algorithm (oracle port on scipy, i.e. the same scipy.ndimage C kernels
-mustache.py calls) on all host cores over a bounded sample of the same workload.
+DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over one synthetic batch.
+
+  --config 2 (default)  BASELINE configs[1]: synthetic 10k x 10k dense band (dpx 5000), 4 octaves x 12 sigma; with N > 1
+                        every rank runs the same-shaped tile with its own seed (weak scaling).  The line also carries a
+                        "config4" object: the 226-block workload of BASELINE configs[3] through the product's sharded
+                        path at this N (strong scaling: compare the objects of the N = 1, 2, 4, 8 lines).
+  --config 3 / 4 / 5    BASELINE configs[2] / [3] / [4] in full: the synthetic chromosomes of SURVEY 8(d) generated,
+                        normalised and tiled exactly as the CLI does, the block pool spread over the N ranks by
+                        mustache_b200.blockrun (owner ranks prepare, all_to_all exchange of block COO): strong scaling.
+  --config chr / 3s     dense-band stand-ins of the 5 kb / 1 kb block shapes (24 x 2000^2, 6 x 4000^2).
+
+`value`  : contact-bins/s with the tiles already resident in HBM, device time from CUDA events on the engine's stream
+           (N > 1: wall clock around synchronised, barrier-bracketed steps, max over ranks).
+`e2e`    : same metric through the public API with HOST buffers: host -> device upload of every tile (dense pinned tile
+           for config 2, block COO for the chromosome configs), all kernels, ONE packed device -> host read of the
+           records per batch, and for N > 1 the gather of the per-block result rows on the rank that writes the TSV.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, mustache.py:697-778 up to the intercepted
+multipletests call) on all host cores over a bounded sample of the same workload; when baseline/_ref is absent, the
+oracle port on the same scipy kernels.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -32,13 +41,21 @@ BYTES_PER_BIN_PER_OCTAVE = 272          # (12 reads + 11 writes 
 FP64_INSTR_PEAK = 1.849e13              # measured on this pool's B200 with tools/fp64_peak.cu (profiles/fp64_peak_r01.jsonl)
 
 CONFIGS = {
-    # name: (n, dpx, octaves, blocks per rank, description)
-    "2": dict(n=10000, dpx=5000, octaves=[1.6, 3.2, 6.4, 12.8], blocks=1,
+    "2": dict(kind="dense", n=10000, dpx=5000, octaves=[1.6, 3.2, 6.4, 12.8], blocks=1,
               workload="synthetic 10k x 10k dense band (dpx 5000), 4 octaves x 12 sigma (BASELINE configs[1])"),
-    "3s": dict(n=4000, dpx=2000, octaves=[1.6, 3.2], blocks=6,
-               workload="6 blocks of a synthetic 1kb-style band (N 4000, dpx 2000), 2 octaves (slice of configs[2])"),
-    "chr": dict(n=2000, dpx=400, octaves=[1.6, 3.2], blocks=24,
-                workload="24 dense-band blocks of 2000 x 2000 (dpx 400), 2 octaves (5 kb chromosome shape, configs[3])"),
+    "3s": dict(kind="dense", n=4000, dpx=2000, octaves=[1.6, 3.2], blocks=6,
+               workload="6 dense-band blocks of 4000 x 4000 (dpx 2000), 2 octaves (1 kb block shape)"),
+    "chr": dict(kind="dense", n=2000, dpx=400, octaves=[1.6, 3.2], blocks=24,
+                workload="24 dense-band blocks of 2000 x 2000 (dpx 400), 2 octaves (5 kb block shape)"),
+    "3": dict(kind="chrom", n=4000, dpx=2000, octaves=[1.6, 3.2], maps=1,
+              workload="synthetic 50k-bin chromosome at 1 kb, Poisson(4/(d+1)) + 2000 loops, normalised, 24 blocks of "
+                       "4000 x 4000 (dpx 2000), 2 octaves (BASELINE configs[2])"),
+    "4": dict(kind="chrom", n=2000, dpx=400, octaves=[1.6, 3.2], maps=1,
+              workload="8 synthetic chromosomes of 10k..80k bins at 5 kb, Poisson(18/(d+1)) + loops, normalised, 226 blocks "
+                       "of 2000 x 2000 (dpx 400), 2 octaves (BASELINE configs[3])"),
+    "5": dict(kind="chrom", n=2000, dpx=400, octaves=[1.6, 3.2], maps=2,
+              workload="differential: two synthetic 20k-bin maps at 5 kb (map B = 0.6 thinning of A, 100 loops deleted, 100 "
+                       "added), 13 block pairs x 3 filter stacks, 2 octaves (BASELINE configs[4])"),
 }
 
 
@@ -64,12 +81,14 @@ def fp64_instr_per_bin(octaves, dedupe=True):
 
 
 def load_traffic():
-    """DRAM bytes per launch of the three kernels from the committed `ncu --set full` capture of this workload
-    (profiles/traffic_r01.json, written by tools/ncu_summary.py --traffic); None when the capture is for another config."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-    except Exception:
-        return None
+    """DRAM bytes per launch of the kernels from the committed `ncu --set full` captures (profiles/traffic_r02.json, else
+    round 1's), keyed by config name."""
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -119,8 +138,11 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_host_tiles(cfg, rank, pinned=True):
-    """Synthetic tiles in the reference-facing form: dense row-major N x N float64 (pinned host memory)."""
+# ------------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------------
+def make_host_tiles(cfg, rank):
+    """Dense-band workloads in the reference-facing form: dense row-major N x N float64 tiles in pinned host memory."""
     from mustache_b200 import synth as gen
     from mustache_b200.engine import PinnedBuffer
     n, dpx = cfg["n"], cfg["dpx"]
@@ -128,13 +150,10 @@ def make_host_tiles(cfg, rank, pinned=True):
     for b in range(cfg["blocks"]):
         band = gen.dense_band_tile(n, dpx, seed=1001 + 100 * rank + 7 * b, blob_seed=1002 + 100 * rank + 7 * b,
                                    nblobs=200 if n >= 4000 else 40)
-        if pinned:
-            buf = PinnedBuffer((n, n))
-            keep.append(buf)
-            dense = buf.array
-            dense[:] = 0.0
-        else:
-            dense = np.zeros((n, n))
+        buf = PinnedBuffer((n, n))
+        keep.append(buf)
+        dense = buf.array
+        dense[:] = 0.0
         w = band.shape[1]
         safe = max(0, min(n, n - 4 - w + 1))
         if safe > 0:
@@ -148,22 +167,62 @@ def make_host_tiles(cfg, rank, pinned=True):
     return tiles, keep
 
 
+def chromosome_specs(name):
+    """[(chromosome name, generator kwargs, res)] of a chromosome config, as tests/golden/make_golden.py fed the reference."""
+    from mustache_b200 import synth as gen
+    if name == "3":
+        return [("chrS", dict(gen.CONFIG3))]
+    if name == "4":
+        return [(k, dict(v)) for k, v in gen.CONFIG4.items()]
+    if name == "5":
+        return [("chrD", dict(gen.CONFIG5))]
+    raise KeyError(name)
+
+
+def prepare_owned(name, rank, world):
+    """What the CLI's owner ranks do for their chromosomes (read + normalise), minus the text round trip: generate the
+    raw counts, normalise with the host normaliser the CLI uses.  Returns (preps, n_chrom, owners)."""
+    from mustache_b200 import sharding, synth as gen
+    from mustache_b200.normalize import normalize_sparse
+    specs = chromosome_specs(name)
+    owners = sharding.chromosome_owners(len(specs), world, sizes=[s["n"] for _, s in specs])
+    preps = {}
+    for c, (_, spec) in enumerate(specs):
+        if owners[c] != rank:
+            continue
+        res = spec.pop("res")
+        if name == "5":
+            maps = [(x, y, v.astype(np.float64)) for x, y, v in gen.config5_maps(**spec)]
+        else:
+            x, y, v = gen.synthetic_chromosome(**spec)
+            maps = [(x, y, v.astype(np.float64))]
+        for x, y, v in maps:
+            normalize_sparse(x, y, v, res, spec["dpx"])
+        preps[c] = dict(maps=maps, n=spec["n"])
+    return preps, len(specs), owners
+
+
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port (scipy path), all host cores, bounded sample
+# reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    n, dpx, octaves, seed = args
+    n, dpx, octaves, seed, use_reference = args
     from mustache_b200 import synth as gen
-    from oracle import scalespace as osc
     c = gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=seed, blob_seed=seed + 1, nblobs=10), n)
+    if use_reference:
+        from baseline import reference_arm
+        return reference_arm.time_scale_space(c, dpx, octaves)
+    from oracle import scalespace as osc
     t0 = time.perf_counter()
     res = osc.scale_space(c, dpx, octaves, use_scipy=True)
     return time.perf_counter() - t0, int((res["p"] != 2).sum())
 
 
 def cpu_sample_geometry(cfg, target_core_seconds=12.0):
-    """Sub-tile with the same band-to-tile ratio as the workload, sized for ~target seconds per core."""
+    """Sub-tile with the same band-to-tile ratio as the workload's blocks, sized for ~target seconds per core."""
     per_bin = 1.0 / (37.4e3 if len(cfg["octaves"]) >= 4 else 88.6e3)        # SURVEY.md section 6, per core
+    if contact_bins(cfg["n"], cfg["dpx"]) * per_bin <= 1.5 * target_core_seconds:
+        return cfg["n"], cfg["dpx"]                                          # a whole block of the workload fits the budget
     ratio = cfg["dpx"] / cfg["n"]
     n = 400
     while n < cfg["n"]:
@@ -173,8 +232,12 @@ def cpu_sample_geometry(cfg, target_core_seconds=12.0):
     return n, max(8, int(n * ratio))
 
 
-def run_cpu_port(cfg, steps, warmup, cores=None):
+def run_cpu_arm(cfg, steps, warmup, cores=None):
+    """The reference's scale-space loop over Pool(cores), one tile per process and step.  Returns value, ms, cores,
+    kind, sample description."""
     import multiprocessing as mp
+    from baseline import reference_arm
+    use_ref = reference_arm.available()
     cores = cores or os.cpu_count() or 1
     n, dpx = cpu_sample_geometry(cfg)
     bins = contact_bins(n, dpx) * cores
@@ -183,14 +246,174 @@ def run_cpu_port(cfg, steps, warmup, cores=None):
     with ctx.Pool(cores) as pool:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker, [(n, dpx, cfg["octaves"], 5000 + 31 * it + k) for k in range(cores)])
+            pool.map(_cpu_worker, [(n, dpx, cfg["octaves"], 5000 + 31 * it + k, use_ref) for k in range(cores)])
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
     dt = float(np.mean(times))
-    sample = "%d tiles of %d x %d (dpx %d, %d octaves), one per process, scipy path of the oracle port" % (
-        cores, n, n, dpx, len(cfg["octaves"]))
-    return bins / dt, dt * 1e3, cores, sample
+    what = ("unmodified reference mustache() from entry to its multipletests call (baseline/_ref, mustache.py:697-778)"
+            if use_ref else "scipy path of the oracle port (baseline/_ref absent)")
+    sample = "%d tiles of %d x %d (dpx %d, %d octaves) per step, one per process over Pool(%d); %s" % (
+        cores, n, n, dpx, len(cfg["octaves"]), cores, what)
+    return bins / dt, dt * 1e3, cores, ("reference" if use_ref else "port"), sample
+
+
+# ------------------------------------------------------------------------------------------------------------
+# measurement
+# ------------------------------------------------------------------------------------------------------------
+class Harness:
+    def __init__(self, rank, local_rank, world):
+        import torch
+        self.torch, self.rank, self.local_rank, self.world = torch, rank, local_rank, world
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def measure(h, eng, cfg, name, steps, warmup, device_only=False):
+    """Device-resident and end-to-end timing of one workload on this rank's engine.  Returns a dict of raw figures."""
+    from mustache_b200 import blockrun, sharding
+    rank, world = h.rank, h.world
+    eng.set_octaves(cfg["octaves"], differential=(cfg.get("maps", 1) == 2))
+    n, dpx = cfg["n"], cfg["dpx"]
+    nmaps = cfg.get("maps", 1)
+    if cfg["kind"] == "dense":
+        tiles, keep = make_host_tiles(cfg, rank)
+        nblk = cfg["blocks"]
+
+        def upload():
+            for b, t in enumerate(tiles):
+                eng.upload_dense(b, t)
+        wc = min(dpx + 1, n - 1) - 3
+        h2d = nblk * n * wc * 8
+        stacks = 1
+    else:
+        preps, n_chrom, owners = prepare_owned(name, rank, world)
+        tasks, geom = blockrun.build_tasks(preps, n_chrom, dpx, nmaps, rank, world, eng, owners)
+        nblk = nmaps * len(tasks)
+        flat = [(np.ascontiguousarray(m[0], np.int32), np.ascontiguousarray(m[1], np.int32), np.ascontiguousarray(m[2], np.float64))
+                for t in tasks for m in t.maps]
+
+        def upload():
+            for b, m in enumerate(flat):
+                eng.upload_coo(b, *m)
+        h2d = sum(16 * len(m[2]) for m in flat)
+        stacks = 3 if nmaps == 2 else 1                  # SURVEY 8(d) counts the three filter stacks of a block pair
+    bins_rank = contact_bins(n, dpx) * (nblk // nmaps) * stacks
+    run = eng.run_differential if nmaps == 2 else eng.run
+    eng.configure(n, dpx, max(nblk, nmaps))
+    upload()
+    eng.sync()
+
+    for _ in range(warmup):
+        run()
+    h.barrier()
+    dev_ms, phases = 0.0, {"prep_ms": 0.0, "kv_ms": 0.0, "kh_ms": 0.0, "ks_ms": 0.0, "fin_ms": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+        eng.sync()
+        tm = eng.timing()
+        dev_ms += tm["total_ms"]
+        for k in phases:
+            phases[k] += tm[k]
+    h.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = eng.launches() * steps
+    step_ms = h.max_over_ranks((wall_ms if world > 1 else dev_ms) / steps)
+    bins_all = h.sum_over_ranks(bins_rank)
+    out = dict(step_ms=step_ms, bins_rank=bins_rank, bins_all=bins_all, value=bins_all / (step_ms * 1e-3), launches=launches,
+               phases={k: v / steps for k, v in phases.items()}, dev_ms=dev_ms / steps, blocks_rank=nblk // nmaps)
+    if device_only:
+        return out
+
+    # ---- end to end through the public API with host buffers ----
+    # Every step: host tiles -> device, all kernels, ONE packed records fetch, and for N > 1 the gather of the per-block
+    # result rows on rank 0.  The uploads of step k+1 are issued right after the run of step k (the engine double-buffers
+    # tiles on a second stream), which is how a caller with more than one batch uses the API.
+    dev = blockrun.collective_device(eng)
+
+    def e2e_step():
+        run()
+        upload()
+        recs = eng.records_batch(sort=False, pair=(nmaps == 2))
+        rows = np.array([[rank, b, r["n_found"], r["nz_count"]] for b, r in enumerate(recs)], dtype=np.float64).reshape(-1, 4)
+        got = sharding.gather_loops(rows, rank, world, dev) if world > 1 else rows
+        return recs, got
+
+    upload()
+    for _ in range(max(1, warmup // 2)):
+        recs, got = e2e_step()
+    h.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        recs, got = e2e_step()
+    h.barrier()
+    e2e_ms = h.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    eng.sync()
+    n_found = int(sum(r["n_found"] for r in recs))
+    total_found = h.sum_over_ranks(n_found)
+    if rank == 0:
+        assert int(got[:, 2].sum()) == int(total_found), "rank 0 did not receive every block's result row"
+    per_rec = 44 if nmaps == 2 else 36                   # rows, cols, score id (int32), v, p, sigma (+ pPair) (float64)
+    out.update(e2e_ms=e2e_ms, e2e_value=bins_all / (e2e_ms * 1e-3), h2d=int(h.sum_over_ranks(h2d)),
+               d2h=int(h.sum_over_ranks(n_found * per_rec + nblk * 16)), n_found=int(total_found))
+    return out
+
+
+def roofline(cfg, name, m, peak, peaks_found):
+    n_oct = len(cfg["octaves"])
+    bytes_per_bin = BYTES_PER_BIN_PER_OCTAVE * n_oct
+    ph = m["phases"]
+    kern = {"kv_kernel": ph["kv_ms"], "kh_kernel": ph["kh_ms"], "ks_kernel": ph["ks_ms"]}
+    dom = max(kern, key=kern.get)
+    achieved = m["bins_rank"] * bytes_per_bin / (m["dev_ms"] * 1e-3) / 1e9
+    instr_ref, instr_exec = fp64_instr_per_bin(cfg["octaves"])
+    hot_ms = ph["kv_ms"] + ph["kh_ms"]
+    share = {"kv_kernel": 12 * 8 * n_oct, "kh_kernel": 11 * 8 * n_oct, "ks_kernel": 11 * 8 * n_oct}
+    tr = (load_traffic() or {}).get(name, {})
+    per_kernel = {}
+    for kname, key in (("kv_kernel", "kv_ms"), ("kh_kernel", "kh_ms"), ("ks_kernel", "ks_ms")):
+        if ph[key] <= 0:
+            continue
+        ach = m["bins_rank"] * share[kname] / (ph[key] * 1e-3) / 1e9
+        per_kernel[kname] = {"ms": ph[key], "algorithmic_bytes_per_bin": share[kname], "achieved": ach, "frac": ach / peak,
+                             "traffic": tr.get(kname)}
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": tr.get(dom), "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks_found else "fallback",
+            "algorithmic_bytes_per_bin": bytes_per_bin, "bins_per_launch": m["bins_rank"],
+            "scope": "whole step on rank 0 (prep + axis-0 + axis-1/DoG + scoring + statistics), device time from CUDA events",
+            "dominant_kernel": dom, "dominant_kernel_share": kern[dom] / max(m["dev_ms"], 1e-9),
+            "traffic_note": ("dram__bytes_read+write of the dominant kernel per launch, ncu --set full capture of this command "
+                             "(profiles/)") if tr else "no ncu capture committed for this config",
+            "kernels": per_kernel,
+            "fp64": {"instr_per_bin_reference": instr_ref, "instr_per_bin_executed": instr_exec,
+                     "achieved_instr_per_s": instr_exec * m["bins_rank"] / max(hot_ms * 1e-3, 1e-12),
+                     "peak_instr_per_s": FP64_INSTR_PEAK,
+                     "frac": instr_exec * m["bins_rank"] / max(hot_ms * 1e-3, 1e-12) / FP64_INSTR_PEAK,
+                     "note": "axis-0 + axis-1 kernels; an FP64 instruction holds the SM sub-partition's dispatch for 2 cycles, "
+                             "every other instruction costs ~0.75 more (tools/fp64_peak.cu)"}}
 
 
 def main():
@@ -201,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="2", choices=list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 strong-scaling object of multi-GPU lines")
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
     args = ap.parse_args()
@@ -208,21 +432,24 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_oct = len(cfg["octaves"])
-    bytes_per_bin = BYTES_PER_BIN_PER_OCTAVE * n_oct
+    strong = cfg["kind"] == "chrom"
     config = {"workload": cfg["workload"], "n": cfg["n"], "dpx": cfg["dpx"], "octaves": cfg["octaves"],
-              "blocks_per_gpu": cfg["blocks"], "l2": "inputs larger than L2 (band tile + axis-0 scratch >> 126 MB)",
-              "parallelism": "blocks sharded one set per GPU, NCCL gather of the records to rank 0 only" if world > 1 else "single GPU"}
+              "l2": "inputs larger than L2 (band tiles + axis-0 scratch >> 126 MB)",
+              "parallelism": ("block pool of all chromosomes spread evenly over the ranks (owner ranks prepare, all_to_all of "
+                              "block COO), per-rank post-processing, gather of result rows to rank 0" if strong else
+                              "one tile set per GPU, gather of result rows to rank 0") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        val, ms, cores, sample = run_cpu_port(cfg, steps, warm)
+        val, ms, cores, kind, sample = run_cpu_arm(cfg, steps, warm)
+        config["workload"] = cfg["workload"] + " -- CPU arm sampled as: " + sample
         print(json.dumps({"impl": "reference", "metric": "contact_bins_per_sec", "value": val, "unit": "contact-bins/s",
                           "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": val, "unit": "contact-bins/s", "cores": cores, "kind": "port", "sample": sample},
+                          "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": config,
+                          "cpu_baseline": {"value": val, "unit": "contact-bins/s", "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": val, "unit": "contact-bins/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -230,155 +457,54 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from mustache_b200.engine import ScaleSpaceEngine
-    from mustache_b200 import gather
-
+    h = Harness(rank, local_rank, world)
     eng = ScaleSpaceEngine(local_rank)
-    eng.set_octaves(cfg["octaves"])
-    tiles, keep = make_host_tiles(cfg, rank)
-    n, dpx, B = cfg["n"], cfg["dpx"], cfg["blocks"]
-    bins_rank = contact_bins(n, dpx) * B
-    eng.configure(n, dpx, B)
-    for b, t in enumerate(tiles):
-        eng.upload_dense(b, t)
-    eng.sync()
-
-    def device_step():
-        eng.run()
-        if world > 1:                        # the path's only collective: candidate records, device to device over NCCL
-            for b in range(B):
-                gather.gather_device_to_root(eng.records_device(b), world, rank)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()              # 200 ms period: started before the warm-up so that short timed regions are covered
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    dev_ms, phases = 0.0, {"prep_ms": 0.0, "kv_ms": 0.0, "kh_ms": 0.0, "ks_ms": 0.0, "fin_ms": 0.0}
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        device_step()
-        eng.sync()
-        tm = eng.timing()
-        dev_ms += tm["total_ms"]
-        for k in phases:
-            phases[k] += tm[k]
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    m = measure(h, eng, cfg, args.config, args.steps, args.warmup, device_only=args.device_only)
     clocks = sampler.stop() if rank == 0 else None
-    launches = eng.launches() * args.steps
-    step_ms = (wall_ms if world > 1 else dev_ms) / args.steps
-    if world > 1:
-        tt = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        step_ms = float(tt.item())
-    value = bins_rank * world / (step_ms * 1e-3)
-
     if args.device_only:
         if rank == 0:
-            print(json.dumps({"device_only": True, "ms_per_step": step_ms, "value": value,
-                              "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()}}))
+            print(json.dumps({"device_only": True, "ms_per_step": m["step_ms"], "value": m["value"],
+                              "phases_ms_per_step": m["phases"]}))
         return
-
-    # ---- end to end through the public API with host buffers ----
-    # Every step: pinned host tiles -> device (band only), all kernels, records device -> host.  The uploads of step k+1
-    # are issued right after mb200_run of step k (the engine double-buffers tiles on a second stream), which is how a
-    # caller with more than one batch uses the API; K steps = K uploads + K runs + K record fetches inside the region.
-    def e2e_upload():
-        for b, t in enumerate(tiles):
-            eng.upload_dense(b, t)
-
-    def e2e_step():
-        eng.run()
-        e2e_upload()
-        if world > 1:
-            for b in range(B):
-                gather.gather_device_to_root(eng.records_device(b), world, rank)
-        recs = [eng.records(b, sort=False, pinned=(B == 1)) for b in range(B)]
-        return recs
-
-    e2e_upload()
-    for _ in range(max(1, args.warmup // 2)):
-        recs = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        recs = e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    eng.sync()
-    if world > 1:
-        tt = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
-    wc = min(dpx + 1, n - 1) - 3
-    h2d = B * n * wc * 8
-    d2h = int(sum(r["n_found"] for r in recs)) * 36 + B * 20      # rows, cols, score id (int32), v, p, sigma (float64) + counters
-    n_found = int(sum(r["n_found"] for r in recs))
-
+    c4 = None
+    if not strong and not args.no_config4:
+        c4m = measure(h, eng, CONFIGS["4"], "4", max(3, args.steps), 3)
+        c4 = {"workload": CONFIGS["4"]["workload"], "scaling": "strong", "n_gpus": world, "value": c4m["value"],
+              "unit": "contact-bins/s", "ms_per_step": c4m["step_ms"], "blocks_on_rank0": c4m["blocks_rank"],
+              "e2e": {"value": c4m["e2e_value"], "ms_per_step": c4m["e2e_ms"], "h2d_bytes_per_step": c4m["h2d"],
+                      "d2h_bytes_per_step": c4m["d2h"]}, "records_per_step": c4m["n_found"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    hot_ms = (phases["kv_ms"] + phases["kh_ms"]) / args.steps
-    kern = {"kv_kernel": phases["kv_ms"], "kh_kernel": phases["kh_ms"], "ks_kernel": phases["ks_ms"]}
-    dom = max(kern, key=kern.get)
-    achieved = bins_rank * bytes_per_bin / (dev_ms / args.steps * 1e-3) / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    instr_ref, instr_exec = fp64_instr_per_bin(cfg["octaves"])
-    instr = instr_exec * bins_rank
-    steps_ms = {k: v / args.steps for k, v in phases.items()}
-    # SURVEY 8(d) accounting split by the kernel that moves the bytes: 12 input reads (axis-0 pass), 11 DoG writes
-    # (axis-1 pass), 11 DoG reads (scoring) per octave
-    share = {"kv_kernel": 12 * 8 * n_oct, "kh_kernel": 11 * 8 * n_oct, "ks_kernel": 11 * 8 * n_oct}
-    traffic = load_traffic()
-    tr = (traffic or {}).get(args.config, {})
-    per_kernel = {}
-    for kname, ph in (("kv_kernel", "kv_ms"), ("kh_kernel", "kh_ms"), ("ks_kernel", "ks_ms")):
-        ach = bins_rank * share[kname] / (steps_ms[ph] * 1e-3) / 1e9
-        per_kernel[kname] = {"ms": steps_ms[ph], "algorithmic_bytes_per_bin": share[kname], "achieved": ach,
-                             "frac": ach / peak, "traffic": tr.get(kname)}
-    out = {"metric": "contact_bins_per_sec", "value": value, "unit": "contact-bins/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": config,
+    config["blocks_on_rank0"] = m["blocks_rank"]
+    out = {"metric": "contact_bins_per_sec", "value": m["value"], "unit": "contact-bins/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": m["step_ms"], "higher_is_better": True,
+           "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks,
-           "e2e": {"value": bins_rank * world / (e2e_ms * 1e-3), "unit": "contact-bins/s", "ms_per_step": e2e_ms,
-                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-           "gpu_launches": launches,
-           "records_per_step": n_found,
-           "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
-           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": tr.get(dom), "peak_source": "measured" if peaks else "fallback",
-                        "algorithmic_bytes_per_bin": bytes_per_bin, "bins_per_launch": bins_rank,
-                        "scope": "whole step (prep + kv_kernel + kh_kernel + ks_kernel + statistics), device time from CUDA events",
-                        "dominant_kernel": dom, "dominant_kernel_share": kern[dom] / max(dev_ms, 1e-9),
-                        "traffic_note": "dram__bytes_read+write of the dominant kernel per launch, ncu --set full capture "
-                                        "of this command (profiles/)" if tr else "no ncu capture committed for this config",
-                        "kernels": per_kernel,
-                        "fp64": {"instr_per_bin_reference": instr_ref, "instr_per_bin_executed": instr_exec,
-                                 "achieved_instr_per_s": instr / (hot_ms * 1e-3), "peak_instr_per_s": FP64_INSTR_PEAK,
-                                 "frac": instr / (hot_ms * 1e-3) / FP64_INSTR_PEAK,
-                                 "note": "kv_kernel + kh_kernel; an FP64 instruction holds the SM sub-partition's dispatch "
-                                         "for 2 cycles, every other instruction costs ~0.75 more (tools/fp64_peak.cu)"}}}
+           "e2e": {"value": m["e2e_value"], "unit": "contact-bins/s", "ms_per_step": m["e2e_ms"],
+                   "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+           "gpu_launches": m["launches"], "records_per_step": m["n_found"], "phases_ms_per_step": m["phases"],
+           "roofline": roofline(cfg, args.config, m, peak, bool(peaks))}
+    if c4 is not None:
+        out["config4"] = c4
     if not args.no_cpu_baseline and world == 1:
-        val, ms, cores, sample = run_cpu_port(cfg, args.cpu_steps, 0)
-        out["cpu_baseline"] = {"value": val, "unit": "contact-bins/s", "cores": cores, "kind": "port", "sample": sample,
+        val, ms, cores, kind, sample = run_cpu_arm(cfg, args.cpu_steps, 0)
+        out["cpu_baseline"] = {"value": val, "unit": "contact-bins/s", "cores": cores, "kind": kind, "sample": sample,
                                "ms_per_sample": ms}
     print(json.dumps(out))
     if world > 1:

@@ -88,12 +88,18 @@ def diagonal_means(mask_rows, mask_cols, mask_vals, dpx, wanted, intra=True):
     """
     d = mask_cols.astype(np.int64) - mask_rows.astype(np.int64)
     out = {}
-    for k in np.unique(wanted):
+    uniq = np.unique(wanted)
+    by_diag = None
+    if len(uniq) > 16:                          # many diagonals: one stable sort instead of a pass over the mask per diagonal
+        order = np.argsort(d, kind="stable")
+        ds = d[order]
+        by_diag = (order, np.searchsorted(ds, uniq, side="left"), np.searchsorted(ds, uniq, side="right"))
+    for pos, k in enumerate(uniq):
         k = int(k)
         if k <= 4 or (intra and k >= dpx + 1):
             out[k] = 2.0
             continue
-        vals = mask_vals[d == k]
+        vals = mask_vals[d == k] if by_diag is None else mask_vals[by_diag[0][by_diag[1][pos]:by_diag[2][pos]]]
         vals = vals[vals != 0]
         with np.errstate(all="ignore"):
             out[k] = float(np.mean(vals)) if vals.size else float("nan")

@@ -105,9 +105,11 @@ def poisson_chromosome(n, dpx, lam_scale=18.0, seed=3000, nloops=None, loop_seed
 # ------------------------------------------------------------------------------------------------------------------
 # BASELINE configs 3 / 4 / 5: whole synthetic chromosomes as raw count maps
 # ------------------------------------------------------------------------------------------------------------------
-def _plant_loops(band, n, dpx, nloops, rng, boost, sign=+1):
-    """Adds (or with sign=-1 re-draws and removes) Poisson(boost) counts in a 3x3 patch around `nloops` random centres."""
-    d0 = rng.integers(12, dpx - 4, size=nloops)
+def _plant_loops(band, n, dpx, nloops, rng, boost, sign=+1, dmax=None):
+    """Adds Poisson(boost) counts in a 3x3 patch around `nloops` random centres at distances [12, dpx - 4), or
+    [8, dmax) when dmax is given: the reference's sparsity filter (mustache.py:800-811) only keeps calls whose
+    (4s+1)^2 neighbourhood is >= 60 % non-zero, which at these depths means close to the diagonal."""
+    d0 = rng.integers(12, dpx - 4, size=nloops) if dmax is None else rng.integers(8, min(dmax, dpx - 4), size=nloops)
     i0 = (rng.random(nloops) * (n - d0 - 4)).astype(np.int64) + 2
     inc = rng.poisson(boost, size=(nloops, 3, 3))
     for a, di in enumerate((-1, 0, 1)):
@@ -145,11 +147,12 @@ def band_counts_to_coo(band):
     return i.astype(np.int64), (i + k).astype(np.int64), band[i, k].astype(np.int64)
 
 
-def synthetic_chromosome(n, dpx, lam_scale, seed, nloops, loop_seed=None, loop_boost=8.0):
+def synthetic_chromosome(n, dpx, lam_scale, seed, nloops, loop_seed=None, loop_boost=8.0, loop_dmax=None):
     """One synthetic chromosome of configs 3 / 4: Poisson background + `nloops` planted 3x3 loops; COO of raw counts."""
     band = poisson_band(n, dpx, lam_scale, seed)
     if nloops:
-        _plant_loops(band, n, dpx, nloops, np.random.default_rng(seed + 1 if loop_seed is None else loop_seed), loop_boost)
+        _plant_loops(band, n, dpx, nloops, np.random.default_rng(seed + 1 if loop_seed is None else loop_seed), loop_boost,
+                     dmax=loop_dmax)
     return band_counts_to_coo(_clip_band(band, n))
 
 
@@ -158,26 +161,26 @@ CONFIG3 = dict(n=50000, res=1000, dpx=2000, lam_scale=4.0, seed=2001, nloops=200
 # same geometry as config 3 (1 kb, N 4000, dpx 2000) but dense enough near the diagonal for loops to survive the
 # reference's sparsity filter (mustache.py:800-811 needs >= 60 % non-zero pixels in a (4s+1)^2 window): config 3 as
 # SURVEY defines it yields 0 loops in the reference
-CONFIG3D = dict(n=12000, res=1000, dpx=2000, lam_scale=60.0, seed=2101, nloops=1500, loop_seed=2102)
+CONFIG3D = dict(n=12000, res=1000, dpx=2000, lam_scale=60.0, seed=2101, nloops=300, loop_seed=2102, loop_dmax=60)
 CONFIG4 = {"s%d" % (k + 1): dict(n=10000 * (k + 1), res=5000, dpx=400, lam_scale=18.0, seed=3000 + k, nloops=40 * (k + 1),
-                                 loop_seed=3100 + k) for k in range(8)}
+                                 loop_seed=3100 + k, loop_dmax=24, loop_boost=25.0) for k in range(8)}
 CONFIG5 = dict(n=20000, res=5000, dpx=400, lam_scale=18.0, seed=4001, loop_seed=4002, thin_seed=4003, nloops=300, ndelete=100,
-               nadd=100, keep_prob=0.6)
+               nadd=100, keep_prob=0.6, loop_dmax=24, loop_boost=25.0)
 
 
 def config5_maps(n=20000, dpx=400, lam_scale=18.0, seed=4001, loop_seed=4002, thin_seed=4003, nloops=300, ndelete=100,
-                 nadd=100, keep_prob=0.6, loop_boost=8.0, **_):
+                 nadd=100, keep_prob=0.6, loop_boost=8.0, loop_dmax=None, **_):
     """Config 5: map A = background + `nloops` loops; map B = binomial(keep_prob) thinning of map A without its last
     `ndelete` loops, plus `nadd` loops of its own.  Returns two COO triples of raw counts."""
     base = poisson_band(n, dpx, lam_scale, seed)
     lrng = np.random.default_rng(loop_seed)
     common = base.copy()
-    _plant_loops(common, n, dpx, nloops - ndelete, lrng, loop_boost)
+    _plant_loops(common, n, dpx, nloops - ndelete, lrng, loop_boost, dmax=loop_dmax)
     a = common.copy()
-    _plant_loops(a, n, dpx, ndelete, lrng, loop_boost)
+    _plant_loops(a, n, dpx, ndelete, lrng, loop_boost, dmax=loop_dmax)
     trng = np.random.default_rng(thin_seed)
     b = trng.binomial(common, keep_prob).astype(np.int32)
-    _plant_loops(b, n, dpx, nadd, trng, loop_boost)
+    _plant_loops(b, n, dpx, nadd, trng, loop_boost, dmax=loop_dmax)
     return band_counts_to_coo(_clip_band(a, n)), band_counts_to_coo(_clip_band(b, n))
 
 

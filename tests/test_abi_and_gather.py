@@ -1,5 +1,6 @@
 """CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/mustache_b200.h declares
-(no compute calls without a GPU), error behaviour without a device, and the world_size-2 record gather over gloo."""
+(no compute calls without a GPU) and error behaviour without a device.  The world_size-2 gloo tests of the multi-GPU host
+path live in tests/test_sharded_blocks.py."""
 import ctypes as C
 import os
 import re
@@ -58,67 +59,6 @@ def test_cli_parsers_match_reference_defaults():
     assert d.pt2 == 0.05 and d.pt == 0.2
     row = mustache.format_row("21", "21", [3161, 3224, 0.0919438088559645, 2.111212657236631], 5000)
     assert row == "21\t15805000\t15810000\t21\t16120000\t16125000\t0.0919438088559645\t2.111212657236631\n"
-
-
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
-
-
-def _gather_worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    sys.path.insert(0, ROOT)
-    import torch
-    import torch.distributed as dist
-    from mustache_b200 import gather
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    rng = np.random.default_rng(100 + rank)
-    recs, ids = [], []
-    for b in range(rank, 5, world):                 # round-robin block shard, ragged sizes, one empty block
-        m = 0 if b == 3 else 3 + 2 * b
-        recs.append(dict(rows=rng.integers(0, 2000, m).astype(np.int32), cols=rng.integers(0, 2000, m).astype(np.int32),
-                         v=rng.random(m), score_id=rng.integers(3, 23, m).astype(np.int32), p=rng.random(m),
-                         pair=rng.random(m), nz_count=1000 + b))
-        ids.append(b)
-    got = gather.all_gather_records(recs, rank, world, torch.device("cpu"), block_ids=ids, with_pair=True)
-    # the device-resident variants on CPU tensors: same collectives, gloo instead of NCCL
-    r0 = recs[0]
-    dev = dict(rows=torch.from_numpy(r0["rows"]), cols=torch.from_numpy(r0["cols"]), v=torch.from_numpy(r0["v"]),
-               scored_index=torch.from_numpy(r0["score_id"]), p=torch.from_numpy(r0["p"]), n_found=len(r0["rows"]),
-               nz_count=r0["nz_count"])
-    s_all, f_all = gather.all_gather_device(dev, world)
-    s_root, f_root = gather.gather_device_to_root(dev, world, rank)
-    ok = s_all == s_root and ((rank != 0 and f_root is None) or
-                              all(torch.equal(f_all[k][w, :s_all[w]], f_root[k][w, :s_all[w]]) for k in f_all for w in range(world)))
-    q.put((rank, got, gather.pack_records(recs, 0, ids, with_pair=True), ok))
-    dist.destroy_process_group()
-
-
-def test_gather_world_size_2_gloo():
-    import torch.multiprocessing as mp
-    from mustache_b200 import gather
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    full = np.concatenate([res[0][2], res[1][2]], axis=0)
-    for rank, got, _, root_gather_ok in res:
-        assert np.array_equal(got, full)            # every rank sees every record, rank order, bit-exact
-        assert root_gather_ok                       # gather-to-root of a block == the all_gather of the same block
-    by = gather.split_by_block(full)
-    assert sorted(k[1] for k in by) == [0, 1, 2, 4]  # block 3 had no records
-    r4 = by[(0, 4)]
-    assert r4["n_found"] == 11 and r4["nz_count"] == 1004 and "pair" in r4
-    assert (np.diff(r4["rows"].astype(np.int64) * 4096 + r4["cols"]) >= 0).all()    # row-major within a block
 
 
 def test_kv_plan_is_a_partition_with_the_optimal_cost():

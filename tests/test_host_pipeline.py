@@ -153,3 +153,48 @@ def test_normaliser_equals_literal_restatement(chr21):
         wb = onorm.normalize_sparse(x, y, b, res, dpx)
         assert wa == wb and np.array_equal(a, b)
         assert not np.array_equal(a, v)
+
+
+def test_integer_counts_keep_reference_truncation(tmp_path):
+    """read_pd without a bias file on integer text yields int64 values and normalize_sparse truncates its z-scores into
+    them (mustache.py:668, 683): the reader keeps the dtype, so the CLI pipeline reproduces what the literal restatement
+    of the reference's normaliser (oracle/normalize.py) does on the same integer array."""
+    from mustache_b200 import normalize, readers
+    from oracle import normalize as onorm
+    p = str(tmp_path / "ints.txt")
+    rng = np.random.default_rng(3)
+    with open(p, "w") as f:
+        for i in range(300):
+            for d in range(0, 30):
+                if i + d < 300:
+                    f.write("chr1\t%d\tchr1\t%d\t%d\n" % (i * 5000, (i + d) * 5000, rng.integers(1, 40)))
+    x, y, v = readers.read_text(p, 2000000, False, "chr1", 5000)
+    assert v.dtype.kind == "i"
+    ref = v.copy()
+    onorm.normalize_sparse(np.asarray(x), np.asarray(y), ref, 5000, 400)
+    normalize.normalize(x, y, v, 5000, 400, eng=None)
+    assert v.dtype.kind == "i" and np.array_equal(v, ref) and set(np.unique(v)) <= {-2, -1, 0, 1, 2} and (v != 0).any()
+
+
+def test_block_slicer_equals_block_coo():
+    """tiler.BlockSlicer (one sort, contiguous row ranges) selects exactly what the reference's boolean masks select
+    (mustache.py:919-922), in the same order, also for unsorted input with duplicate coordinates."""
+    from mustache_b200 import tiler
+    rng = np.random.default_rng(11)
+    n = 700
+    x = rng.integers(0, n, 5000)
+    y = np.minimum(x + rng.integers(0, 60, 5000), n - 1)
+    v = rng.random(5000)
+    x[100:110], y[100:110] = x[90:100], y[90:100]                 # duplicates: last write wins
+    sl = tiler.BlockSlicer(x, y, v)
+    chunk, starts, ends = 260, [0, 130, 440], [260, 390, 700]
+    for s0, e0 in zip(starts, ends):
+        a = tiler.block_mask_pixels(*tiler.block_coo(x, y, v, s0, e0), chunk)
+        b = tiler.block_mask_pixels(*sl.block(s0, e0), chunk)
+        for p, q in zip(a, b):
+            assert np.array_equal(p, q)
+    xs = np.sort(x)
+    sl2 = tiler.BlockSlicer(xs, y, v)                             # already row sorted: no copy, same answer as the masks
+    a = tiler.block_coo(xs, y, v, 130, 390)
+    b = sl2.block(130, 390)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))

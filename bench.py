@@ -312,13 +312,20 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
         preps, n_chrom, owners = prepare_owned(name, rank, world)
         tasks, geom = blockrun.build_tasks(preps, n_chrom, dpx, nmaps, rank, world, eng, owners)
         nblk = nmaps * len(tasks)
-        flat = [(np.ascontiguousarray(m[0], np.int32), np.ascontiguousarray(m[1], np.int32), np.ascontiguousarray(m[2], np.float64))
-                for t in tasks for m in t.maps]
+        # block COO of the whole batch, concatenated, in page-locked host memory (what a caller that wants full-speed
+        # uploads hands to mb200_upload_coo_batch)
+        from mustache_b200.engine import PinnedBuffer
+        offsets, rows, cols, vals = blockrun.concat_coo([m for t in tasks for m in t.maps])
+        keep = [PinnedBuffer((max(len(vals), 1),), np.int32), PinnedBuffer((max(len(vals), 1),), np.int32),
+                PinnedBuffer((max(len(vals), 1),), np.float64)]
+        flat = [buf.array[:len(vals)] for buf in keep]
+        for dst, src in zip(flat, (rows, cols, vals)):
+            dst[:] = src
 
         def upload():
-            for b, m in enumerate(flat):
-                eng.upload_coo(b, *m)
-        h2d = sum(16 * len(m[2]) for m in flat)
+            if nblk:
+                eng.upload_coo_batch(0, offsets, *flat)
+        h2d = 16 * len(vals)
         stacks = 3 if nmaps == 2 else 1                  # SURVEY 8(d) counts the three filter stacks of a block pair
     bins_rank = contact_bins(n, dpx) * (nblk // nmaps) * stacks
     run = eng.run_differential if nmaps == 2 else eng.run

@@ -66,6 +66,12 @@ MB200_API int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nb
  *  _band_host  : band layout [n][wsrc], element (i, k) = tile[i][i+4+k]  (host pointer) */
 MB200_API int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const int32_t* cols, const double* vals,
                           int64_t nnz);
+/* A run of blocks in one call: entries [offsets[b], offsets[b+1]) of the concatenated arrays are the block-local COO of
+ * block first_block + b (offsets: nblk + 1 entries, offsets[0] = 0): one host -> device copy per array and one scatter
+ * kernel for the whole batch instead of one of each per block.  Pageable arrays are staged before the call returns;
+ * page-locked ones (mb200_host_alloc) are read by DMA and must stay valid until mb200_run / mb200_sync. */
+MB200_API int mb200_upload_coo_batch(mb200_engine* e, int first_block, int nblk, const int64_t* offsets, const int32_t* rows,
+                                     const int32_t* cols, const double* vals);
 MB200_API int mb200_upload_coo_dev(mb200_engine* e, int block, const int32_t* rows_dev, const int32_t* cols_dev,
                                    const double* vals_dev, int64_t nnz);   /* same, device pointers, complete before the call */
 MB200_API int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int64_t ld);

@@ -67,6 +67,18 @@ def build_tasks(preps, n_chrom, dpx, nmaps, rank, world, eng, owners=None):
     return tasks, geom
 
 
+def concat_coo(maps):
+    """[(rows, cols, vals)] -> (offsets, rows int32, cols int32, vals float64) for ScaleSpaceEngine.upload_coo_batch."""
+    offsets = np.zeros(len(maps) + 1, np.int64)
+    np.cumsum([len(m[2]) for m in maps], out=offsets[1:])
+    tot = int(offsets[-1])
+    rows, cols, vals = np.empty(tot, np.int32), np.empty(tot, np.int32), np.empty(tot, np.float64)
+    for k, m in enumerate(maps):
+        a, z = offsets[k], offsets[k + 1]
+        rows[a:z], cols[a:z], vals[a:z] = m[0], m[1], m[2]
+    return offsets, rows, cols, vals
+
+
 def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timings=None, totals=None):
     """Generator over (task, [records per map]) for this rank's tasks.  Engine batches are bounded by the tile memory;
     a batch whose records overflow the engine's capacity is re-run with a larger one (MB200_ERR_CAPACITY contract)."""
@@ -80,11 +92,10 @@ def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timin
         fraction = -1.0
         while True:
             eng.configure(chunk, dpx, nmaps * len(batch), record_fraction=fraction)
-            for k, t in enumerate(batch):
-                if verbose:
+            if verbose:
+                for t in batch:
                     print("Starting block ", t.block + 1, "/", (totals or {}).get(t.chrom, "?"), "...", sep="")
-                for w, m in enumerate(t.maps):
-                    eng.upload_coo(nmaps * k + w, *m)
+            eng.upload_coo_batch(0, *concat_coo([m for t in batch for m in t.maps]))
             if differential:
                 eng.run_differential()
             else:

@@ -45,7 +45,8 @@ struct mb200_engine {
     int ncta_h = 0;
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
-        nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines;
+        nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets;
+    std::vector<long long> h_offsets;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
     bool counts_valid = false;
@@ -367,7 +368,7 @@ void mb200_destroy(mb200_engine* e) {
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
                      &e->d_score_id, &e->d_score_sigma, &e->rec_sid, &e->rec_sigma, &e->d_tmaps, &e->d_dtmaps, &e->nz_xs, &e->nz_ds, &e->nz_perm,
                      &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines,
-                     &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets};
+                     &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -623,6 +624,37 @@ int mb200_upload_coo_host(mb200_engine* e, int block, const int32_t* rows, const
     // The staging buffers are reused by the next upload; uploads are ordered on up_stream, so the scatter above has read
     // them before the next copies land.  The host arrays are pageable (numpy): cudaMemcpyAsync returns once they have been
     // staged, so they may be released when this call returns; no stream synchronisation per block.
+    return MB200_OK;
+}
+
+int mb200_upload_coo_batch(mb200_engine* e, int first_block, int nblk, const int64_t* offsets, const int32_t* rows,
+                           const int32_t* cols, const double* vals) {
+    int st = check_block(e, first_block);
+    if (st) return st;
+    if (nblk < 1 || first_block + nblk > e->nblocks || !offsets) return fail(e, MB200_ERR_ARG, "bad block range");
+    const int64_t nnz = offsets[nblk];
+    if (offsets[0] != 0 || nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(e, MB200_ERR_ARG, "bad COO arguments");
+    for (int b = 0; b < nblk; ++b)
+        if (offsets[b + 1] < offsets[b]) return fail(e, MB200_ERR_ARG, "offsets must not decrease");
+    if ((st = use_device(e))) return st;
+    if ((st = ensure(e, e->st_rows, std::max<int64_t>(nnz, 1) * sizeof(int)))) return st;
+    if ((st = ensure(e, e->st_cols, std::max<int64_t>(nnz, 1) * sizeof(int)))) return st;
+    if ((st = ensure(e, e->st_vals, std::max<int64_t>(nnz, 1) * sizeof(double)))) return st;
+    if ((st = ensure(e, e->st_offsets, (size_t)(e->nblocks + 1) * sizeof(long long)))) return st;
+    if ((st = begin_upload(e))) return st;
+    double* raw0 = raw_slot(e, e->slot_up) + (size_t)first_block * e->n * e->wc;
+    CU(e, cudaMemsetAsync(raw0, 0, (size_t)nblk * e->n * e->wc * sizeof(double), e->up_stream));
+    if (nnz == 0) return MB200_OK;
+    e->h_offsets.assign(offsets, offsets + nblk + 1);                 // engine-owned copy: the caller's may go away
+    CU(e, cudaMemcpyAsync(e->st_offsets.p, e->h_offsets.data(), (size_t)(nblk + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->st_rows.p, rows, nnz * sizeof(int), cudaMemcpyHostToDevice, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->st_cols.p, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->st_vals.p, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, e->up_stream));
+    const int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 8);
+    scatter_coo_batch_kernel<<<grid, 256, 0, e->up_stream>>>((const int*)e->st_rows.p, (const int*)e->st_cols.p,
+                                                             (const double*)e->st_vals.p, (const long long*)e->st_offsets.p, nblk,
+                                                             raw0, e->n, e->wc, e->dhi);
+    CU(e, cudaGetLastError());
     return MB200_OK;
 }
 

@@ -149,7 +149,9 @@ constexpr int KS_K = 8;
 constexpr int KS_THREADS = (KS_TC / KS_K) * 32;   // 256
 constexpr int KS_SR = KS_TR - 2;   // scored rows per CTA
 constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
-constexpr int KS_PITCH = KS_TC + 2;   // 66: box width of the staged DoG tile, == 2 (mod 4)
+constexpr int KS_PITCH = KS_TC + 6;   // 70: box width of the staged DoG tile (tile + even start column + row stagger); with
+                                      // 70 = 6 (mod 16) and the one-column stagger of rows 8-15 / 24-31 the 16 lanes (= rows) of a
+                                      // half warp read 16 different 8-byte bank pairs
 constexpr int KS_DEPTH = 6;           // ring stages per CTA: level being scored, the two before it, three in flight
 
 // width of the staged box of a step with radius R: the filter support of the tile plus one element (the box must start
@@ -162,6 +164,15 @@ __host__ __device__ inline int kh_box_width(int R) {
 __host__ __device__ inline int kh_vbuf_pitch(int rmax) { return kh_box_width(rmax); }
 // staging ring of kh_kernel: half an SM's shared memory (two CTAs per SM), at least two of the widest boxes
 constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the slowest warp (6: no measurable difference)
+#ifndef MB_KH_PREFETCH
+#define MB_KH_PREFETCH 0
+#endif
+constexpr int KH_PREFETCH = MB_KH_PREFETCH;   // boxes beyond the ring that are prefetched into L2 (0: off; measured: 4 and 8
+                                              // are 2-3 % slower on both the 4-octave tile and the 2000^2 blocks, profiles/README.md)
+#ifndef MB_KS_PREFETCH
+#define MB_KS_PREFETCH 0
+#endif
+constexpr int KS_PREFETCH = MB_KS_PREFETCH;   // DoG levels beyond the ring that are prefetched into L2 (0: off)
 constexpr int KH_XP = KH_K + 1;        // pitch of the per-warp 32 x 8 transpose buffer (odd: lanes index rows)
 __host__ __device__ inline int kh_ring_doubles(int rmax) {
     const int widest = KH_TR * kh_vbuf_pitch(rmax);
@@ -505,6 +516,12 @@ __device__ __forceinline__ void tma_load_box3d(void* dst, const CUtensorMap* map
         : "memory");
 }
 
+// TMA prefetch of a box into L2 only (no shared memory, no barrier): lets a kernel look further ahead than its
+// shared-memory ring holds boxes, so that the real copy later is an L2 hit
+__device__ __forceinline__ void tma_prefetch_box3d(const CUtensorMap* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // MODE: KH_MAIN  DoG of every step -> L (scored by ks_kernel)
 //       KH_DIFF  difference stack of diff_mustache: only the DoGs of MB_FLAG_DIFFREF steps are kept, in dout
 //       KH_DEBUG KH_MAIN plus the dense dumps of mb200_debug_level
@@ -551,41 +568,47 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 
     // Everything the DoG store needs that does not depend on the step.  The owner layout (lane = row) would store 32
     // separate 8-byte pieces per instruction, so the 32 x 8 DoG chunk of the warp takes a trip through the warp's
-    // transpose buffer: store instruction q writes tile rows 4q..4q+3 (lane>>3 selects the row), 8 columns each.
+    // transpose buffer: store instruction q writes tile rows q, q+8, q+16, q+24 (lane>>3 selects the row), 8 columns each.
+    // With the buffer pitch of 9 doubles, rows 8 apart sit 72 = 8 (mod 16) doubles apart: the 16 lanes of a half warp read
+    // 16 different 8-byte bank pairs (rows q..q+3 per instruction, as in round 1, made every read a 2-way conflict).
     unsigned zmask = 0;                                 // owner side: pixels that hold a DoG (others hold the cval 0)
 #pragma unroll
     for (int k = 0; k < KH_K; ++k)
         if (row_in && jc0 + k < g.n) zmask |= 1u << k;
     const int kk = lane & 7;
+    const int r0 = lane >> 3;                                   // this lane writes tile rows q + 8*r0
     const int pitch = (MODE == KH_DIFF) ? g.wc : g.wl;          // row length of the destination band
     const int dlo = (MODE == KH_DIFF) ? 4 : 2;                  // first diagonal it stores
     const int dhi_st = (MODE == KH_DIFF) ? g.dhi : g.dhi + 2;   // last one
+    const int jst = js + warp * KH_K + kk + (r0 & 1);           // image column it writes (rows 8-15, 24-31 are staggered)
     unsigned qmask = 0;                                 // writer side: valid (row, column) of store instruction q
-    int qoff0 = 0;                                      // element offset of q = 0; q adds 4*(pitch-1) (+1 for staggered rows)
-    {
-        const int r0 = lane >> 3;
-        const int jw = js + warp * KH_K + kk;
 #pragma unroll
-        for (int q = 0; q < KH_TR / 4; ++q) {
-            const int r = 4 * q + r0;
-            const int ii = i0 + r;
-            const int jj = jw + ((q >> 1) & 1);                 // rows 8-15, 24-31 are staggered
-            const int d = jj - ii;
-            bool ok = ii < g.n && d >= dlo && d <= dhi_st;
-            if (MODE == KH_DIFF) ok = ok && jj < g.n;
-            if (ok) qmask |= 1u << q;
-        }
-        qoff0 = (i0 + r0) * (pitch - 1) + jw - dlo;             // row*pitch + (d - dlo) = row*(pitch-1) + col - dlo
+    for (int q = 0; q < KH_TR / 4; ++q) {
+        const int ii = i0 + q + 8 * r0;
+        const int d = jst - ii;
+        bool ok = ii < g.n && d >= dlo && d <= dhi_st;
+        if (MODE == KH_DIFF) ok = ok && jst < g.n;
+        if (ok) qmask |= 1u << q;
     }
-    const int qstride = 4 * (pitch - 1);
+    // element offset of q = 0: row*pitch + (d - dlo) = row*(pitch-1) + col - dlo; q adds pitch - 1
+    const long long qoff0 = (long long)(i0 + 8 * r0) * (pitch - 1) + jst - dlo;
+    const int qstride = pitch - 1;
     // warp-uniform: no pixel of the chunk needs a mask (true for all but the tiles on the band / image edges)
     const bool interior = __all_sync(0xffffffffu, zmask == (1u << KH_K) - 1u && qmask == (1u << (KH_TR / 4)) - 1u);
 
     // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
     // into its slot of the ring, after every warp released the boxes it overlaps.
     const MbStage* stg = prog.stage;
-    int next_issue = 0;
+    int next_issue = 0, next_prefetch = 0;
     auto issue_ready = [&](int p_now) {
+        if (KH_PREFETCH > 0) {                                  // boxes the ring cannot hold yet: into L2
+            while (next_prefetch < n_steps && next_prefetch <= p_now + KH_LOOKAHEAD + KH_PREFETCH) {
+                if (next_prefetch > p_now + KH_LOOKAHEAD && elect_one())
+                    tma_prefetch_box3d(&tm->v[next_prefetch], (js - prog.st[next_prefetch].radius - g.vlo) & ~1, i0,
+                                       next_prefetch * g.nblk + b);
+                ++next_prefetch;
+            }
+        }
         while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
             const int dep = stg[next_issue].dep;
             if (dep >= p_now) break;                            // the overlapped box is still ahead of this warp
@@ -660,14 +683,14 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)b * g.ndiff + prog.st[sl].score_idx) * g.n * g.wc
                                             : g.L + ((size_t)sl * g.nblk + b) * g.plane_l;
             dst += qoff0;
-            const double* xrd = xbuf + (lane >> 3) * KH_XP + kk;
+            const double* xrd = xbuf + (8 * r0) * KH_XP + kk;
             if (MODE != KH_DEBUG && interior) {
                 // every pixel of the warp's chunk is inside the image and on a stored diagonal: no masks
 #pragma unroll
                 for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gprev[k], gnew[k]);
                 __syncwarp();
 #pragma unroll
-                for (int q = 0; q < KH_TR / 4; ++q) dst[(long long)q * qstride + ((q >> 1) & 1)] = xrd[4 * q * KH_XP];
+                for (int q = 0; q < KH_TR / 4; ++q) dst[(long long)q * qstride] = xrd[q * KH_XP];
             } else {
                 // columns past the image hold the maximum filter's cval 0
 #pragma unroll
@@ -676,12 +699,12 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
                 for (int q = 0; q < KH_TR / 4; ++q) {
                     if (qmask & (1u << q)) {
-                        const double l = xrd[4 * q * KH_XP];
-                        dst[(q >> 1) & 1] = l;
+                        const double l = xrd[q * KH_XP];
+                        *dst = l;
                         if (MODE == KH_DEBUG) {
                             if (g.dbgL != nullptr && sl == g.dbg_step && b == 0) {
-                                const int ii = i0 + 4 * q + (lane >> 3), jj = js + warp * KH_K + kk + ((q >> 1) & 1);
-                                if (jj < g.n) g.dbgL[(size_t)ii * g.n + jj] = l;
+                                const int ii = i0 + q + 8 * r0;
+                                if (jst < g.n) g.dbgL[(size_t)ii * g.n + jst] = l;
                             }
                         }
                     }
@@ -748,7 +771,12 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     }
     const double* rawb = g.raw + (size_t)b * g.n * g.wc;
     const int i = i0 + lane;                            // this thread's image row
-    const int c0 = warp * KS_K;                         // first tile column of this thread
+    // Rows 8-15 and 24-31 of every tile are shifted one column to the right (as in kh_kernel): with the even row pitch of
+    // the dense TMA box, lanes (= rows) r and r+8 would otherwise hit the same 8-byte bank pair.  All tiles share the
+    // stagger, so they still partition the band (the column a staggered row gives up on the left is never in the mask:
+    // it sits on a diagonal < 4 for every row but the first of the tile).
+    const int stag = (lane >> 3) & 1;
+    const int c0 = warp * KS_K + stag;                  // first tile column of this thread
     const int jc0 = js - 1 + c0;                        // image column of its first pixel
     const bool row_in = (i >= 0) && (i < g.n);
     const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
@@ -756,10 +784,10 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     // the staged tile is a dense [KS_TR][PL] box; the box starts on the even column below tile column 0
     const int x_first = js - 1 - 2;                     // column index (skewed view of L) of tile column 0
     const int off_c = lane * PL + (x_first & 1) + c0;
-    // the columns left of tile column 0 / right of column 63 are not staged: the edge warps clamp them (they only feed
-    // the halo pixels, which are never scored)
-    const int cl = (warp == 0) ? 0 : -1;
-    const int cr = (warp == NW - 1) ? KS_K - 1 : KS_K;
+    // the column left of tile column 0 is not staged: warp 0 clamps it on the rows that start there (it only feeds the
+    // halo pixel, which is never scored); on the right the box is wide enough
+    const int cl = (c0 == 0) ? 0 : -1;
+    const int cr = KS_K;
 
     if (threadIdx.x == 0) {
         for (int d = 0; d < D; ++d) {
@@ -782,7 +810,7 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
         for (int k = 0; k < KS_K; ++k) {
             const int c = c0 + k, j = jc0 + k, d = j - i;
-            if (c >= 1 && c <= KS_SC && j < g.n && d >= 4 && d <= g.dhi) {
+            if (c >= 1 + stag && c <= KS_SC + stag && j < g.n && d >= 4 && d <= g.dhi) {
                 if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
             }
         }
@@ -795,6 +823,8 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const int st = nl % D;
         mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
         tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.nblk + b, &full[st]);
+        if (KS_PREFETCH > 0 && nl + KS_PREFETCH < n_levels_s)       // the level that will take this stage's successor: into L2
+            tma_prefetch_box3d(&tm->l, x_first & ~1, i0, lvl_step[nl + KS_PREFETCH] * g.nblk + b);
     };
 
     double vbest[KS_K], lA[KS_K], lB[KS_K];
@@ -1004,6 +1034,22 @@ scatter_coo_kernel(const int* __restrict__ rows, const int* __restrict__ cols, c
     for (long long e = blockIdx.x * 256LL + threadIdx.x; e < nnz; e += (long long)gridDim.x * 256LL) {
         const int r = rows[e], c = cols[e], d = c - r;
         if (r >= 0 && r < n && c >= 0 && c < n && d >= 4 && d <= dhi) rawb[(size_t)r * wc + (d - 4)] = vals[e];
+    }
+}
+
+// same for a whole batch: entries [offsets[b], offsets[b+1]) belong to block b (mb200_upload_coo_batch)
+__global__ void __launch_bounds__(256)
+scatter_coo_batch_kernel(const int* __restrict__ rows, const int* __restrict__ cols, const double* __restrict__ vals,
+                         const long long* __restrict__ offsets, int nblk, double* __restrict__ raw, int n, int wc, int dhi) {
+    const long long nnz = offsets[nblk];
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < nnz; e += (long long)gridDim.x * 256LL) {
+        int lo = 0, hi = nblk;                          // last b with offsets[b] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (offsets[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int r = rows[e], c = cols[e], d = c - r;
+        if (r >= 0 && r < n && c >= 0 && c < n && d >= 4 && d <= dhi) raw[((size_t)lo * n + r) * wc + (d - 4)] = vals[e];
     }
 }
 

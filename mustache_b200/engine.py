@@ -29,6 +29,7 @@ SIGNATURES = {
     "mb200_set_program": (C.c_int, [_H, C.c_int, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int]),
     "mb200_configure": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mb200_upload_coo_host": (C.c_int, [_H, C.c_int, _i32p, _i32p, _f64p, C.c_int64]),
+    "mb200_upload_coo_batch": (C.c_int, [_H, C.c_int, C.c_int, _i64p, _i32p, _i32p, _f64p]),
     "mb200_upload_coo_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mb200_upload_dense_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "mb200_upload_dense_dev": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
@@ -219,6 +220,14 @@ class ScaleSpaceEngine:
         vals = np.ascontiguousarray(vals, np.float64)
         self._chk(self.lib.mb200_upload_coo_host(self.h, int(block), _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(vals, _f64p),
                                                  len(vals)))
+
+    def upload_coo_batch(self, first_block, offsets, rows, cols, vals):
+        """Blocks first_block .. first_block + len(offsets) - 2 in one call: concatenated block-local COO (int32, int32,
+        float64) with entries [offsets[b], offsets[b+1]) belonging to block first_block + b."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        assert rows.dtype == np.int32 and cols.dtype == np.int32 and vals.dtype == np.float64
+        self._chk(self.lib.mb200_upload_coo_batch(self.h, int(first_block), len(offsets) - 1, _ptr(offsets, _i64p),
+                                                  _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(vals, _f64p)))
 
     def upload_coo_dev(self, block, rows, cols, vals):
         """Block-local COO already on the engine's device (torch tensors: int32, int32, float64), complete on their stream."""

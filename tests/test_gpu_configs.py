@@ -203,7 +203,8 @@ def test_capacity_retry(eng):
     """A batch whose records overflow the configured capacity is re-run with a larger one, not lost (the
     MB200_ERR_CAPACITY contract of include/mustache_b200.h)."""
     from mustache_b200.engine import EngineError
-    n, dpx, tiles = _three_tiles()
+    n, dpx = 1024, 400                     # ~14 k records per tile: above the engine's minimum capacity of 4096
+    tiles = [gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=70 + b, blob_seed=80 + b, nblobs=12, missing=0.1), n) for b in range(3)]
     _set(eng, [1.6, 3.2])
     masks = []
     for t in tiles:
@@ -217,7 +218,7 @@ def test_capacity_retry(eng):
         eng.records_batch()
     assert err.value.code == -3
     nz, found = eng.batch_counts()
-    assert (found > 100).all()
+    assert (found > 4096).all()
     tasks = [blockrun.BlockTask(0, b, [m]) for b, m in enumerate(masks)]
     real_configure, calls = eng.configure, []
 
@@ -255,3 +256,28 @@ def test_differential_multi_pass(eng):
         _equal_records(res[0][b], res[1][b], keys=("rows", "cols", "v", "p", "score_id", "sigma", "pair"))
     for b, pre in ((0, "m1_"), (1, "m2_")):
         assert np.array_equal(res[1][b]["rows"], z[pre + "rows"]) and np.abs(res[1][b]["pair"] - z[pre + "pair"]).max() <= 1e-9
+
+
+def test_batched_coo_upload_equals_per_block(eng):
+    """mb200_upload_coo_batch (one copy per array, one scatter kernel) builds the same tiles as per-block uploads, also
+    into a block range that does not start at 0 and with an empty block in the middle."""
+    n, dpx, tiles = _three_tiles()
+    _set(eng, [1.6, 3.2])
+    masks = []
+    for t in tiles:
+        r, c = np.nonzero(np.triu(t, 4))
+        masks.append((r, c, t[r, c]))
+    empty = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0))
+    order = [masks[0], empty, masks[1], masks[2]]
+    eng.configure(n, dpx, 5)
+    for b, m in enumerate(order):
+        eng.upload_coo(b + 1, *m)
+    eng.run()
+    ref = eng.records_batch()
+    eng.configure(n, dpx, 5)
+    eng.upload_coo_batch(1, *blockrun.concat_coo(order))
+    eng.run()
+    got = eng.records_batch()
+    assert ref[0]["n_found"] == 0 and ref[2]["n_found"] == 0 and ref[1]["n_found"] > 100
+    for a, b in zip(ref, got):
+        _equal_records(a, b)

@@ -35,6 +35,11 @@ class OracleEngine:
         c[rows, cols] = vals
         self.tiles[block] = c
 
+    def upload_coo_batch(self, first_block, offsets, rows, cols, vals):
+        for b in range(len(offsets) - 1):
+            a, z = offsets[b], offsets[b + 1]
+            self.upload_coo(first_block + b, rows[a:z], cols[a:z], vals[a:z])
+
     def run(self):
         self.diff = False
 

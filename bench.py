@@ -15,8 +15,9 @@ DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over 
                         mustache_b200.blockrun (owner ranks prepare, all_to_all exchange of block COO): strong scaling.
   --config chr / 3s     dense-band stand-ins of the 5 kb / 1 kb block shapes (24 x 2000^2, 6 x 4000^2).
 
-`value`  : contact-bins/s with the tiles already resident in HBM, device time from CUDA events on the engine's stream
-           (N > 1: wall clock around synchronised, barrier-bracketed steps, max over ranks).
+`value`  : contact-bins/s with the tiles already resident in HBM, device time from CUDA events on the engine's stream,
+           K steps bracketed by barrier + synchronize, max over ranks (the device-resident step has no collective: blocks
+           are independent; `wall_ms_per_step` is the host clock around the same region).
 `e2e`    : same metric through the public API with HOST buffers: host -> device upload of every tile (dense pinned tile
            for config 2, block COO for the chromosome configs), all kernels, ONE packed device -> host read of the
            records per batch, and for N > 1 the gather of the per-block result rows on the rank that writes the TSV.
@@ -348,10 +349,12 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     h.barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = eng.launches() * steps
-    step_ms = h.max_over_ranks((wall_ms if world > 1 else dev_ms) / steps)
+    step_ms = h.max_over_ranks(dev_ms / steps)        # CUDA events on the engine's stream, every N; max over ranks
+    wall_step_ms = h.max_over_ranks(wall_ms / steps)
     bins_all = h.sum_over_ranks(bins_rank)
     out = dict(step_ms=step_ms, bins_rank=bins_rank, bins_all=bins_all, value=bins_all / (step_ms * 1e-3), launches=launches,
-               phases={k: v / steps for k, v in phases.items()}, dev_ms=dev_ms / steps, blocks_rank=nblk // nmaps)
+               phases={k: v / steps for k, v in phases.items()}, dev_ms=dev_ms / steps, blocks_rank=nblk // nmaps,
+               wall_step_ms=wall_step_ms)
     if device_only:
         return out
 
@@ -386,6 +389,41 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     per_rec = 44 if nmaps == 2 else 36                   # rows, cols, score id (int32), v, p, sigma (+ pPair) (float64)
     out.update(e2e_ms=e2e_ms, e2e_value=bins_all / (e2e_ms * 1e-3), h2d=int(h.sum_over_ranks(h2d)),
                d2h=int(h.sum_over_ranks(n_found * per_rec + nblk * 16)), n_found=int(total_found))
+    return out
+
+
+def bench_normaliser(eng, steps, warmup):
+    """normalize_sparse (mustache.py:622-686) on the device, the producer of the tile values.  Inputs:
+    the BASELINE configs[2] chromosome (1 kb, 2 000-bin windows) and a 5 kb chromosome of configs[3]; bias-corrected counts.
+    Timed through the C ABI with host arrays (H2D of x, y, v and D2H of v inside); the numpy normaliser the CLI would
+    otherwise run (the reference's own code path, one core) beside it on the same input."""
+    from mustache_b200 import synth as gen
+    from mustache_b200.normalize import normalize_sparse, normalize_sparse_device
+    out = {}
+    for name, spec in (("config3_1kb", dict(gen.CONFIG3)), ("config4_s8_5kb", dict(gen.CONFIG4["s8"]))):
+        res = spec.pop("res")
+        x, y, c = gen.synthetic_chromosome(**spec)
+        bias = np.random.default_rng(5).uniform(0.6, 1.6, size=spec["n"])
+        v0 = c / bias[x] / bias[y]
+        x32, y32 = x.astype(np.int32), y.astype(np.int32)
+        for _ in range(warmup):
+            normalize_sparse_device(eng, x32, y32, v0.copy(), res, spec["dpx"])
+        ts = []
+        for _ in range(steps):
+            v = v0.copy()
+            t0 = time.perf_counter()
+            normalize_sparse_device(eng, x32, y32, v, res, spec["dpx"])
+            ts.append(time.perf_counter() - t0)
+        dev = v
+        t0 = time.perf_counter()
+        ref = v0.copy()
+        normalize_sparse(x, y, ref, res, spec["dpx"])
+        cpu_s = time.perf_counter() - t0
+        ms = float(np.median(ts)) * 1e3
+        out[name] = {"contacts": int(len(v0)), "bins": spec["n"], "diagonals": spec["dpx"] + 2, "window_bins": 2000000 // res,
+                     "ms": ms, "contacts_per_s": len(v0) / (ms * 1e-3), "bytes_per_s": 24 * len(v0) / (ms * 1e-3),
+                     "launches": eng.launches(), "numpy_one_core_s": cpu_s, "speedup_vs_numpy": cpu_s / (ms * 1e-3),
+                     "max_abs_diff_vs_numpy": float(np.abs(dev - ref).max())}
     return out
 
 
@@ -429,12 +467,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="2", choices=list(CONFIGS))
+    ap.add_argument("--config", default="2", choices=list(CONFIGS) + ["norm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 strong-scaling object of multi-GPU lines")
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
     args = ap.parse_args()
+    if args.config == "norm":
+        from mustache_b200.engine import ScaleSpaceEngine
+        print(json.dumps({"metric": "normalize_sparse_contacts_per_sec", "unit": "contacts/s", "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "dtype": "f64", "data": "synthetic",
+                          "inputs": bench_normaliser(ScaleSpaceEngine(int(os.environ.get("LOCAL_RANK", "0"))), args.steps, args.warmup)}))
+        return
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -506,6 +550,7 @@ def main():
            "e2e": {"value": m["e2e_value"], "unit": "contact-bins/s", "ms_per_step": m["e2e_ms"],
                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
            "gpu_launches": m["launches"], "records_per_step": m["n_found"], "phases_ms_per_step": m["phases"],
+           "wall_ms_per_step": m["wall_step_ms"],
            "roofline": roofline(cfg, args.config, m, peak, bool(peaks))}
     if c4 is not None:
         out["config4"] = c4

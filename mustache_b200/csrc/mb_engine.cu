@@ -3,6 +3,7 @@
 #include "../../include/mustache_b200.h"
 #include "mb_kernels.cuh"
 #include "mb_normalize.cuh"
+#include "mb_sort.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -45,7 +46,8 @@ struct mb200_engine {
     int ncta_h = 0;
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
-        nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets;
+        nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
+        nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist;
     std::vector<long long> h_offsets;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
@@ -320,6 +322,30 @@ int refresh_counts(mb200_engine* e) {
     return MB200_OK;
 }
 
+// Stable segmented LSD radix sort (mb_sort.cuh) of sort_keys[0] / sort_vals[0]; the result is back in buffer 0 (the
+// number of passes is rounded up to an even count).  nseg segments of at most max_len keys.
+int radix_sort(mb200_engine* e, const RsSegments& sg, int nseg, long long max_len, int key_bits, cudaStream_t sq) {
+    if (nseg < 1 || max_len < 1) return MB200_OK;
+    const int ntiles = (int)((max_len + RS_TILE - 1) / RS_TILE);
+    int st = ensure(e, e->sort_hist, (size_t)nseg * RS_RADIX * ntiles * sizeof(unsigned));
+    if (st) return st;
+    int passes = (key_bits + RS_BITS - 1) / RS_BITS;
+    passes += passes & 1;
+    for (int p = 0; p < passes; ++p) {
+        const unsigned long long* kin = (const unsigned long long*)e->sort_keys[p & 1].p;
+        unsigned long long* kout = (unsigned long long*)e->sort_keys[(p & 1) ^ 1].p;
+        const unsigned* vin = (const unsigned*)e->sort_vals[p & 1].p;
+        unsigned* vout = (unsigned*)e->sort_vals[(p & 1) ^ 1].p;
+        rs_hist_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, sg, p * RS_BITS, ntiles, (unsigned*)e->sort_hist.p);
+        rs_scan_kernel<<<nseg, 1024, 0, sq>>>((unsigned*)e->sort_hist.p, ntiles);
+        rs_scatter_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, vin, kout, vout, sg, p * RS_BITS, ntiles,
+                                                                      (const unsigned*)e->sort_hist.p);
+        CU(e, cudaGetLastError());
+    }
+    e->launches += 3 * passes;
+    return MB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -368,7 +394,8 @@ void mb200_destroy(mb200_engine* e) {
                      &e->st_vals, &e->st_dense, &e->dbgG, &e->dbgL, &e->rawD, &e->dout, &e->dmu, &e->dsd, &e->rec_pair,
                      &e->d_score_id, &e->d_score_sigma, &e->rec_sid, &e->rec_sigma, &e->d_tmaps, &e->d_dtmaps, &e->nz_xs, &e->nz_ds, &e->nz_perm,
                      &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines,
-                     &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets};
+                     &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
+                     &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -1112,6 +1139,7 @@ int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, 
     if (nnz < 0 || (nnz > 0 && (!x || !y || !v)) || resolution < 1 || distance_in_px < 0)
         return fail(e, MB200_ERR_ARG, "bad arguments to mb200_normalize_sparse");
     if (nnz == 0) return MB200_OK;
+    if (nnz >= (1LL << 32)) return fail(e, MB200_ERR_ARG, "more than 2^32 contacts in one chromosome");
     int st = use_device(e);
     if (st) return st;
     long long n = 0;
@@ -1120,80 +1148,87 @@ int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const int32_t* y, 
         n = std::max<long long>(n, std::max(x[k], y[k]));
     }
     n += 1;                                                                   // mustache.py:623
+    if (n >= (1LL << NZ_POS_BITS)) return fail(e, MB200_ERR_ARG, "chromosome of %lld bins (limit %d)", n, 1 << NZ_POS_BITS);
     const bool windowed = (n - distance_in_px) * (long long)resolution > 2000000;      // mustache.py:628
     const long long D = windowed ? (long long)distance_in_px + 2 : std::min<long long>(distance_in_px, n);
-    // stable counting sort by diagonal; contacts the reference's loop never visits go to bucket D
-    std::vector<long long> seg(D + 2, 0);
-    std::vector<int> dd(nnz);
-    for (int64_t k = 0; k < nnz; ++k) {
-        const long long d = std::llabs((long long)y[k] - (long long)x[k]);
-        dd[k] = (int)std::min<long long>(d, D);
-        ++seg[dd[k] + 1];
+    const size_t m8 = (size_t)nnz * sizeof(double), m4 = (size_t)nnz * sizeof(int);
+    if ((st = ensure(e, e->nz_x, m4))) return st;
+    if ((st = ensure(e, e->nz_y, m4))) return st;
+    if ((st = ensure(e, e->nz_v, m8))) return st;
+    if ((st = ensure(e, e->nz_xs, m4))) return st;
+    if ((st = ensure(e, e->nz_vs, m8))) return st;
+    if ((st = ensure(e, e->nz_out, m8))) return st;
+    for (int k = 0; k < 2; ++k) {
+        if ((st = ensure(e, e->sort_keys[k], (size_t)nnz * sizeof(unsigned long long)))) return st;
+        if ((st = ensure(e, e->sort_vals[k], (size_t)nnz * sizeof(unsigned)))) return st;
     }
-    for (long long d = 0; d <= D; ++d) seg[d + 1] += seg[d];
-    std::vector<long long> cur(seg.begin(), seg.end() - 1), perm(nnz);
-    std::vector<int> xs(nnz), ds(nnz);
-    std::vector<double> vs(nnz);
-    for (int64_t k = 0; k < nnz; ++k) {
-        const long long o = cur[dd[k]]++;
-        perm[o] = k;
-        xs[o] = x[k];
-        ds[o] = dd[k];
-        double val = v[k];
-        if (!windowed && !std::isfinite(val)) val = 0.0;                      // mustache.py:672
-        vs[o] = val;
-    }
-    const long long m = seg[D];                                               // contacts on the visited diagonals
-    if ((st = ensure(e, e->nz_xs, nnz * sizeof(int)))) return st;
-    if ((st = ensure(e, e->nz_ds, nnz * sizeof(int)))) return st;
-    if ((st = ensure(e, e->nz_perm, nnz * sizeof(long long)))) return st;
-    if ((st = ensure(e, e->nz_vs, nnz * sizeof(double)))) return st;
-    if ((st = ensure(e, e->nz_out, nnz * sizeof(double)))) return st;
     if ((st = ensure(e, e->nz_seg, (D + 2) * sizeof(long long)))) return st;
     if ((st = ensure(e, e->nz_mean, (D + 1) * sizeof(double)))) return st;
     if ((st = ensure(e, e->nz_sd, (D + 1) * sizeof(double)))) return st;
     if ((st = ensure(e, e->nz_w, (D + 1) * sizeof(double)))) return st;
     cudaStream_t sq = e->stream;
-    CU(e, cudaMemcpyAsync(e->nz_xs.p, xs.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, sq));
-    CU(e, cudaMemcpyAsync(e->nz_ds.p, ds.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, sq));
-    CU(e, cudaMemcpyAsync(e->nz_perm.p, perm.data(), nnz * sizeof(long long), cudaMemcpyHostToDevice, sq));
-    CU(e, cudaMemcpyAsync(e->nz_vs.p, vs.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, sq));
-    CU(e, cudaMemcpyAsync(e->nz_seg.p, seg.data(), (D + 2) * sizeof(long long), cudaMemcpyHostToDevice, sq));
-    // pass-through for the contacts no diagonal loop visits: out starts as (cleaned) v in the caller's order
-    std::vector<double> base(nnz);
-    for (int64_t o = 0; o < nnz; ++o) base[perm[o]] = vs[o];
-    CU(e, cudaMemcpyAsync(e->nz_out.p, base.data(), nnz * sizeof(double), cudaMemcpyHostToDevice, sq));
+    e->launches = 0;
+    CU(e, cudaMemcpyAsync(e->nz_x.p, x, m4, cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_y.p, y, m4, cudaMemcpyHostToDevice, sq));
+    CU(e, cudaMemcpyAsync(e->nz_v.p, v, m8, cudaMemcpyHostToDevice, sq));
+    const int grid = (int)std::min<long long>((nnz + 255) / 256, 148LL * 16);
+    // 1. contacts grouped by diagonal, by position inside a diagonal (stable: input order for row-sorted input);
+    //    contacts the reference's loop never visits (|y - x| >= D) land in bucket D and pass through
+    nz_keys_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_x.p, (const int*)e->nz_y.p, nnz, (int)D,
+                                         (unsigned long long*)e->sort_keys[0].p, (unsigned*)e->sort_vals[0].p);
+    CU(e, cudaGetLastError());
+    std::vector<long long> one_seg = {0, (long long)nnz};
+    CU(e, cudaMemcpyAsync(e->nz_seg.p, one_seg.data(), 2 * sizeof(long long), cudaMemcpyHostToDevice, sq));
+    CU(e, cudaStreamSynchronize(sq));                                          // one_seg is a local
+    RsSegments sg = {(const long long*)e->nz_seg.p, nullptr, 0, 0};
+    int dbits = 1;
+    while ((1LL << dbits) <= D) ++dbits;
+    // the sort reads its single segment's bounds from nz_seg[0..1]; the diagonals' bounds replace them afterwards
+    if ((st = radix_sort(e, sg, 1, nnz, NZ_POS_BITS + dbits, sq))) return st;
+    const unsigned long long* keys = (const unsigned long long*)e->sort_keys[0].p;
+    const unsigned* idx = (const unsigned*)e->sort_vals[0].p;
+    nz_segments_kernel<<<(unsigned)((D + 2 + 255) / 256), 256, 0, sq>>>(keys, nnz, (int)D, (long long*)e->nz_seg.p);
+    nz_gather_kernel<<<grid, 256, 0, sq>>>(keys, idx, (const double*)e->nz_v.p, nnz, windowed ? 0 : 1, (int*)e->nz_xs.p,
+                                           (double*)e->nz_vs.p);
+    CU(e, cudaGetLastError());
+    // 2. np.mean / np.std per diagonal
     if (D > 0) {
-        nz_stats_kernel<<<(unsigned)((D + 63) / 64), 64, 0, sq>>>((const double*)e->nz_vs.p, (const long long*)e->nz_seg.p, (int)D,
-                                                                  (double*)e->nz_mean.p, (double*)e->nz_sd.p);
+        nz_stats_kernel<<<(unsigned)((D * 8 + 255) / 256), 256, 0, sq>>>((const double*)e->nz_vs.p, (const long long*)e->nz_seg.p,
+                                                                         (int)D, (double*)e->nz_mean.p, (double*)e->nz_sd.p);
         CU(e, cudaGetLastError());
     }
-    const int grid = (int)std::min<long long>((m + 255) / 256, 148LL * 16);
-    if (windowed && m > 0) {
+    e->launches += 4;
+    // 3. z-scores; the pass-through bucket keeps its (cleaned) values
+    if (windowed) {
         std::vector<double> mean(D), w(D);
         CU(e, cudaMemcpyAsync(mean.data(), e->nz_mean.p, D * sizeof(double), cudaMemcpyDeviceToHost, sq));
         CU(e, cudaStreamSynchronize(sq));
-        for (long long d = 0; d < D; ++d) w[d] = 1.0 + std::log(1.0 + mean[d]) / std::log(30.0);     // mustache.py:667-668
+        // 1 + math.log(1 + mean, 30) with the host's libm, as the reference evaluates it (mustache.py:667-668)
+        for (long long d = 0; d < D; ++d) w[d] = 1.0 + std::log(1.0 + mean[d]) / std::log(30.0);
         CU(e, cudaMemcpyAsync(e->nz_w.p, w.data(), D * sizeof(double), cudaMemcpyHostToDevice, sq));
         if (weights)
             for (long long d = 0; d < D && d < weights_cap; ++d) weights[d] = w[d];
         if (n_weights) *n_weights = (int)D;
-        if ((st = ensure(e, e->nz_lines, (size_t)D * n * sizeof(double)))) return st;
-        CU(e, cudaMemsetAsync(e->nz_lines.p, 0, (size_t)D * n * sizeof(double), sq));
-        nz_fill_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_xs.p, (const int*)e->nz_ds.p, (const double*)e->nz_vs.p, m, n,
-                                             (double*)e->nz_lines.p);
+        CU(e, cudaMemcpyAsync(e->nz_out.p, e->nz_v.p, m8, cudaMemcpyDeviceToDevice, sq));      // pass-through default
+        long long h_seg_D = 0;
+        CU(e, cudaMemcpyAsync(&h_seg_D, (long long*)e->nz_seg.p + D, sizeof(long long), cudaMemcpyDeviceToHost, sq));
+        CU(e, cudaStreamSynchronize(sq));                                      // w is a local; h_seg_D = visited contacts
+        if (h_seg_D > 0) {
+            const int wgrid = (int)std::min<long long>((h_seg_D + 7) / 8, 148LL * 32);
+            nz_window_kernel<<<wgrid, 256, 0, sq>>>(keys, (const int*)e->nz_xs.p, (const double*)e->nz_vs.p, idx,
+                                                    (const long long*)e->nz_seg.p, h_seg_D, n, (int)(2000000 / resolution),
+                                                    (const double*)e->nz_mean.p, (const double*)e->nz_sd.p,
+                                                    (const double*)e->nz_w.p, (double*)e->nz_out.p);
+            CU(e, cudaGetLastError());
+            e->launches += 1;
+        }
+    } else {
+        nz_global_kernel<<<grid, 256, 0, sq>>>(keys, idx, (const double*)e->nz_vs.p, nnz, (int)D, (const double*)e->nz_mean.p,
+                                               (const double*)e->nz_sd.p, (double*)e->nz_out.p);
         CU(e, cudaGetLastError());
-        nz_window_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_xs.p, (const int*)e->nz_ds.p, (const long long*)e->nz_perm.p, m, n,
-                                               (int)(2000000 / resolution), (const double*)e->nz_lines.p,
-                                               (const double*)e->nz_mean.p, (const double*)e->nz_sd.p, (const double*)e->nz_w.p,
-                                               (double*)e->nz_out.p);
-        CU(e, cudaGetLastError());
-    } else if (m > 0) {
-        nz_global_kernel<<<grid, 256, 0, sq>>>((const int*)e->nz_ds.p, (const long long*)e->nz_perm.p, (const double*)e->nz_vs.p, m,
-                                               (int)D, (const double*)e->nz_mean.p, (const double*)e->nz_sd.p, (double*)e->nz_out.p);
-        CU(e, cudaGetLastError());
+        e->launches += 1;
     }
-    CU(e, cudaMemcpyAsync(v, e->nz_out.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, sq));
+    CU(e, cudaMemcpyAsync(v, e->nz_out.p, m8, cudaMemcpyDeviceToHost, sq));
     CU(e, cudaStreamSynchronize(sq));
     return MB200_OK;
 }

@@ -155,8 +155,8 @@ def prepare_pair(f1, f2, norm_method, CHRM_SIZE, res, distance_filter, bias1, bi
         print("Normalizing contact map...")
     dpx = tiler.distance_in_px(distance_filter, res)
     n = int(max(max(m[0].max(), m[1].max()) + 1 for m in maps))
-    for m in maps:
-        normalize(m[0], m[1], m[2], res, dpx, eng=get_engine())
+    for m, b in zip(maps, (bias1, bias2)):
+        normalize(m[0], m[1], m[2], res, dpx, eng=get_engine(), biased=bool(b))
     return dict(maps=[tuple(m) for m in maps], n=n)
 
 

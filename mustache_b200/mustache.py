@@ -202,7 +202,7 @@ def prepare_chromosome(f, norm_method, CHRM_SIZE, res, distance_filter, bias, ch
         print("Normalizing contact map...")
     dpx = tiler.distance_in_px(distance_filter, res)
     n = int(max(np.max(x), np.max(y)) + 1)
-    normalize(x, y, v, res, dpx, eng=get_engine())      # in place
+    normalize(x, y, v, res, dpx, eng=get_engine(), biased=bool(bias))      # in place
     return dict(maps=[(np.asarray(x), np.asarray(y), np.asarray(v))], n=n)
 
 

@@ -8,8 +8,8 @@ is CPU dependent, so no implementation can match it bit for bit on every host). 
 to ~1e-13 and give the same loops (chr21: 90 loops, FDR within 1e-6).  On raw integer counts (what diff_mustache.py
 feeds for map 1, quirk #13) the reference's z-scores inside windows of identical counts are rounding noise divided by
 rounding noise (val - mean ~ 1e-16, std ~ 1e-8), some of them NaN -> 0 -> off the mask: there the reference's own result
-depends on its BLAS build, and only the numpy path on the same host reproduces it.  The CLI therefore keeps the numpy
-normaliser by default and switches to the device one with MUSTACHE_NORMALIZE=device.
+depends on its BLAS build, and only the numpy path on the same host reproduces it.  The CLI therefore uses the device
+normaliser for bias-corrected input (`-b`) and the numpy one for raw counts; MUSTACHE_NORMALIZE=host|device overrides.
 """
 import ctypes as C
 import os
@@ -105,9 +105,15 @@ def normalize_sparse_device(eng, x, y, v, resolution, distance_in_px):
     return list(w[:nw.value])
 
 
-def normalize(x, y, v, resolution, distance_in_px, eng=None):
-    """What the CLI calls: the numpy normaliser (reference-exact), or the device one when MUSTACHE_NORMALIZE=device."""
-    integer_counts = np.asarray(v).dtype.kind in "iu"        # z-scores truncate into the integer array: numpy path only
-    if os.environ.get("MUSTACHE_NORMALIZE", "host") != "device" or eng is None or integer_counts:
+def normalize(x, y, v, resolution, distance_in_px, eng=None, biased=False):
+    """What the CLI calls.  Bias-corrected maps (`-b`, the recommended way to run the reference) go through the device
+    normaliser; raw counts stay on the numpy path: inside a window of identical counts the reference's z-score is rounding
+    noise over rounding noise (some of it NaN -> 0 -> off the mask) and depends on the BLAS behind np.convolve, so only
+    numpy on the same host reproduces it (diff_mustache.py feeds map 1 that way), and integer arrays
+    must take the truncating numpy assignment (mustache.py:668).  MUSTACHE_NORMALIZE=host|device overrides."""
+    mode = os.environ.get("MUSTACHE_NORMALIZE", "auto")
+    integer_counts = np.asarray(v).dtype.kind in "iu"
+    use_device = eng is not None and not integer_counts and (mode == "device" or (mode == "auto" and biased))
+    if not use_device:
         return normalize_sparse(x, y, v, resolution, distance_in_px)
     return normalize_sparse_device(eng, x, y, v, resolution, distance_in_px)

@@ -129,3 +129,37 @@ def test_windowed_branch_other_window(eng):
     w_got = normalize.normalize_sparse_device(eng, x, y, got, res, dpx)
     assert w_got == w_ref and len(w_ref) == dpx + 2
     assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_unsorted_input(eng):
+    """Contacts in random order: the device groups them by (diagonal, position) itself.  np.mean then sees another order
+    than numpy's, so everything is compared at tolerance level."""
+    rng = np.random.default_rng(23)
+    n, res, dpx = 3000, 5000, 400
+    x, y, c = gen.synthetic_chromosome(n, dpx, 18.0, seed=5, nloops=20, loop_dmax=30)
+    v = c.astype(np.float64) * rng.uniform(0.7, 1.3, size=len(c))
+    perm = rng.permutation(len(v))
+    x, y, v = x[perm], y[perm], v[perm]
+    ref = v.copy()
+    w_ref = normalize.normalize_sparse(x, y, ref, res, dpx)
+    got = v.copy()
+    w_got = normalize.normalize_sparse_device(eng, x, y, got, res, dpx)
+    assert np.allclose(w_got, w_ref, rtol=1e-13, atol=0)
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_config3_input_at_1kb(eng):
+    """BASELINE configs[2] input (1.3 M contacts, 2 002 diagonals, 2 000-bin windows) with a non-trivial bias so that no
+    window holds identical values: device vs numpy normaliser."""
+    spec = dict(gen.CONFIG3)
+    res = spec.pop("res")
+    spec["n"] = 12000                                           # 5 blocks' worth: keeps the numpy side at ~15 s
+    x, y, c = gen.synthetic_chromosome(**spec)
+    bias = np.random.default_rng(5).uniform(0.6, 1.6, size=spec["n"])
+    v = c / bias[x] / bias[y]
+    ref = v.copy()
+    w_ref = normalize.normalize_sparse(x, y, ref, res, spec["dpx"])
+    got = v.copy()
+    w_got = normalize.normalize_sparse_device(eng, x, y, got, res, spec["dpx"])
+    assert w_got == w_ref
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())

@@ -111,6 +111,21 @@ MB200_API int mb200_fetch_packed(mb200_engine* e, int64_t capacity, int32_t* row
 MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, void** v, void** score_id, void** scored_index,
                                   void** p, void** sigma, void** pair);
 
+/* Device half of the block post-processing, mustache.py:774-811 (and the per-map half of diff_mustache.py:428-500): for every
+ * block of the batch, Benjamini-Hochberg over its found p-values (mustache.py:778; statsmodels' fdrcorrection formula, same
+ * IEEE operations), selection `o < pt` (:791), the sparsity filter with numpy's slice semantics and threshold st (:800-811).
+ * What leaves the GPU is one entry per SELECTED pixel: block, tile row / column, q (FDR), sigma (Scales), flags (bit 0: passed
+ * the sparsity filter), cval (its value in the 2-filled tile, for the enrichment filter :822-828) and the 3 x 3 neighbourhoods
+ * of the dense `o` and `so` matrices (:789-795; row-major, 1 off the mask, 2 / 1 on the mask but never updated), which is all
+ * the clustering step (:830-848) reads.  candidate_fraction: capacity as a fraction of the record capacity (<= 0: 1/16);
+ * mb200_fetch_candidates returns MB200_ERR_CAPACITY when it was exceeded.  Order of the entries is unspecified.
+ * mb200_fetch_q: q of every record of a block in the order of mb200_fetch_records (parity hook). */
+MB200_API int mb200_select_candidates(mb200_engine* e, double pt, double st, double candidate_fraction);
+MB200_API int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, int32_t* row, int32_t* col, int32_t* flags,
+                                     double* q, double* sigma, double* cval, double* o9, double* so9, int64_t* n_out);
+MB200_API int mb200_fetch_q(mb200_engine* e, int block, int64_t capacity, double* q, int64_t* n_out);
+MB200_API int mb200_last_post_ms(mb200_engine* e, float* ms);
+
 /* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The
  * reference's analogue is `-p`, the number of block processes alive at a time (mustache.py:931-934).  Takes effect at the
  * next mb200_configure. */

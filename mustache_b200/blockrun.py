@@ -79,9 +79,11 @@ def concat_coo(maps):
     return offsets, rows, cols, vals
 
 
-def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timings=None, totals=None):
+def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timings=None, totals=None, select=None):
     """Generator over (task, [records per map]) for this rank's tasks.  Engine batches are bounded by the tile memory;
-    a batch whose records overflow the engine's capacity is re-run with a larger one (MB200_ERR_CAPACITY contract)."""
+    a batch whose records overflow the engine's capacity is re-run with a larger one (MB200_ERR_CAPACITY contract).
+    select=(pt, st): BH, the `o < pt` cut and the sparsity filter run on the device and the generator yields the selected
+    candidates (ScaleSpaceEngine.candidates_batch) instead of every record."""
     from .engine import EngineError
     nmaps = 2 if differential else 1
     wc = min(dpx + 1, chunk - 1) - 3
@@ -101,7 +103,11 @@ def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timin
             else:
                 eng.run()
             try:
-                recs = eng.records_batch(pair=differential)
+                if select is not None:
+                    eng.select_candidates(*select)
+                    recs = eng.candidates_batch()
+                else:
+                    recs = eng.records_batch(pair=differential)
                 break
             except EngineError as err:
                 if err.code != -3 or fraction >= 1.0:
@@ -115,7 +121,7 @@ def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timin
 
 
 def shard_and_call(preps, n_chrom, dpx, nmaps, eng, block_fn, rank=0, world=1, verbose=True, owners=None, timings=None,
-                   width=4):
+                   width=4, select=None):
     """Runs every block of every chromosome once, somewhere, and returns {chromosome index: [call, ...]} on rank 0
     ({} elsewhere).  block_fn(task, records, chunk, start) -> list of calls [x, y, ..(width-2 more)] of that block in
     chromosome coordinates BEFORE the overlap de-duplication of process_block (mustache.py:945-960), applied here."""
@@ -125,7 +131,7 @@ def shard_and_call(preps, n_chrom, dpx, nmaps, eng, block_fn, rank=0, world=1, v
     chunk = max(2 * dpx, 2000) if not geom else next(iter(geom.values()))[0]
     totals = {c: len(g[1]) for c, g in geom.items()}
     for task, recs in run_batches(eng, tasks, chunk, dpx, differential=(nmaps == 2), verbose=verbose, timings=timings,
-                                  totals=totals):
+                                  totals=totals, select=select):
         _, starts, ends = geom[task.chrom]
         ms = tiler.block_mask_size(task.block, starts, ends, dpx)
         for call in block_fn(task, recs, chunk, starts[task.block]):

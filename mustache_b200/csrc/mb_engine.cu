@@ -4,6 +4,7 @@
 #include "mb_kernels.cuh"
 #include "mb_normalize.cuh"
 #include "mb_sort.cuh"
+#include "mb_post.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -47,7 +48,12 @@ struct mb200_engine {
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
-        nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist;
+        nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist,
+        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count;
+    long long cand_cap = 0;
+    bool post_done = false;
+    cudaEvent_t ev_post0 = nullptr, ev_post1 = nullptr;
+    float t_post = 0;
     std::vector<long long> h_offsets;
     std::vector<unsigned long long> h_nz, h_rec;
     std::vector<int> h_nonfinite;
@@ -376,7 +382,8 @@ int mb200_create(int device, mb200_engine** out) {
         cudaEventCreateWithFlags(&e->ev_run[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_prep) != cudaSuccess ||
-        cudaEventCreate(&e->ev_end) != cudaSuccess) {
+        cudaEventCreate(&e->ev_end) != cudaSuccess || cudaEventCreate(&e->ev_post0) != cudaSuccess ||
+        cudaEventCreate(&e->ev_post1) != cudaSuccess) {
         delete e;
         return MB200_ERR_CUDA;
     }
@@ -395,12 +402,16 @@ void mb200_destroy(mb200_engine* e) {
                      &e->d_score_id, &e->d_score_sigma, &e->rec_sid, &e->rec_sigma, &e->d_tmaps, &e->d_dtmaps, &e->nz_xs, &e->nz_ds, &e->nz_perm,
                      &e->nz_vs, &e->nz_out, &e->nz_seg, &e->nz_mean, &e->nz_sd, &e->nz_w, &e->nz_lines,
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
-                     &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist};
+                     &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
+                     &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_prep) cudaEventDestroy(e->ev_prep);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->ev_post0) cudaEventDestroy(e->ev_post0);
+    if (e->ev_post1) cudaEventDestroy(e->ev_post1);
     if (e->ev_up) cudaEventDestroy(e->ev_up);
     for (int k = 0; k < 2; ++k)
         if (e->ev_run[k]) cudaEventDestroy(e->ev_run[k]);
@@ -621,6 +632,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->ran = false;
     e->counts_valid = false;
     e->packed = false;
+    e->post_done = false;
     return MB200_OK;
 }
 
@@ -761,6 +773,7 @@ int mb200_run(mb200_engine* e) {
     e->counts_valid = false;
     e->ran_diff = false;
     e->packed = false;
+    e->post_done = false;
     if ((st = adopt_uploads(e))) return st;
     const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
     while ((int)e->ev_pass.size() < 4 * npass) {
@@ -948,6 +961,128 @@ int mb200_batch_counts(mb200_engine* e, int64_t* nz_count, int64_t* n_found) {
         if (nz_count) nz_count[b] = (int64_t)e->h_nz[b];
         if (n_found) n_found[b] = (int64_t)e->h_rec[b];
     }
+    return MB200_OK;
+}
+
+// Device half of the block post-processing (mb_post.cuh): BH per block, o < pt, sparsity filter, neighbourhood patches.
+int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double candidate_fraction) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->configured || !e->ran) return fail(e, MB200_ERR_ARG, "mb200_run has not been called for this batch");
+    if (!(pt <= 1.0)) return fail(e, MB200_ERR_ARG, "pt > 1 would select off-mask pixels in the reference; not supported");
+    int st = use_device(e);
+    if (st) return st;
+    const int B = e->nblocks;
+    const size_t slots = (size_t)B * e->rec_cap;
+    cudaStream_t sq = e->stream;
+    for (int k = 0; k < 2; ++k) {
+        if ((st = ensure(e, e->sort_keys[k], slots * sizeof(unsigned long long)))) return st;
+        if ((st = ensure(e, e->sort_vals[k], slots * sizeof(unsigned)))) return st;
+    }
+    if ((st = ensure(e, e->rec_q, slots * sizeof(double)))) return st;
+    const int ntiles = (int)((e->rec_cap + RS_TILE - 1) / RS_TILE);
+    if ((st = ensure(e, e->bh_tmin, (size_t)B * ntiles * sizeof(double)))) return st;
+    const size_t tile = (size_t)e->n * e->wc;
+    if ((st = ensure(e, e->slotmap, (size_t)B * tile * sizeof(int)))) return st;
+    const double frac = candidate_fraction > 0 ? candidate_fraction : 1.0 / 16.0;
+    e->cand_cap = std::max<long long>(256, (long long)(frac * (double)slots));
+    const size_t cc = (size_t)e->cand_cap;
+    if ((st = ensure(e, e->cd_block, cc * sizeof(int)))) return st;
+    if ((st = ensure(e, e->cd_row, cc * sizeof(int)))) return st;
+    if ((st = ensure(e, e->cd_col, cc * sizeof(int)))) return st;
+    if ((st = ensure(e, e->cd_flags, cc * sizeof(int)))) return st;
+    if ((st = ensure(e, e->cd_q, cc * sizeof(double)))) return st;
+    if ((st = ensure(e, e->cd_sigma, cc * sizeof(double)))) return st;
+    if ((st = ensure(e, e->cd_cval, cc * sizeof(double)))) return st;
+    if ((st = ensure(e, e->cd_o9, cc * 9 * sizeof(double)))) return st;
+    if ((st = ensure(e, e->cd_so9, cc * 9 * sizeof(double)))) return st;
+    if ((st = ensure(e, e->cd_count, sizeof(unsigned long long)))) return st;
+    CU(e, cudaEventRecord(e->ev_post0, sq));
+    const unsigned long long* cnt = (const unsigned long long*)e->rec_count.p;
+    const int gx = B >= 8 ? 16 : 148 * 2;
+    bh_keys_kernel<<<dim3(gx, B), 256, 0, sq>>>(cnt, e->rec_cap, (const double*)e->rec_p.p, (unsigned long long*)e->sort_keys[0].p,
+                                                (unsigned*)e->sort_vals[0].p);
+    CU(e, cudaGetLastError());
+    RsSegments sg = {nullptr, cnt, e->rec_cap, e->rec_cap};
+    if ((st = radix_sort(e, sg, B, e->rec_cap, 64, sq))) return st;
+    const unsigned long long* keys = (const unsigned long long*)e->sort_keys[0].p;
+    bh_tilemin_kernel<<<dim3(ntiles, B), RS_THREADS, 0, sq>>>(keys, cnt, e->rec_cap, ntiles, (double*)e->bh_tmin.p);
+    bh_suffix_kernel<<<(B + 63) / 64, 64, 0, sq>>>(B, ntiles, (double*)e->bh_tmin.p);
+    bh_q_kernel<<<dim3(ntiles, B), RS_THREADS, 0, sq>>>(keys, (const unsigned*)e->sort_vals[0].p, cnt, e->rec_cap, ntiles,
+                                                         (const double*)e->bh_tmin.p, (double*)e->rec_q.p);
+    CU(e, cudaGetLastError());
+    CU(e, cudaMemsetAsync(e->slotmap.p, 0xFF, (size_t)B * tile * sizeof(int), sq));
+    CU(e, cudaMemsetAsync(e->cd_count.p, 0, sizeof(unsigned long long), sq));
+    post_slotmap_kernel<<<dim3(gx, B), 256, 0, sq>>>(cnt, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, e->n, e->wc,
+                                                     (int*)e->slotmap.p);
+    PostOut po = {(int*)e->cd_block.p, (int*)e->cd_row.p, (int*)e->cd_col.p, (int*)e->cd_flags.p, (double*)e->cd_q.p,
+                  (double*)e->cd_sigma.p, (double*)e->cd_cval.p, (double*)e->cd_o9.p, (double*)e->cd_so9.p,
+                  (unsigned long long*)e->cd_count.p, e->cand_cap};
+    post_candidates_kernel<<<dim3(B >= 8 ? 32 : 148 * 4, B), 256, 0, sq>>>(
+        cnt, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, (const double*)e->rec_q.p, (const double*)e->rec_sigma.p,
+        raw_slot(e, e->slot_run), (const int*)e->slotmap.p, e->n, e->wc, e->dhi, e->dpx, pt, st_thr, po);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(e->ev_post1, sq));
+    CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));          // the candidate kernel reads the tile slot too
+    e->launches += 6;
+    e->post_done = true;
+    return MB200_OK;
+}
+
+int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, int32_t* row, int32_t* col, int32_t* flags, double* q,
+                           double* sigma, double* cval, double* o9, double* so9, int64_t* n_out) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
+    int st = use_device(e);
+    if (st) return st;
+    if ((st = refresh_counts(e))) return st;                      // also reports non-finite tiles / record overflow
+    for (int b = 0; b < e->nblocks; ++b) {
+        if (e->h_nonfinite[b]) return fail(e, MB200_ERR_NONFINITE, "block %d holds non-finite values", b);
+        if ((long long)e->h_rec[b] > e->rec_cap)
+            return fail(e, MB200_ERR_CAPACITY, "block %d produced %llu records, capacity %lld", b, e->h_rec[b], e->rec_cap);
+    }
+    unsigned long long tot = 0;
+    CU(e, cudaMemcpyAsync(&tot, e->cd_count.p, sizeof(tot), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (n_out) *n_out = (int64_t)tot;
+    if ((long long)tot > e->cand_cap)
+        return fail(e, MB200_ERR_CAPACITY, "%llu candidates, capacity %lld: raise candidate_fraction and call mb200_select_candidates again", tot, e->cand_cap);
+    if (tot == 0 || capacity <= 0) return MB200_OK;
+    if ((int64_t)tot > capacity) return fail(e, MB200_ERR_CAPACITY, "%llu candidates, caller capacity %lld", tot, (long long)capacity);
+    const size_t m = (size_t)tot;
+    if (block) CU(e, cudaMemcpyAsync(block, e->cd_block.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (row) CU(e, cudaMemcpyAsync(row, e->cd_row.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (col) CU(e, cudaMemcpyAsync(col, e->cd_col.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (flags) CU(e, cudaMemcpyAsync(flags, e->cd_flags.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (q) CU(e, cudaMemcpyAsync(q, e->cd_q.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (sigma) CU(e, cudaMemcpyAsync(sigma, e->cd_sigma.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (cval) CU(e, cudaMemcpyAsync(cval, e->cd_cval.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (o9) CU(e, cudaMemcpyAsync(o9, e->cd_o9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (so9) CU(e, cudaMemcpyAsync(so9, e->cd_so9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_fetch_q(mb200_engine* e, int block, int64_t capacity, double* q, int64_t* n_out) {
+    int64_t nz = 0, nf = 0;
+    int st = mb200_block_counts(e, block, &nz, &nf);
+    if (n_out) *n_out = nf;
+    if (st) return st;
+    if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
+    const int64_t m = std::min<int64_t>(nf, capacity);
+    if (m <= 0) return MB200_OK;
+    if (!q) return fail(e, MB200_ERR_ARG, "null output array");
+    CU(e, cudaMemcpyAsync(q, (double*)e->rec_q.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_last_post_ms(mb200_engine* e, float* ms) {
+    if (!e || !ms) return MB200_ERR_ARG;
+    if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
+    int st = use_device(e);
+    if (st) return st;
+    CU(e, cudaEventSynchronize(e->ev_post1));
+    CU(e, cudaEventElapsedTime(ms, e->ev_post0, e->ev_post1));
     return MB200_OK;
 }
 

@@ -117,19 +117,26 @@ def mustache(c, chromosome, chromosome2, res, pval_weights, start, end, mask_siz
     """
     if chromosome != chromosome2:
         raise NotImplementedError("inter-chromosomal tiles: the reference path is broken (mustache.py:939-942); unsupported")
+    from . import blockrun
     n = c.shape[0]
     d = np.subtract.outer(np.arange(n), np.arange(c.shape[1])) * -1
     nzmask = (c != 0) & (d >= 4)
+    if (nzmask & (d > distance_in_px + 1)).any():
+        # regulator() never builds such a tile (the readers keep |j - i| <= dpx + 1, mustache.py:264); the engine stores the
+        # band only, so refuse loudly instead of scoring a different mask than the reference would
+        raise ValueError("tile holds contacts beyond distance_in_px + 1 diagonals; not supported by the banded engine")
     mr, mc = np.nonzero(nzmask)
     mv = c[mr, mc]
     if len(mr) < 50:
         return []
     eng = get_engine()
     _set_octaves(eng, octave_values)
-    rec = eng.scale_space_dense(np.ascontiguousarray(c, dtype=np.float64), distance_in_px)
+    task = blockrun.BlockTask(0, 0, [(mr, mc, np.ascontiguousarray(mv, dtype=np.float64))])
+    (_, cands), = blockrun.run_batches(eng, [task], n, distance_in_px, select=(pt, st))
+    assert cands[0]["nz_count"] == len(mr)
     c[d <= 4] = 2
     c[d >= distance_in_px + 1] = 2
-    return _loops_from_records(n, distance_in_px, start, (mr, mc, mv), rec, st, pt)
+    return postprocess.call_loops_from_candidates(n, distance_in_px, start, mr, mc, mv, cands[0])
 
 
 def process_block(i, start, end, overlap_size, loops, o):
@@ -155,9 +162,14 @@ def _dist_env():
 
 
 def _block_calls(dpx, st, pt):
-    """Post-processing of one block where it was computed (mustache.py:774-850)."""
-    def fn(task, recs, chunk, start):
-        return _loops_from_records(chunk, dpx, start, task.maps[0], recs[0], st, pt)
+    """Host half of the post-processing of one block, on the rank that computed it: the device delivered the candidates
+    that passed BH, `o < pt` and the sparsity filter (mustache.py:774-811); enrichment filter and clustering here
+    (mustache.py:816-848)."""
+    def fn(task, cands, chunk, start):
+        mr, mc, mv = task.maps[0]
+        if cands[0]["nz_count"] < 50:                            # mustache.py:701-702
+            return []
+        return postprocess.call_loops_from_candidates(chunk, dpx, start, mr, mc, mv, cands[0])
     return fn
 
 
@@ -170,7 +182,7 @@ def call_chromosomes(preps, n_chrom, distance_in_px, octave_values, st, pt, verb
     eng = get_engine()
     _set_octaves(eng, octave_values)
     return blockrun.shard_and_call(preps, n_chrom, distance_in_px, 1, eng, _block_calls(distance_in_px, st, pt), rank=rank,
-                                   world=world, verbose=verbose, owners=owners, timings=timings, width=4)
+                                   world=world, verbose=verbose, owners=owners, timings=timings, width=4, select=(pt, st))
 
 
 def call_blocks(x, y, v, n, distance_in_px, octave_values, st, pt, verbose=True, rank=0, world=1, device=None,

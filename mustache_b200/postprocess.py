@@ -208,3 +208,37 @@ def call_loops(n, dpx, start, mask_rows, mask_cols, mask_vals, rec_rows, rec_col
     for a, b in reps:
         loops.append([a + start, b + start, float(o_of([a], [b])[0]), float(so_of([a], [b])[0])])
     return loops, aux
+
+
+def call_loops_from_candidates(n, dpx, start, mask_rows, mask_cols, mask_vals, cand, intra=True):
+    """The rest of mustache.py:774-850 for one block when the device already did BH, the `o < pt` cut and the sparsity
+    filter (mb200_select_candidates): `cand` is one entry of ScaleSpaceEngine.candidates_batch().  Enrichment filter
+    (:816-828) from the block's mask pixels, clustering (:830-848) from the candidates' 3 x 3 neighbourhoods of `o` / `so`.
+    Same loops as call_loops() on the full record list."""
+    if len(mask_rows) < MIN_MASK_FOR_BH:                     # mustache.py:775: `len(pFound)` is the MASK size
+        return []
+    keep = cand["keep"]
+    x, y = cand["rows"][keep].astype(np.int64), cand["cols"][keep].astype(np.int64)
+    if len(x) == 0:
+        return []
+    o9, so9 = cand["o9"][keep], cand["so9"][keep]
+    if intra:
+        d = y - x
+        means = diagonal_means(np.asarray(mask_rows), np.asarray(mask_cols), np.asarray(mask_vals), dpx, d, intra)
+        mvec = np.array([means[int(k)] for k in d])
+        with np.errstate(invalid="ignore"):
+            passing = cand["cval"][keep] > 2 * mvec
+        if passing.sum() == 0:
+            return []
+        x, y, o9, so9 = x[passing], y[passing], o9[passing], so9[passing]
+    o_at, so_at = {}, {}
+    for a, b, ov, sv in zip(x.tolist(), y.tolist(), o9, so9):
+        for k in range(9):
+            key = (a + k // 3 - 1, b + k % 3 - 1)
+            o_at[key] = ov[k]
+            so_at[key] = sv[k]
+
+    def o_of(r, c):
+        return np.array([o_at[(int(a), int(b))] for a, b in zip(r, c)])
+    reps = cluster_representatives(x, y, o_of)
+    return [[a + start, b + start, float(o_at[(a, b)]), float(so_at[(a, b)])] for a, b in reps]

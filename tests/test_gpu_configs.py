@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from mustache_b200 import blockrun, normalize, synth as gen, tiler
+from mustache_b200.fdr import fdr_bh
 from mustache_b200 import mustache as mm
 from tests import synth
 from tests.test_gpu_e2e import FDR_TOL, _read_tsv
@@ -58,9 +59,13 @@ def test_config2_tile_matches_reference_run(eng):
     fits = eng.fits(0)                                                          # expon.fit of the 36 scored levels (mustache.py:755)
     assert np.array_equal(fits["loc"], z["fits"][:, 0])
     assert np.abs(fits["scale"] / z["fits"][:, 1] - 1).max() <= 1e-13
-    # and the loops mustache() returned for the tile (post-processing on 1.3 M records)
-    loops, _ = mm.postprocess.call_loops(n, dpx, 0, *gen.band_to_coo(band, n), rec["rows"], rec["cols"], rec["p"], rec["sigma"],
-                                         0.88, 0.1)
+    # and the loops mustache() returned for the tile: BH over 1.34 M p-values, o < pt and the sparsity filter on the
+    # device (mb200_select_candidates), enrichment filter and clustering on the host from the selected candidates
+    eng.select_candidates(0.1, 0.88)
+    cand = eng.candidates_batch()[0]
+    assert 0 < len(cand["rows"]) < rec["n_found"] // 20
+    assert np.array_equal(eng.q_values(0), fdr_bh(rec["p"]))       # same IEEE operations as the host formula
+    loops = mm.postprocess.call_loops_from_candidates(n, dpx, 0, *gen.band_to_coo(band, n), cand)
     got, ref = np.array(sorted(loops), float).reshape(-1, 4), z["loops"][np.lexsort((z["loops"][:, 1], z["loops"][:, 0]))]
     assert got.shape == ref.shape and np.array_equal(got[:, [0, 1, 3]], ref[:, [0, 1, 3]])
     assert np.abs(got[:, 2] - ref[:, 2]).max() <= FDR_TOL
@@ -281,3 +286,60 @@ def test_batched_coo_upload_equals_per_block(eng):
     assert ref[0]["n_found"] == 0 and ref[2]["n_found"] == 0 and ref[1]["n_found"] > 100
     for a, b in zip(ref, got):
         _equal_records(a, b)
+
+
+def _host_candidates(n, dpx, mask, rec, pt, st):
+    """What mb200_select_candidates must deliver, derived on the host from the full record list with the product's
+    (reference-pinned) sparse post-processing pieces."""
+    pp = mm.postprocess
+    mr, mc, mv = mask
+    index = pp.MaskIndex(mr, mc, n)
+    q = fdr_bh(rec["p"])
+    sel = q < pt
+    x, y, sg = rec["rows"][sel].astype(np.int64), rec["cols"][sel].astype(np.int64), rec["sigma"][sel]
+    keep = pp.sparsity_filter(index, x, y, sg, st)
+    pos = index.lookup(rec["rows"], rec["cols"])
+    o_mask, s_mask = np.full(index.keys.size, 2.0), np.ones(index.keys.size)
+    o_mask[pos], s_mask[pos] = q, rec["sigma"]
+
+    def dense(vals, r, c):
+        ok = (r >= 0) & (r < n) & (c >= 0) & (c < n)
+        p_ = index.lookup(np.where(ok, r, 0), np.where(ok, c, 0))
+        return np.where(ok & (p_ >= 0), vals[np.maximum(p_, 0)], 1.0)
+    dr, dc = np.repeat([-1, 0, 1], 3), np.tile([-1, 0, 1], 3)
+    o9 = np.stack([dense(o_mask, x + a, y + b) for a, b in zip(dr, dc)], axis=1).reshape(-1, 9)
+    so9 = np.stack([dense(s_mask, x + a, y + b) for a, b in zip(dr, dc)], axis=1).reshape(-1, 9)
+    d = y - x
+    cval = np.where((d <= 4) | (d >= dpx + 1), 2.0, mv[np.maximum(index.lookup(x, y), 0)])
+    return dict(rows=x, cols=y, q=q[sel], sigma=sg, keep=keep, cval=cval, o9=o9, so9=so9)
+
+
+@pytest.mark.parametrize("octs,pt,st", [([1.6, 3.2], 0.3, 0.6), ([1.6, 3.2, 6.4, 12.8], 0.8, 0.3)])
+def test_device_candidates_equal_host_selection(eng, octs, pt, st):
+    """BH, o < pt, sparsity windows (incl. the negative-slice and clipped-window quirks near the tile edges) and the 3 x 3
+    neighbourhoods of o / so: device vs the host's sparse post-processing on the same records, field for field."""
+    n, dpx = 400, 150
+    tiles = [gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=170 + b, blob_seed=180 + b, nblobs=25, missing=0.05 + 0.2 * b), n)
+             for b in range(3)]
+    _set(eng, octs)
+    masks = []
+    for t in tiles:
+        r, c = np.nonzero(np.triu(t, 4))
+        masks.append((r, c, t[r, c]))
+    eng.configure(n, dpx, 3)
+    eng.upload_coo_batch(0, *blockrun.concat_coo(masks))
+    eng.run()
+    recs = eng.records_batch()
+    eng.select_candidates(pt, st)
+    cands = eng.candidates_batch()
+    for b in range(3):
+        assert np.array_equal(eng.q_values(b), fdr_bh(recs[b]["p"]))
+        ref = _host_candidates(n, dpx, masks[b], recs[b], pt, st)
+        got = cands[b]
+        assert len(ref["rows"]) > 20 and ref["keep"].any() and not ref["keep"].all()
+        for k in ("rows", "cols", "q", "sigma", "keep", "cval", "o9", "so9"):
+            assert np.array_equal(got[k], ref[k]), (b, k)
+    # candidate capacity overflow: the fetch re-runs the selection with room for every record
+    eng.select_candidates(pt, st, candidate_fraction=1e-9)
+    small = eng.candidates_batch()
+    assert all(np.array_equal(small[b]["rows"], cands[b]["rows"]) for b in range(3))

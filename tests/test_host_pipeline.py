@@ -198,3 +198,31 @@ def test_block_slicer_equals_block_coo():
     a = tiler.block_coo(xs, y, v, 130, 390)
     b = sl2.block(130, 390)
     assert all(np.array_equal(p, q) for p, q in zip(a, b))
+
+
+@pytest.mark.parametrize("seed,n,dpx,missing,st,pt", [(101, 240, 90, 0.05, 0.6, 0.3), (102, 260, 300, 0.25, 0.4, 0.5),
+                                                       (103, 300, 120, 0.4, 0.2, 0.8)])
+def test_candidate_postprocess_equals_record_postprocess(seed, n, dpx, missing, st, pt):
+    """The split the product uses (device: BH, o < pt, sparsity, 3 x 3 neighbourhoods; host: enrichment + clustering from
+    those candidates, postprocess.call_loops_from_candidates) gives the loops of the all-host path on the full record
+    list (postprocess.call_loops, itself pinned to the dense oracle and the reference dumps above).  The device half is
+    stood in for by its dense restatement on the oracle (tests/test_sharded_blocks.py:OracleEngine.candidates_batch)."""
+    from tests.test_sharded_blocks import OracleEngine
+    c = synth.make_tile(n=n, dpx=dpx, seed=seed, blob_seed=seed + 50, nblobs=14, missing=missing)
+    r, cc = np.nonzero(np.triu(c, 4))
+    old = postprocess.MIN_MASK_FOR_BH
+    postprocess.MIN_MASK_FOR_BH = 100
+    try:
+        eng = OracleEngine()
+        eng.set_octaves([1.6, 3.2])
+        eng.configure(n, dpx, 1)
+        eng.upload_coo(0, r, cc, c[r, cc])
+        eng.run()
+        rec = eng.records_batch()[0]
+        eng.select_candidates(pt, st)
+        cand = eng.candidates_batch()[0]
+        a, _ = postprocess.call_loops(n, dpx, 7, r, cc, c[r, cc], rec["rows"], rec["cols"], rec["p"], rec["sigma"], st, pt)
+        b = postprocess.call_loops_from_candidates(n, dpx, 7, r, cc, c[r, cc], cand)
+    finally:
+        postprocess.MIN_MASK_FOR_BH = old
+    assert len(a) > 0 and a == b

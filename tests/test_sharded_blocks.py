@@ -67,6 +67,52 @@ class OracleEngine:
         return dict(rows=e.astype(np.int32), cols=e.astype(np.int32), v=e, p=e, score_id=e.astype(np.int32), sigma=e, pair=e,
                     nz_count=nz_count, n_found=0)
 
+    def select_candidates(self, pt, st, candidate_fraction=-1.0):
+        self.post = (pt, st)
+
+    def candidates_batch(self):
+        """What mb200_select_candidates + mb200_fetch_candidates deliver, restated densely on the oracle's output
+        (mustache.py:774-811 literally: BH, o < pt, numpy-slice sparsity windows, dense o / so neighbourhoods)."""
+        from mustache_b200.engine import EngineError
+        from oracle import postprocess as opost
+        from oracle import scalespace as osc
+        if self.capacity_errors > 0:
+            self.capacity_errors -= 1
+            raise EngineError(-3, "block 0 produced too many records")
+        pt, st = self.post
+        out = []
+        for b in range(self.nblocks):
+            c = self.tiles[b]
+            res = osc.scale_space(c, self.dpx, self.octs, use_scipy=True)
+            if res["skipped"]:
+                e = np.zeros(0)
+                out.append(dict(rows=e.astype(np.int32), cols=e.astype(np.int32), q=e, sigma=e, cval=e, keep=e.astype(bool),
+                                o9=np.zeros((0, 9)), so9=np.zeros((0, 9)), nz_count=res["nz_count"], n_found=0))
+                continue
+            nz, filled = osc.mask_and_fill(c, self.dpx)
+            found = res["p"] != 2
+            p_all = res["p"].copy()
+            p_all[found] = opost.bh_statsmodels_form(res["p"][found])
+            n = c.shape[0]
+            o, so = np.ones((n + 2, n + 2)), np.ones((n + 2, n + 2))          # one-pixel apron of "off the tile" = 1
+            o[1:-1, 1:-1][nz] = p_all
+            so[1:-1, 1:-1][nz] = res["scale"]
+            sel = found & (p_all < pt)
+            x, y, sc = res["rows"][sel], res["cols"][sel], res["scale"][sel]
+            keep = x != 0
+            for i in range(len(x)):
+                s = int(np.ceil(sc[i]))
+                c1 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
+                s *= 2
+                c2 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
+                if c1 < st or c2 < 0.6:
+                    keep[i] = False
+            o9 = np.array([o[a:a + 3, bb:bb + 3].ravel() for a, bb in zip(x, y)]).reshape(-1, 9)
+            so9 = np.array([so[a:a + 3, bb:bb + 3].ravel() for a, bb in zip(x, y)]).reshape(-1, 9)
+            out.append(dict(rows=x.astype(np.int32), cols=y.astype(np.int32), q=p_all[sel], sigma=sc, cval=filled[x, y], keep=keep,
+                            o9=o9, so9=so9, nz_count=res["nz_count"], n_found=int(found.sum())))
+        return out
+
     def records_batch(self, sort=True, pair=False, pinned=True):
         from mustache_b200.engine import EngineError
         from oracle import scalespace as osc

@@ -82,6 +82,24 @@ def fp64_instr_per_bin(octaves, dedupe=True):
     return reference, executed
 
 
+def fp64_instr_per_bin_fma(octaves):
+    """Executed FP64 instructions per contact-bin in the opt-in fast mode: a fused multiply-add per tap, i.e. R*(n+1)+n per
+    axis-0 group of n steps and 2R+1 per axis-1 output."""
+    from mustache_b200 import ladder
+    radii = sorted(s.radius for s in ladder.build_program(octaves).steps)
+    gmax, n = 5, len(radii)
+    best = [0] * (n + 1)                                  # the grouping is the exact mode's (mb_engine.cu:plan_kv)
+    take = [1] * (n + 1)
+    for i in range(n - 1, -1, -1):
+        best[i], take[i] = min((radii[i + c - 1] * (2 * c + 1) + c + best[i + c], c) for c in range(1, gmax + 1) if i + c <= n)
+    kv, i = 0, 0
+    while i < n:
+        c = take[i]
+        kv += radii[i + c - 1] * (c + 1) + c
+        i += c
+    return kv + sum(2 * r + 1 for r in radii)
+
+
 def load_traffic():
     """DRAM bytes per launch of the kernels from the committed `ncu --set full` captures (profiles/traffic_r02.json, else
     round 1's), keyed by config name."""
@@ -483,6 +501,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 strong-scaling object of multi-GPU lines")
     ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--no-fast", action="store_true", help="skip the extra device-resident measurement in the opt-in FMA mode")
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
     args = ap.parse_args()
     if args.config == "norm":
@@ -537,6 +556,11 @@ def main():
             print(json.dumps({"device_only": True, "ms_per_step": m["step_ms"], "value": m["value"],
                               "phases_ms_per_step": m["phases"]}))
         return
+    fastm = None
+    if not args.no_fast and world == 1:
+        eng.set_arithmetic(True)
+        fastm = measure(h, eng, cfg, args.config, args.steps, args.warmup, device_only=True)
+        eng.set_arithmetic(False)
     c4 = None
     if not strong and not args.no_config4:
         c4m = measure(h, eng, CONFIGS["4"], "4", max(3, args.steps), 3)
@@ -565,6 +589,16 @@ def main():
            "post_ms_per_step": m["post_ms"], "phases_ms_per_step": m["phases"],
            "wall_ms_per_step": m["wall_step_ms"],
            "roofline": roofline(cfg, args.config, m, peak, bool(peaks))}
+    if fastm is not None:
+        fi = fp64_instr_per_bin_fma(cfg["octaves"])
+        hot = (fastm["phases"]["kv_ms"] + fastm["phases"]["kh_ms"]) * 1e-3
+        out["fast_mode"] = {"note": "opt-in mb200_set_arithmetic(1) / MUSTACHE_FAST=1: one FMA per tap instead of scipy's multiply-then-add; "
+                                    "not the reference's arithmetic, gated by tests/test_gpu_fast_mode.py on BASELINE's tolerance; "
+                                    "every other figure of this line is the exact mode",
+                            "ms_per_step": fastm["step_ms"], "value": fastm["value"], "phases_ms_per_step": fastm["phases"],
+                            "hbm_frac": fastm["bins_rank"] * BYTES_PER_BIN_PER_OCTAVE * len(cfg["octaves"]) / (fastm["dev_ms"] * 1e-3) / 1e9 / peak,
+                            "fp64": {"instr_per_bin_executed": fi, "achieved_instr_per_s": fi * fastm["bins_rank"] / hot,
+                                     "frac": fi * fastm["bins_rank"] / hot / FP64_INSTR_PEAK}}
     if c4 is not None:
         out["config4"] = c4
     if not args.no_cpu_baseline and world == 1:

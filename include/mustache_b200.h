@@ -126,6 +126,13 @@ MB200_API int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t*
 MB200_API int mb200_fetch_q(mb200_engine* e, int block, int64_t capacity, double* q, int64_t* n_out);
 MB200_API int mb200_last_post_ms(mb200_engine* e, float* ms);
 
+/* Arithmetic of the two Gaussian passes.  0 (default): the reference's own -- scipy's correlate1d multiplies, then adds
+ * (two roundings per tap), which makes every Gaussian bit-identical to scipy.ndimage.gaussian_filter.  1: opt-in fast mode,
+ * one fused multiply-add per tap (2R+1 instead of 3R+1 FP64 instructions per output); Gaussians then differ from scipy's in
+ * the last bits (~1e-16 relative), which BASELINE's tolerance (coordinates and scale exact, p within 1e-6) absorbs on every
+ * golden input (tests/test_gpu_fast_mode.py) but which is NOT the reference's arithmetic.  Takes effect at the next run. */
+MB200_API int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add);
+
 /* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The
  * reference's analogue is `-p`, the number of block processes alive at a time (mustache.py:931-934).  Takes effect at the
  * next mb200_configure. */

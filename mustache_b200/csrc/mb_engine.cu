@@ -68,6 +68,7 @@ struct mb200_engine {
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
     long long plane_v = 0, plane_l = 0;
+    int fast = 0;                    // mb200_set_arithmetic: 0 = the reference's multiply-then-add, 1 = fused multiply-add
     int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
     int ndiff = 0;                   // MB_FLAG_DIFFREF steps of the difference chain
     // packed view of the batch's records (mb200_pack_records): block b occupies [pk_off[b], pk_off[b+1])
@@ -259,14 +260,19 @@ int set_smem_limits(mb200_engine* e) {
     if (kvb > 227 * 1024 || khb > 227 * 1024)
         return fail(e, MB200_ERR_ARG, "radius %d needs %zu / %zu bytes of shared memory (> 227 KB)", e->prog.rmax, kvb, khb);
     if (kvb != e->kv_smem_set) {
-        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
-        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
         e->kv_smem_set = kvb;
     }
     if (khb != e->kh_smem_set) {
-        CU(e, cudaFuncSetAttribute(kh_kernel<KH_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
-        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
-        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_MAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DIFF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DEBUG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_MAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DIFF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
+        CU(e, cudaFuncSetAttribute(kh_kernel<KH_DEBUG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
         e->kh_smem_set = khb;
     }
     const size_t ksb = ks_smem_bytes(e->prog.n_scored);
@@ -284,18 +290,28 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     const int th = kv_tile_rows(e);
     const size_t kvb = kv_smem_bytes(pg.rmax, th), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
     const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
-    if (th == KV_TH_WIDE)
-        kv_kernel<KV_TH_WIDE><<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
-    else
-        kv_kernel<KV_TH_NARROW><<<kv_grid(e, nblk), KV_THREADS, kvb, e->stream>>>(program ? e->dkvplan : e->kvplan, g);
+    const KvPlan& kp = program ? e->dkvplan : e->kvplan;
+    const dim3 gv = kv_grid(e, nblk), gh = kh_grid(e, nblk);
+    if (e->fast) {
+        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+        else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+    } else {
+        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, false><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+        else kv_kernel<KV_TH_NARROW, false><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+    }
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
-    if (g.dout != nullptr)                          // difference stack: only the DIFFREF DoGs are kept
-        kh_kernel<KH_DIFF><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
-    else if (g.dbgG != nullptr || g.dbgL != nullptr)
-        kh_kernel<KH_DEBUG><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
-    else
-        kh_kernel<KH_MAIN><<<kh_grid(e, nblk), KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    const int mode = g.dout != nullptr ? KH_DIFF : ((g.dbgG != nullptr || g.dbgL != nullptr) ? KH_DEBUG : KH_MAIN);
+    // KH_DIFF: difference stack, only the DIFFREF DoGs are kept; KH_DEBUG: dense dumps of mb200_debug_level
+    if (e->fast) {
+        if (mode == KH_DIFF) kh_kernel<KH_DIFF, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        else kh_kernel<KH_MAIN, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    } else {
+        if (mode == KH_DIFF) kh_kernel<KH_DIFF, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        else kh_kernel<KH_MAIN, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+    }
     CU(e, cudaGetLastError());
     if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
     e->launches += 2;
@@ -857,6 +873,12 @@ int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* r
     CU(e, cudaMemcpyAsync(v, (double*)e->rec_v.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaMemcpyAsync(p, (double*)e->rec_p.p + o, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    return MB200_OK;
+}
+
+int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add) {
+    if (!e || fused_multiply_add < 0 || fused_multiply_add > 1) return MB200_ERR_ARG;
+    e->fast = fused_multiply_add;
     return MB200_OK;
 }
 

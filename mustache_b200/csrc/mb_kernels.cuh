@@ -215,9 +215,16 @@ __device__ __forceinline__ double filled_at(const MbGeom& g, const double* __res
 // first trip enters the unrolled body at tap u0 = (K - R % K) % K (Duff's device) with the windows loaded in the state
 // u0 taps would have left them in, so there is no remainder loop and no padded tap.
 // ---------------------------------------------------------------------------------------------------------------
+// acc + t * w: the reference's arithmetic (scipy multiplies, then adds: two roundings) or, in the opt-in fast mode
+// (mb200_set_arithmetic), one fused multiply-add (one rounding, one FP64 instruction instead of two)
+template <bool FAST>
+__device__ __forceinline__ double mb_mac(double acc, double t, double w) {
+    return FAST ? __fma_rn(t, w, acc) : __dadd_rn(acc, __dmul_rn(t, w));
+}
+
 // Radii below K never complete a trip of the unrolled loop; for them the whole support (K + 2R values) fits in
 // registers and the sum is written out with compile-time indices: no window rotation, no loop, no entry switch.
-template <int R, int K, int STRIDE>
+template <int R, int K, int STRIDE, bool FAST>
 __device__ __forceinline__ void conv_small(const double* __restrict__ ctr, const double* __restrict__ tp, double (&acc)[K]) {
     double x[K + 2 * R];
 #pragma unroll
@@ -229,23 +236,23 @@ __device__ __forceinline__ void conv_small(const double* __restrict__ ctr, const
     for (int j = R; j >= 1; --j) {
         const double w = tp[j];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], __dmul_rn(__dadd_rn(x[k + R - j], x[k + R + j]), w));
+        for (int k = 0; k < K; ++k) acc[k] = mb_mac<FAST>(acc[k], __dadd_rn(x[k + R - j], x[k + R + j]), w);
     }
 }
 
-template <int K, int STRIDE>
+template <int K, int STRIDE, bool FAST>
 __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const int R, const double* __restrict__ tp,
                                            double (&acc)[K]) {
     static_assert(K == 8, "the unrolled body below is written for K = 8");
     if (R < K) {
         switch (R) {
-            case 1: conv_small<1, K, STRIDE>(ctr, tp, acc); break;
-            case 2: conv_small<2, K, STRIDE>(ctr, tp, acc); break;
-            case 3: conv_small<3, K, STRIDE>(ctr, tp, acc); break;
-            case 4: conv_small<4, K, STRIDE>(ctr, tp, acc); break;
-            case 5: conv_small<5, K, STRIDE>(ctr, tp, acc); break;
-            case 6: conv_small<6, K, STRIDE>(ctr, tp, acc); break;
-            default: conv_small<7, K, STRIDE>(ctr, tp, acc); break;
+            case 1: conv_small<1, K, STRIDE, FAST>(ctr, tp, acc); break;
+            case 2: conv_small<2, K, STRIDE, FAST>(ctr, tp, acc); break;
+            case 3: conv_small<3, K, STRIDE, FAST>(ctr, tp, acc); break;
+            case 4: conv_small<4, K, STRIDE, FAST>(ctr, tp, acc); break;
+            case 5: conv_small<5, K, STRIDE, FAST>(ctr, tp, acc); break;
+            case 6: conv_small<6, K, STRIDE, FAST>(ctr, tp, acc); break;
+            default: conv_small<7, K, STRIDE, FAST>(ctr, tp, acc); break;
         }
         return;
     }
@@ -282,8 +289,12 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
         const double w = wj[-(u)];                                                                             \
         double t[K];                                                                                           \
         _Pragma("unroll") for (int k = 0; k < K; ++k) t[k] = __dadd_rn(pl[(k + u) % K], pr[(k - u + K) % K]);  \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);                               \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);                        \
+        if (FAST) {                                                                                            \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) acc[k] = __fma_rn(t[k], w, acc[k]);                  \
+        } else {                                                                                               \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) t[k] = __dmul_rn(t[k], w);                           \
+            _Pragma("unroll") for (int k = 0; k < K; ++k) acc[k] = __dadd_rn(acc[k], t[k]);                    \
+        }                                                                                                      \
         pl[u % K] = xl[(u) * STRIDE];                                                                          \
         pr[(K - 1 - u) % K] = xr[-(u) * STRIDE];                                                               \
     }
@@ -313,7 +324,7 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
 // bit-identical to scipy's; the FP64 instruction count per output drops from sum(3R+1) = 2415 to 1987 for 4 octaves
 // (532 -> 431 for 2).  The tap loop has no step-dependent control flow: four taps per trip from windows loaded once.
 // ---------------------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool FAST>
 __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const double* __restrict__ tp, const int rtop,
                                          const int* __restrict__ steps, double* __restrict__ vrow, const long long step_stride,
                                          const int kstride, const unsigned vmask) {
@@ -346,7 +357,7 @@ __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const d
                 for (int s = 0; s < N; ++s) {
                     const double w = pw[s - u * N];
 #pragma unroll
-                    for (int k = 0; k < KV_K; ++k) acc[s][k] = __dadd_rn(acc[s][k], __dmul_rn(t[k], w));
+                    for (int k = 0; k < KV_K; ++k) acc[s][k] = mb_mac<FAST>(acc[s][k], t[k], w);
                 }
             }
         }
@@ -365,7 +376,7 @@ __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const d
     }
 }
 
-template <int KV_TH>
+template <int KV_TH, bool FAST>
 __global__ void __launch_bounds__(KV_THREADS, 2)
 kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     extern __shared__ double smem[];
@@ -432,11 +443,11 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
             if (dmax_w < 2 - gr.rmax || dmin_w > g.dhi + 2 + gr.rmax) continue;     // warp-uniform: nobody reads these
             const double* tp = plan.tapsT + gr.tap_off;
             switch (gr.n) {
-                case 1: kv_group<1>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 2: kv_group<2>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 3: kv_group<3>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 4: kv_group<4>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                default: kv_group<5>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 1: kv_group<1, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 2: kv_group<2, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 3: kv_group<3, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                case 4: kv_group<4, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                default: kv_group<5, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
             }
         }
     }
@@ -527,7 +538,7 @@ __device__ __forceinline__ void tma_prefetch_box3d(const CUtensorMap* map, int x
 //       KH_DEBUG KH_MAIN plus the dense dumps of mb200_debug_level
 constexpr int KH_MAIN = 0, KH_DIFF = 1, KH_DEBUG = 2;
 
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(KH_THREADS, KH_CTAS)
 kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
     extern __shared__ __align__(128) double smem[];
@@ -657,7 +668,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             __syncthreads();
         }
         if (chunk_live && row_in) {
-            conv_slide<KH_K, 1>(vst + lane * bw + shift + c0 + R, R, prog.taps + prog.st[s].tap_off, gnew);
+            conv_slide<KH_K, 1, FAST>(vst + lane * bw + shift + c0 + R, R, prog.taps + prog.st[s].tap_off, gnew);
         } else {
 #pragma unroll
             for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;

@@ -33,6 +33,8 @@ def get_engine(device=None):
         device = int(os.environ.get("MUSTACHE_GPU", os.environ.get("LOCAL_RANK", "0")))
     if device not in _ENGINES:
         _ENGINES[device] = ScaleSpaceEngine(device)
+        if os.environ.get("MUSTACHE_FAST", "0") == "1":          # opt-in FMA arithmetic (include/mustache_b200.h)
+            _ENGINES[device].set_arithmetic(True)
     return _ENGINES[device]
 
 

@@ -117,7 +117,7 @@ MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, voi
  * What leaves the GPU is one entry per SELECTED pixel: block, tile row / column, q (FDR), sigma (Scales), flags (bit 0: passed
  * the sparsity filter), cval (its value in the 2-filled tile, for the enrichment filter :822-828) and the 3 x 3 neighbourhoods
  * of the dense `o` and `so` matrices (:789-795; row-major, 1 off the mask, 2 / 1 on the mask but never updated), which is all
- * the clustering step (:830-848) reads.  candidate_fraction: capacity as a fraction of the record capacity (<= 0: 1/16);
+ * the clustering step (:830-848) reads.  candidate_fraction: capacity as a fraction of the batch's found records (<= 0: 1/16);
  * mb200_fetch_candidates returns MB200_ERR_CAPACITY when it was exceeded.  Order of the entries is unspecified.
  * mb200_fetch_q: q of every record of a block in the order of mb200_fetch_records (parity hook). */
 MB200_API int mb200_select_candidates(mb200_engine* e, double pt, double st, double candidate_fraction);

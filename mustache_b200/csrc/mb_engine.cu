@@ -49,7 +49,7 @@ struct mb200_engine {
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
         nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist,
-        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count;
+        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot;
     long long cand_cap = 0;
     bool post_done = false;
     cudaEvent_t ev_post0 = nullptr, ev_post1 = nullptr;
@@ -349,8 +349,10 @@ int refresh_counts(mb200_engine* e) {
 int radix_sort(mb200_engine* e, const RsSegments& sg, int nseg, long long max_len, int key_bits, cudaStream_t sq) {
     if (nseg < 1 || max_len < 1) return MB200_OK;
     const int ntiles = (int)((max_len + RS_TILE - 1) / RS_TILE);
-    int st = ensure(e, e->sort_hist, (size_t)nseg * RS_RADIX * ntiles * sizeof(unsigned));
+    int st = ensure(e, e->sort_hist, (size_t)nseg * RS_RADIX * (ntiles + 1) * sizeof(unsigned));
     if (st) return st;
+    unsigned* hist = (unsigned*)e->sort_hist.p;
+    unsigned* tot = hist + (size_t)nseg * RS_RADIX * ntiles;
     int passes = (key_bits + RS_BITS - 1) / RS_BITS;
     passes += passes & 1;
     for (int p = 0; p < passes; ++p) {
@@ -358,13 +360,13 @@ int radix_sort(mb200_engine* e, const RsSegments& sg, int nseg, long long max_le
         unsigned long long* kout = (unsigned long long*)e->sort_keys[(p & 1) ^ 1].p;
         const unsigned* vin = (const unsigned*)e->sort_vals[p & 1].p;
         unsigned* vout = (unsigned*)e->sort_vals[(p & 1) ^ 1].p;
-        rs_hist_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, sg, p * RS_BITS, ntiles, (unsigned*)e->sort_hist.p);
-        rs_scan_kernel<<<nseg, 1024, 0, sq>>>((unsigned*)e->sort_hist.p, ntiles);
-        rs_scatter_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, vin, kout, vout, sg, p * RS_BITS, ntiles,
-                                                                      (const unsigned*)e->sort_hist.p);
+        rs_hist_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, sg, p * RS_BITS, ntiles, hist);
+        rs_scan_tiles_kernel<<<dim3(RS_RADIX, nseg), 256, 0, sq>>>(hist, ntiles, tot);
+        rs_scan_digits_kernel<<<nseg, RS_RADIX, 0, sq>>>(tot);
+        rs_scatter_kernel<<<dim3(ntiles, nseg), RS_THREADS, 0, sq>>>(kin, vin, kout, vout, sg, p * RS_BITS, ntiles, hist, tot);
         CU(e, cudaGetLastError());
     }
-    e->launches += 3 * passes;
+    e->launches += 4 * passes;
     return MB200_OK;
 }
 
@@ -420,7 +422,7 @@ void mb200_destroy(mb200_engine* e) {
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
                      &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
                      &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
-                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count};
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -996,17 +998,28 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     const int B = e->nblocks;
     const size_t slots = (size_t)B * e->rec_cap;
     cudaStream_t sq = e->stream;
+    // one small device -> host read of the record counters: the sort and BH grids are sized by the fullest block, not by
+    // the capacity, and an overflow or a non-finite tile is reported before any work is queued
+    if ((st = refresh_counts(e))) return st;
+    long long max_found = 1, total_found = 0;
+    for (int b = 0; b < B; ++b) {
+        if (e->h_nonfinite[b]) return fail(e, MB200_ERR_NONFINITE, "block %d holds non-finite values", b);
+        if ((long long)e->h_rec[b] > e->rec_cap)
+            return fail(e, MB200_ERR_CAPACITY, "block %d produced %llu records, capacity %lld", b, e->h_rec[b], e->rec_cap);
+        max_found = std::max<long long>(max_found, (long long)e->h_rec[b]);
+        total_found += (long long)e->h_rec[b];
+    }
     for (int k = 0; k < 2; ++k) {
         if ((st = ensure(e, e->sort_keys[k], slots * sizeof(unsigned long long)))) return st;
         if ((st = ensure(e, e->sort_vals[k], slots * sizeof(unsigned)))) return st;
     }
     if ((st = ensure(e, e->rec_q, slots * sizeof(double)))) return st;
-    const int ntiles = (int)((e->rec_cap + RS_TILE - 1) / RS_TILE);
+    const int ntiles = (int)((max_found + RS_TILE - 1) / RS_TILE);
     if ((st = ensure(e, e->bh_tmin, (size_t)B * ntiles * sizeof(double)))) return st;
     const size_t tile = (size_t)e->n * e->wc;
     if ((st = ensure(e, e->slotmap, (size_t)B * tile * sizeof(int)))) return st;
     const double frac = candidate_fraction > 0 ? candidate_fraction : 1.0 / 16.0;
-    e->cand_cap = std::max<long long>(256, (long long)(frac * (double)slots));
+    e->cand_cap = std::max<long long>(16, (long long)(frac * (double)total_found) + 1);
     const size_t cc = (size_t)e->cand_cap;
     if ((st = ensure(e, e->cd_block, cc * sizeof(int)))) return st;
     if ((st = ensure(e, e->cd_row, cc * sizeof(int)))) return st;
@@ -1018,6 +1031,7 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     if ((st = ensure(e, e->cd_o9, cc * 9 * sizeof(double)))) return st;
     if ((st = ensure(e, e->cd_so9, cc * 9 * sizeof(double)))) return st;
     if ((st = ensure(e, e->cd_count, sizeof(unsigned long long)))) return st;
+    if ((st = ensure(e, e->cd_slot, cc * sizeof(int)))) return st;
     CU(e, cudaEventRecord(e->ev_post0, sq));
     const unsigned long long* cnt = (const unsigned long long*)e->rec_count.p;
     const int gx = B >= 8 ? 16 : 148 * 2;
@@ -1025,7 +1039,7 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
                                                 (unsigned*)e->sort_vals[0].p);
     CU(e, cudaGetLastError());
     RsSegments sg = {nullptr, cnt, e->rec_cap, e->rec_cap};
-    if ((st = radix_sort(e, sg, B, e->rec_cap, 64, sq))) return st;
+    if ((st = radix_sort(e, sg, B, max_found, 64, sq))) return st;
     const unsigned long long* keys = (const unsigned long long*)e->sort_keys[0].p;
     bh_tilemin_kernel<<<dim3(ntiles, B), RS_THREADS, 0, sq>>>(keys, cnt, e->rec_cap, ntiles, (double*)e->bh_tmin.p);
     bh_suffix_kernel<<<(B + 63) / 64, 64, 0, sq>>>(B, ntiles, (double*)e->bh_tmin.p);
@@ -1039,13 +1053,14 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     PostOut po = {(int*)e->cd_block.p, (int*)e->cd_row.p, (int*)e->cd_col.p, (int*)e->cd_flags.p, (double*)e->cd_q.p,
                   (double*)e->cd_sigma.p, (double*)e->cd_cval.p, (double*)e->cd_o9.p, (double*)e->cd_so9.p,
                   (unsigned long long*)e->cd_count.p, e->cand_cap};
-    post_candidates_kernel<<<dim3(B >= 8 ? 32 : 148 * 4, B), 256, 0, sq>>>(
-        cnt, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, (const double*)e->rec_q.p, (const double*)e->rec_sigma.p,
-        raw_slot(e, e->slot_run), (const int*)e->slotmap.p, e->n, e->wc, e->dhi, e->dpx, pt, st_thr, po);
+    post_select_kernel<<<dim3(gx, B), 256, 0, sq>>>(cnt, e->rec_cap, (const double*)e->rec_q.p, pt, po, (int*)e->cd_slot.p);
+    post_candidates_kernel<<<148 * 4, 256, 0, sq>>>(
+        e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, (const double*)e->rec_q.p, (const double*)e->rec_sigma.p,
+        raw_slot(e, e->slot_run), (const int*)e->slotmap.p, (const int*)e->cd_slot.p, e->n, e->wc, e->dhi, e->dpx, st_thr, po);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_post1, sq));
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));          // the candidate kernel reads the tile slot too
-    e->launches += 6;
+    e->launches += 7;
     e->post_done = true;
     return MB200_OK;
 }

@@ -157,22 +157,39 @@ __device__ __forceinline__ int post_window_count(const double* __restrict__ rawb
     return cnt;
 }
 
-// one warp per record: selection, sparsity filter, neighbourhood patches
+// selection o < pt (mustache.py:791), one thread per record: the selected records' (block, slot) go to the candidate list
 __global__ void __launch_bounds__(256)
-post_candidates_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const int* __restrict__ rec_row,
-                       const int* __restrict__ rec_col, const double* __restrict__ rec_q, const double* __restrict__ rec_sigma,
-                       const double* __restrict__ raw, const int* __restrict__ slot, int n, int wc, int dhi, int dpx, double pt,
-                       double st, PostOut out) {
+post_select_kernel(const unsigned long long* __restrict__ rec_count, long long rec_cap, const double* __restrict__ rec_q, double pt,
+                   PostOut out, int* __restrict__ cand_slot) {
     const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
     unsigned long long m = rec_count[b];
     if (m > (unsigned long long)rec_cap) m = rec_cap;
-    const double* rawb = raw + (size_t)b * n * wc;
-    const int* slotb = slot + (size_t)b * n * wc;
-    for (unsigned long long r = blockIdx.x * 8ULL + (threadIdx.x >> 5); r < m; r += (unsigned long long)gridDim.x * 8ULL) {
-        const size_t o = (size_t)b * rec_cap + r;
+    for (unsigned long long r = blockIdx.x * 256ULL + threadIdx.x; r < m; r += (unsigned long long)gridDim.x * 256ULL) {
+        if (rec_q[(size_t)b * rec_cap + r] < pt) {
+            const unsigned long long pos = atomicAdd(out.count, 1ULL);
+            if (pos < (unsigned long long)out.cap) {
+                out.block[pos] = b;
+                cand_slot[pos] = (int)r;
+            }
+        }
+    }
+}
+
+// one warp per selected record: sparsity filter, neighbourhood patches
+__global__ void __launch_bounds__(256)
+post_candidates_kernel(long long rec_cap, const int* __restrict__ rec_row, const int* __restrict__ rec_col,
+                       const double* __restrict__ rec_q, const double* __restrict__ rec_sigma, const double* __restrict__ raw,
+                       const int* __restrict__ slot, const int* __restrict__ cand_slot, int n, int wc, int dhi, int dpx, double st,
+                       PostOut out) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long total = *out.count;
+    if (total > (unsigned long long)out.cap) total = out.cap;
+    for (unsigned long long pos = blockIdx.x * 8ULL + (threadIdx.x >> 5); pos < total; pos += (unsigned long long)gridDim.x * 8ULL) {
+        const int b = out.block[pos];
+        const size_t o = (size_t)b * rec_cap + cand_slot[pos];
+        const double* rawb = raw + (size_t)b * n * wc;
+        const int* slotb = slot + (size_t)b * n * wc;
         const double q = rec_q[o];
-        if (!(q < pt)) continue;                                  // mustache.py:791: o < pt (warp-uniform)
         const int x = rec_row[o], y = rec_col[o];
         const double sg = rec_sigma[o];
         // sparsity filter (mustache.py:800-811)
@@ -187,12 +204,7 @@ post_candidates_kernel(const unsigned long long* __restrict__ rec_count, long lo
             const double c2 = (double)cnt2 / (double)((2 * s2 + 1) * (2 * s2 + 1));
             if (c1 < st || c2 < 0.6) keep = false;
         }
-        unsigned long long pos = 0;
-        if (lane == 0) pos = atomicAdd(out.count, 1ULL);
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (pos >= (unsigned long long)out.cap) continue;
         if (lane == 0) {
-            out.block[pos] = b;
             out.row[pos] = x;
             out.col[pos] = y;
             out.flags[pos] = keep ? 1 : 0;

@@ -2,8 +2,8 @@
 //   * Benjamini-Hochberg per block (mustache.py:778): the found p-values of every block sorted ascending
 //     (64-bit keys = bit patterns of the positive doubles, 8 passes of 8 bits, one segment per block);
 //   * normalize_sparse (mustache.py:632-633): the contacts grouped by diagonal in input order (one segment, keys = |y - x|).
-// One pass = three kernels: per-tile digit histograms, an exclusive scan over (digit, tile) per segment, and a stable
-// scatter.  Stability inside a tile comes from warp-ordered ranking: every warp owns a contiguous slice of the tile,
+// One pass = four short kernels: per-tile digit histograms, an exclusive scan over the tiles per digit, one over the
+// digits, and a stable scatter.  Stability inside a tile comes from warp-ordered ranking: every warp owns a contiguous slice of the tile,
 // walks it 32 keys at a time, and ranks equal digits with __match_any_sync in lane order.
 #pragma once
 #include <cstdint>
@@ -53,20 +53,23 @@ rs_hist_kernel(const unsigned long long* __restrict__ keys, RsSegments sg, int s
     hist[((size_t)s * RS_RADIX + threadIdx.x) * ntiles + tile] = h[threadIdx.x];
 }
 
-// exclusive scan of hist over (digit-major, tile-minor) per segment, in place.  One CTA per segment.
-__global__ void __launch_bounds__(1024)
-rs_scan_kernel(unsigned* __restrict__ hist, int ntiles) {
-    __shared__ unsigned warp_tot[32];
+// Exclusive scan of hist over (digit-major, tile-minor) per segment, in two parallel steps:
+//   rs_scan_tiles_kernel  grid (RS_RADIX, nseg): one CTA per digit scans that digit's counts over the tiles in place and
+//                         leaves the digit's total in tot[seg * RS_RADIX + digit];
+//   rs_scan_digits_kernel grid (nseg): exclusive scan of the RS_RADIX totals in place -> first position of every digit.
+// The scatter adds the two.
+__global__ void __launch_bounds__(256)
+rs_scan_tiles_kernel(unsigned* __restrict__ hist, int ntiles, unsigned* __restrict__ tot) {
+    __shared__ unsigned warp_tot[8];
     __shared__ unsigned carry_s;
-    const int s = blockIdx.x;
-    unsigned* h = hist + (size_t)s * RS_RADIX * ntiles;
-    const int total = RS_RADIX * ntiles;
+    const int dg = blockIdx.x, s = blockIdx.y;
+    unsigned* h = hist + ((size_t)s * RS_RADIX + dg) * ntiles;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < total; base += 1024) {
+    for (int base = 0; base < ntiles; base += 256) {
         const int i = base + threadIdx.x;
-        const unsigned v = i < total ? h[i] : 0u;
+        const unsigned v = i < ntiles ? h[i] : 0u;
         unsigned x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -75,29 +78,40 @@ rs_scan_kernel(unsigned* __restrict__ hist, int ntiles) {
         }
         if (lane == 31) warp_tot[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            unsigned w = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_tot[lane] = w;                         // inclusive totals of the warps
-        }
+        unsigned before = carry_s + (x - v);
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (i < ntiles) h[i] = before;
         __syncthreads();
-        const unsigned before = carry_s + (warp ? warp_tot[warp - 1] : 0u) + (x - v);
-        if (i < total) h[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = before + v;
+        if (threadIdx.x == 255) carry_s = before + v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) tot[(size_t)s * RS_RADIX + dg] = carry_s;
+}
+
+__global__ void __launch_bounds__(RS_RADIX)
+rs_scan_digits_kernel(unsigned* __restrict__ tot) {
+    __shared__ unsigned warp_tot[RS_RADIX / 32];
+    unsigned* t = tot + (size_t)blockIdx.x * RS_RADIX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned v = t[threadIdx.x];
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    unsigned before = x - v;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    t[threadIdx.x] = before;
 }
 
 // stable scatter of one pass: keys (and a 32-bit payload) from `in` to `out` inside their segment
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                   unsigned long long* __restrict__ keys_out, unsigned* __restrict__ vals_out, RsSegments sg, int shift,
-                  int ntiles, const unsigned* __restrict__ hist) {
+                  int ntiles, const unsigned* __restrict__ hist, const unsigned* __restrict__ tot) {
     __shared__ unsigned wh[RS_WARPS][RS_RADIX];            // per-warp digit counts, then the warp's base inside the tile
     const int s = blockIdx.y, tile = blockIdx.x;
     long long off, len;
@@ -130,7 +144,7 @@ rs_scatter_kernel(const unsigned long long* __restrict__ keys_in, const unsigned
     // exclusive scan over the warps per digit + the tile's global offset of that digit
     {
         const int dg = threadIdx.x;                         // RS_THREADS == RS_RADIX
-        unsigned run = hist[((size_t)s * RS_RADIX + dg) * ntiles + tile];
+        unsigned run = tot[(size_t)s * RS_RADIX + dg] + hist[((size_t)s * RS_RADIX + dg) * ntiles + tile];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const unsigned c = wh[w][dg];

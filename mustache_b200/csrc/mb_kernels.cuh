@@ -176,7 +176,7 @@ constexpr int KS_PREFETCH = MB_KS_PREFETCH;   // DoG levels beyond the ring that
 constexpr int KH_XP = KH_K + 1;        // pitch of the per-warp 32 x 8 transpose buffer (odd: lanes index rows)
 __host__ __device__ inline int kh_ring_doubles(int rmax) {
     const int widest = KH_TR * kh_vbuf_pitch(rmax);
-    const int half_sm = ((KH_CTAS == 2 ? 110 : 222) * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP - 2 * MB_MAX_STEPS;
+    const int half_sm = ((KH_CTAS == 2 ? 112 : 222) * 1024) / 8 - (KH_THREADS / 32) * KH_TR * KH_XP - 2 * MB_MAX_STEPS;
     return half_sm > 2 * widest ? half_sm : 2 * widest;
 }
 constexpr int KV_GUARD = 3;
@@ -815,6 +815,20 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     __syncthreads();
     const int n_levels = n_levels_s;
 
+    // Producer side: the DoG tile of the nl-th level of the stream goes into stage nl % D.  A stage is free once every
+    // warp has scored the level two after the one it holds; the warp whose release completes that (the last of the NW
+    // arrivals on the stage's `empty` barrier) issues the stage's next load itself, so nobody ever waits for a free stage.
+    auto issue = [&](int nl) {
+        const int st = nl % D;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
+        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.nblk + b, &full[st]);
+        if (KS_PREFETCH > 0 && nl + KS_PREFETCH < n_levels_s)       // the level that will take this stage's successor: into L2
+            tma_prefetch_box3d(&tm->l, x_first & ~1, i0, lvl_step[nl + KS_PREFETCH] * g.nblk + b);
+    };
+
+    if (threadIdx.x == 0)                                       // prologue: every stage starts loading (before the mask
+        for (int q = 0; q < D && q < n_levels; ++q) issue(q);   // reads below, so that the two latencies overlap)
+
     // mask bits of the 8 owned pixels (mustache.py:699: c != 0 and j - i >= 4, taken before the fills)
     unsigned mask = 0;
     if (row_scored) {
@@ -826,17 +840,6 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             }
         }
     }
-
-    // Producer side: the DoG tile of the nl-th level of the stream goes into stage nl % D.  A stage is free once every
-    // warp has scored the level two after the one it holds; the warp whose release completes that (the last of the NW
-    // arrivals on the stage's `empty` barrier) issues the stage's next load itself, so nobody ever waits for a free stage.
-    auto issue = [&](int nl) {
-        const int st = nl % D;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
-        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.nblk + b, &full[st]);
-        if (KS_PREFETCH > 0 && nl + KS_PREFETCH < n_levels_s)       // the level that will take this stage's successor: into L2
-            tma_prefetch_box3d(&tm->l, x_first & ~1, i0, lvl_step[nl + KS_PREFETCH] * g.nblk + b);
-    };
 
     double vbest[KS_K], lA[KS_K], lB[KS_K];
     unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
@@ -921,8 +924,6 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         e_cur = e_new;
     };
 
-    if (threadIdx.x == 0)                                       // prologue: every stage starts loading
-        for (int q = 0; q < D && q < n_levels; ++q) issue(q);
     for (int nl = 0; nl < n_levels; nl += 2) {
         level(lvl_step[nl], nl, lB, lA);        // even level: own values into lA
         if (nl + 1 < n_levels) level(lvl_step[nl + 1], nl + 1, lA, lB);

@@ -461,16 +461,18 @@ def roofline(cfg, name, m, peak, peaks_found):
     n_oct = len(cfg["octaves"])
     bytes_per_bin = BYTES_PER_BIN_PER_OCTAVE * n_oct
     ph = m["phases"]
-    kern = {"kv_kernel": ph["kv_ms"], "kh_kernel": ph["kh_ms"], "ks_kernel": ph["ks_ms"]}
+    fused = ph["ks_ms"] < 1e-3                          # khs_kernel: axis-1 pass, DoG and scoring in one kernel (2-octave chains)
+    khn = "khs_kernel" if fused else "kh_kernel"
+    kern = {"kv_kernel": ph["kv_ms"], khn: ph["kh_ms"], "ks_kernel": ph["ks_ms"]}
     dom = max(kern, key=kern.get)
     achieved = m["bins_rank"] * bytes_per_bin / (m["dev_ms"] * 1e-3) / 1e9
     instr_ref, instr_exec = fp64_instr_per_bin(cfg["octaves"])
     hot_ms = ph["kv_ms"] + ph["kh_ms"]
-    share = {"kv_kernel": 12 * 8 * n_oct, "kh_kernel": 11 * 8 * n_oct, "ks_kernel": 11 * 8 * n_oct}
+    share = {"kv_kernel": 12 * 8 * n_oct, "kh_kernel": 11 * 8 * n_oct, "ks_kernel": 11 * 8 * n_oct, "khs_kernel": 22 * 8 * n_oct}
     tr = (load_traffic() or {}).get(name, {})
     per_kernel = {}
-    for kname, key in (("kv_kernel", "kv_ms"), ("kh_kernel", "kh_ms"), ("ks_kernel", "ks_ms")):
-        if ph[key] <= 0:
+    for kname, key in (("kv_kernel", "kv_ms"), (khn, "kh_ms"), ("ks_kernel", "ks_ms")):
+        if ph[key] < 1e-3:
             continue
         ach = m["bins_rank"] * share[kname] / (ph[key] * 1e-3) / 1e9
         per_kernel[kname] = {"ms": ph[key], "algorithmic_bytes_per_bin": share[kname], "achieved": ach, "frac": ach / peak,

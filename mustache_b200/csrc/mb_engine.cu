@@ -63,11 +63,13 @@ struct mb200_engine {
     float t_prep = 0, t_kv = 0, t_kh = 0, t_ks = 0, t_fin = 0, t_total = 0;
     int launches = 0;
     size_t kv_smem_set = 0, kh_smem_set = 0, ks_smem_set = 0;
+    bool kf_smem_set = false;
     double score_sigma[MB_MAX_STEPS] = {0};   // detection scale per scored index (mb200_set_score_sigmas), 0 if unset
     MbTensorMaps tmaps;              // main chain (host copy)
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
     long long plane_v = 0, plane_l = 0;
+    int fusion = 1;                  // mb200_set_fusion: 1 = axis-1 + scoring fused (khs_kernel) whenever the chain fits, 0 = never
     int fast = 0;                    // mb200_set_arithmetic: 0 = the reference's multiply-then-add, 1 = fused multiply-add
     int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
     int ndiff = 0;                   // MB_FLAG_DIFFREF steps of the difference chain
@@ -275,6 +277,11 @@ int set_smem_limits(mb200_engine* e) {
         CU(e, cudaFuncSetAttribute(kh_kernel<KH_DEBUG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)khb));
         e->kh_smem_set = khb;
     }
+    if (!e->kf_smem_set) {
+        CU(e, cudaFuncSetAttribute(khs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes()));
+        CU(e, cudaFuncSetAttribute(khs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes()));
+        e->kf_smem_set = true;
+    }
     const size_t ksb = ks_smem_bytes(e->prog.n_scored);
     if (ksb != e->ks_smem_set) {
         CU(e, cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksb));
@@ -302,6 +309,15 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
     const int mode = g.dout != nullptr ? KH_DIFF : ((g.dbgG != nullptr || g.dbgL != nullptr) ? KH_DEBUG : KH_MAIN);
+    if (mode == KH_MAIN && e->fusion && pg.n_scored > 0 && kf_fits(pg.rmax, pg.n_scored)) {
+        // axis-1 pass, DoG and scoring in one kernel: the DoG levels stay in shared memory
+        if (e->fast) khs_kernel<true><<<ks_grid(e, nblk), KS_THREADS, kf_smem_bytes(), e->stream>>>(pg, tm, g);
+        else khs_kernel<false><<<ks_grid(e, nblk), KS_THREADS, kf_smem_bytes(), e->stream>>>(pg, tm, g);
+        CU(e, cudaGetLastError());
+        if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
+        e->launches += 2;
+        return MB200_OK;
+    }
     // KH_DIFF: difference stack, only the DIFFREF DoGs are kept; KH_DEBUG: dense dumps of mb200_debug_level
     if (e->fast) {
         if (mode == KH_DIFF) kh_kernel<KH_DIFF, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
@@ -442,19 +458,23 @@ const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null 
 
 // Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping), and for each step the
 // latest earlier step whose box it overwrites.
-static void plan_kh_ring(MbProgram& p) {
-    const int cap = kh_ring_doubles(p.rmax);
+static void plan_ring(const MbProgram& p, int cap, MbStage* stage) {
     auto size_of = [&](int s) { return (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15; };
     int cur = 0;
     for (int s = 0; s < p.n_steps; ++s) {
         const int size = size_of(s);
         if (cur + size > cap) cur = 0;
-        p.stage[s].off = cur;
-        p.stage[s].dep = -1;
+        stage[s].off = cur;
+        stage[s].dep = -1;
         for (int t = 0; t < s; ++t)
-            if (p.stage[t].off < cur + size && cur < p.stage[t].off + size_of(t)) p.stage[s].dep = t;
+            if (stage[t].off < cur + size && cur < stage[t].off + size_of(t)) stage[s].dep = t;
         cur += size;
     }
+}
+
+static void plan_kh_ring(MbProgram& p) {
+    plan_ring(p, kh_ring_doubles(p.rmax), p.stage);
+    if (kf_fits(p.rmax, p.n_scored)) plan_ring(p, kf_ring_doubles(p.n_scored), p.stage_f);      // fused khs_kernel
 }
 
 // kv_kernel's plan: steps sorted by radius and cut into groups of 1..KV_GMAX consecutive steps.  A group of n steps
@@ -881,6 +901,12 @@ int mb200_fetch_records(mb200_engine* e, int block, int64_t capacity, int32_t* r
 int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add) {
     if (!e || fused_multiply_add < 0 || fused_multiply_add > 1) return MB200_ERR_ARG;
     e->fast = fused_multiply_add;
+    return MB200_OK;
+}
+
+int mb200_set_fusion(mb200_engine* e, int enable) {
+    if (!e || enable < 0 || enable > 1) return MB200_ERR_ARG;
+    e->fusion = enable;
     return MB200_OK;
 }
 

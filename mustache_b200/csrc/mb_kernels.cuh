@@ -52,6 +52,7 @@ struct MbProgram {
     int pad;
     MbStep st[MB_MAX_STEPS];
     MbStage stage[MB_MAX_STEPS];
+    MbStage stage_f[MB_MAX_STEPS];  // same for the (smaller) ring of the fused khs_kernel
     int score_id[MB_MAX_STEPS];   // per scored index: octave*12 + i  (reference's scales[o][i])
     double taps[MB_MAX_TAPS];
 };
@@ -190,6 +191,23 @@ __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
 __host__ __device__ inline size_t ks_smem_bytes(int n_scored) {
     return ((size_t)KS_DEPTH * KS_TR * KS_PITCH + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KS_THREADS / 32) + 2 * KS_DEPTH)
            * sizeof(double);                                                       // stages + per-warp statistics + mbarriers
+}
+
+// khs_kernel (axis-1 pass + DoG + scoring fused, the DoG levels never leave the SM): tile and thread layout of ks_kernel
+// (30 x 62 scored pixels + halo, without the row stagger: every row must hold the same 64 columns because a pixel is
+// compared with the rows above and below), three DoG levels in shared memory written by the threads themselves (odd
+// pitch: the 16 lanes of a half warp hit 16 different bank pairs), the rest of the CTA's share of the SM is the ring of
+// axis-0 boxes.
+constexpr int KF_PL = KS_TC + 1;      // 65: tile columns 0..63 + the right neighbour of the last one; odd
+constexpr int KF_LSTAGES = 3;
+__host__ __device__ inline int kf_ring_doubles(int n_scored) {
+    const int total = (112 * 1024) / 8;
+    return total - KF_LSTAGES * KS_TR * KF_PL - 2 * MB_MAX_STEPS - 2 * (n_scored > 0 ? n_scored : 1) * (KS_THREADS / 32);
+}
+__host__ __device__ inline size_t kf_smem_bytes() { return (size_t)112 * 1024; }
+// the fused kernel needs at least two of the widest boxes in its ring
+__host__ __device__ inline bool kf_fits(int rmax, int n_scored) {
+    return 2 * ((KH_TR * kh_box_width(rmax) + 15) & ~15) <= kf_ring_doubles(n_scored);
 }
 
 // scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
@@ -941,6 +959,260 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     }
     // ---- emit the pixels that were ever updated (pAll != 2, mustache.py:774) ----
     if (lvl != 0) {
+#pragma unroll
+        for (int k = 0; k < KS_K; ++k) {
+            const int id = (int)((lvl >> (8 * k)) & 0xff);
+            if (id) {
+                const unsigned long long slot = atomicAdd(g.rec_count + b, 1ULL);
+                if (slot < (unsigned long long)g.rec_cap) {
+                    const size_t o = (size_t)b * g.rec_cap + slot;
+                    g.rec_row[o] = i;
+                    g.rec_col[o] = jc0 + k;
+                    g.rec_v[o] = vbest[k];
+                    g.rec_sidx[o] = id - 1;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_HS (khs_kernel): kh_kernel and ks_kernel in one -- axis-1 pass, DoG, 3x3 maxima, extremum test, running best and |L|
+// statistics -- for chains whose widest axis-0 box leaves room for three DoG levels in shared memory (kf_fits: the
+// default two octaves).  The DoG levels are written by the threads that computed them into a three-stage ring and scored
+// from there: `L` never goes to HBM (11 writes + 11 reads of 8 B per contact-bin and octave less, half of what the
+// 2-octave path moved).  Tile = 30 x 62 scored pixels + 1-pixel halo, thread = 8 pixels of one row for the whole chain: G_{s-1}, the two last DoGs and the running best in
+// registers.  Two CTA barriers per level: one before a level overwrites the stage of level-3 (everybody is done
+// scoring with it), one after (the level is visible).  The axis-0 boxes arrive by TMA exactly as in kh_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(KS_THREADS, 2)
+khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
+    extern __shared__ __align__(128) double smem[];
+    constexpr int NW = KS_THREADS / 32;
+    constexpr int PL = KF_PL;
+    const int n_scored = max(prog.n_scored, 1);
+    double* vbuf = smem;                                        // ring of staged axis-0 boxes (TMA destination)
+    double* lst = vbuf + kf_ring_doubles(prog.n_scored);        // [3][KS_TR][PL] DoG levels
+    double* pmin = lst + KF_LSTAGES * KS_TR * PL;               // [n_scored][NW]
+    double* psum = pmin + (size_t)n_scored * NW;
+    uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)n_scored * NW);    // [n_steps]
+    uint64_t* empty = full + MB_MAX_STEPS;
+
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int is0 = blockIdx.y * KS_SR;                 // first scored row
+    const int i0 = is0 - 1;                             // tile row 0 (halo)
+    const int js = is0 + 4 + blockIdx.x * KS_SC;        // first scored column of this CTA
+    const int jt = js - 1;                              // image column of tile column 0
+    const int ilast = min(is0 + KS_SR, g.n) - 1;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    if (!((js < g.n) && (js <= ilast + g.dhi))) {       // nothing to score here
+        for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+            g.part_min[o] = kInf;
+            g.part_sum[o] = 0.0;
+        }
+        return;
+    }
+    const int rmax = prog.rmax;
+    const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+    const int i = i0 + lane;                            // this thread's image row
+    const int c0 = warp * KS_K;                         // first tile column of this thread
+    const int jc0 = jt + c0;                            // image column of its first pixel
+    const bool row_in = (i >= 0) && (i < g.n);
+    const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
+    const bool border = (jt - rmax < 0) || (jt + KS_TC + 1 + rmax > g.n);
+    const int n_steps = prog.n_steps;
+
+    for (int t = threadIdx.x; t < n_steps; t += KS_THREADS) {
+        mbar_init(&full[t], 1);
+        mbar_init(&empty[t], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // producer (one elected lane of warp 0), as in kh_kernel: one TMA box per step into its slot of the ring
+    const MbStage* stg = prog.stage_f;
+    int next_issue = 0;
+    auto issue_ready = [&](int p_now) {
+        while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
+            const int dep = stg[next_issue].dep;
+            if (dep >= p_now) break;
+            if (elect_one()) {
+                if (dep >= 0) mbar_wait(&empty[dep], 0);
+                const int s = next_issue;
+                const int R = prog.st[s].radius;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(KS_TR * kh_box_width(R)) * 8u);
+                tma_load_box3d(vbuf + stg[s].off, &tm->v[s], (jt - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+            }
+            ++next_issue;
+        }
+    };
+    if (!border && warp == 0) issue_ready(0);
+
+    // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
+    const bool chunk_live = (jt + warp * KS_K + KS_K - i0 >= 2) && (jt + warp * KS_K - (i0 + KS_TR - 1) <= g.dhi + 2) &&
+                            (jt + warp * KS_K < g.n);
+    unsigned zmask = 0;                                 // pixels inside the image (the others hold the cval 0)
+    unsigned mask = 0;                                  // mask bits (mustache.py:699: c != 0 and j - i >= 4, before the fills)
+#pragma unroll
+    for (int k = 0; k < KS_K; ++k) {
+        const int c = c0 + k, j = jc0 + k, d = j - i;
+        if (row_in && j < g.n) zmask |= 1u << k;
+        if (row_scored && c >= 1 && c <= KS_SC && j < g.n && d >= 4 && d <= g.dhi) {
+            if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
+        }
+    }
+    const int off_c = lane * PL + c0;                   // own pixel 0 inside a DoG stage
+    const int cl = (c0 == 0) ? 0 : -1;                  // the column left of tile column 0 does not exist: clamp (halo only)
+
+    double gA[KS_K], gB[KS_K], dA[KS_K], dB[KS_K], vbest[KS_K];
+#pragma unroll
+    for (int k = 0; k < KS_K; ++k) { gA[k] = gB[k] = dA[k] = dB[k] = vbest[k] = 0.0; }
+    unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
+    unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
+    int nl = 0;                                         // DoG levels formed so far
+
+    // step s: Gaussian into gnew (gprev = step s-1); if the step forms a DoG: level nl = gprev - gnew into dnew (dprev = level
+    // nl-1), staged, and level nl-1 scored against its two neighbours
+    auto step = [&](const int s, const double (&gprev)[KS_K], double (&gnew)[KS_K], const double (&dprev)[KS_K], double (&dnew)[KS_K]) {
+        const int R = prog.st[s].radius;
+        double* vst = vbuf + (border ? 0 : stg[s].off);
+        const int bw = kh_box_width(R);
+        const int shift = border ? 0 : ((jt - R - g.vlo) & 1);
+        if (!border) {
+            if (warp == 0) issue_ready(s);
+            mbar_wait(&full[s], 0);
+        } else {
+            __syncthreads();
+            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
+            const int wlen = KS_TC + 1 + 2 * R;
+            for (int r = warp; r < KS_TR; r += NW) {
+                const int ii = i0 + r;
+                for (int t = lane; t < wlen; t += 32) {
+                    double val = 0.0;
+                    if (ii >= 0 && ii < g.n) {
+                        const int jj = reflect_idx(jt - R + t, g.n);
+                        const int dd = jj - ii - g.vlo;
+                        if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
+                    }
+                    vst[r * bw + t] = val;
+                }
+            }
+            __syncthreads();
+        }
+        if (chunk_live && row_in) {
+            conv_slide<KS_K, 1, FAST>(vst + lane * bw + shift + c0 + R, R, prog.taps + prog.st[s].tap_off, gnew);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) gnew[k] = 0.0;
+        }
+        if (!border) {                                           // release the box: one arrival per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        const int flags = prog.st[s].flags;
+        if (flags & MB_FLAG_RESTART) return;                     // first Gaussian of a chain: no DoG yet
+        // ---- DoG level nl into its stage ----
+        double* st = lst + (nl % KF_LSTAGES) * (KS_TR * PL) + off_c;
+        __syncthreads();                                         // everybody is done scoring with level nl-3 (same stage)
+        if (!border && warp == 0) issue_ready(s + 1);            // ... and has released box s: its slot may be refilled now
+#pragma unroll
+        for (int k = 0; k < KS_K; ++k) {
+            dnew[k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+            st[k] = dnew[k];
+        }
+        __syncthreads();                                         // level nl is visible
+        // ---- score level nl-1 (ks_kernel's level(), own values from registers) ----
+        const double* sp = lst + ((nl + KF_LSTAGES - 2) % KF_LSTAGES) * (KS_TR * PL) + off_c;    // level nl-2
+        unsigned e_new = 0;
+        double tmin = kInf, tsum = 0.0;
+        const bool score = (flags & MB_FLAG_SCORE) != 0;
+        const int sidx = prog.st[s].score_idx;
+        if (row_scored) {
+            double o0, o9, up[KS_K + 2], dn[KS_K + 2];            // rows i-1, i+1: tile columns c0-1 .. c0+8; row i: the two ends
+            o0 = st[cl]; up[0] = st[cl - PL]; dn[0] = st[cl + PL];
+            o9 = st[KS_K]; up[KS_K + 1] = st[KS_K - PL]; dn[KS_K + 1] = st[KS_K + PL];
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) {
+                up[k + 1] = st[k - PL];
+                dn[k + 1] = st[k + PL];
+            }
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) {
+                const double x = dnew[k];
+                const double xl = k == 0 ? o0 : dnew[k - 1], xr = k == KS_K - 1 ? o9 : dnew[k + 1];
+                const bool en = (x >= xl) && (x >= xr) && (x >= up[k]) && (x >= up[k + 1]) && (x >= up[k + 2]) &&
+                                (x >= dn[k]) && (x >= dn[k + 1]) && (x >= dn[k + 2]);
+                if (en) e_new |= 1u << k;
+            }
+            if (score) {
+                const unsigned cand = mask & e_cur & (e_prev | e_new);      // mustache.py:762-763
+#pragma unroll
+                for (int k = 0; k < KS_K; ++k) {
+                    const unsigned bit = 1u << k;
+                    const double x = dprev[k];
+                    if (mask & bit) {                                       // expon.fit over the mask, mustache.py:755
+                        const double a = fabs(x);
+                        tmin = dmin(tmin, a);
+                        tsum = __dadd_rn(tsum, a);
+                    }
+                    if ((cand & bit) && x > vbest[k]) {                     // mustache.py:761
+                        const double xl = k == 0 ? o0 : dnew[k - 1], xr = k == KS_K - 1 ? o9 : dnew[k + 1];
+                        // mustache.py:765  Lc > max3x3(Ln): the next level's 3x3 block is in registers
+                        bool ok = (x > xl) && (x > dnew[k]) && (x > xr) && (x > up[k]) && (x > up[k + 1]) && (x > up[k + 2]) &&
+                                  (x > dn[k]) && (x > dn[k + 1]) && (x > dn[k + 2]);
+                        if (ok) {
+                            // mustache.py:764  Lc > max3x3(Lp): the previous level is still staged
+                            const double* q = sp + k;
+                            const int ql = (k == 0) ? cl : -1;             // left neighbour of own pixel 0: clamped like cl
+                            ok = (x > q[ql]) && (x > q[0]) && (x > q[1]) && (x > q[-PL + ql]) && (x > q[-PL]) && (x > q[-PL + 1]) &&
+                                 (x > q[PL + ql]) && (x > q[PL]) && (x > q[PL + 1]);
+                            if (ok) {
+                                vbest[k] = x;
+                                lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (score) {                                            // per-warp statistics, fixed order (deterministic)
+            tmin = warp_min(tmin);
+            tsum = warp_sum(tsum);
+            if (lane == 0) {
+                pmin[sidx * NW + warp] = tmin;
+                psum[sidx * NW + warp] = tsum;
+            }
+        }
+        e_prev = e_cur;
+        e_cur = e_new;
+        ++nl;
+    };
+
+    // Two steps per trip so that the register arrays swap roles by name.  The DoG arrays follow the step parity too: a step
+    // that forms no DoG (first Gaussian of a chain) leaves `dprev` stale, but nothing is scored before a chain has formed
+    // three DoGs of its own (mb200_set_program checks), and from its second DoG on the parity is right again.
+    int p = 0;
+    for (; p + 1 < n_steps; p += 2) {
+        step(p, gB, gA, dB, dA);
+        step(p + 1, gA, gB, dA, dB);
+    }
+    if (p < n_steps) step(p, gB, gA, dB, dA);
+    __syncthreads();
+    for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+        double mn = pmin[t * NW], sm = psum[t * NW];
+        for (int w = 1; w < NW; ++w) {
+            mn = dmin(mn, pmin[t * NW + w]);
+            sm = __dadd_rn(sm, psum[t * NW + w]);
+        }
+        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+        g.part_min[o] = mn;
+        g.part_sum[o] = sm;
+    }
+    if (lvl != 0) {                                     // the pixels that were ever updated (pAll != 2, mustache.py:774)
 #pragma unroll
         for (int k = 0; k < KS_K; ++k) {
             const int id = (int)((lvl >> (8 * k)) & 0xff);

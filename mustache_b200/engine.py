@@ -47,6 +47,7 @@ SIGNATURES = {
     "mb200_fetch_q": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_last_post_ms": (C.c_int, [_H, _f32p]),
     "mb200_set_arithmetic": (C.c_int, [_H, C.c_int]),
+    "mb200_set_fusion": (C.c_int, [_H, C.c_int]),
     "mb200_set_pass_limit": (C.c_int, [_H, C.c_int]),
     "mb200_set_score_sigmas": (C.c_int, [_H, _f64p, C.c_int]),
     "mb200_fetch_sigma": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
@@ -244,6 +245,10 @@ class ScaleSpaceEngine:
     def set_arithmetic(self, fused_multiply_add):
         """False: scipy's multiply-then-add (bit-exact Gaussians, default).  True: opt-in FMA fast mode."""
         self._chk(self.lib.mb200_set_arithmetic(self.h, 1 if fused_multiply_add else 0))
+
+    def set_fusion(self, enable):
+        """True (default): fused axis-1 + scoring kernel whenever the chain fits; False: always three kernels."""
+        self._chk(self.lib.mb200_set_fusion(self.h, 1 if enable else 0))
 
     def set_pass_limit(self, max_blocks):
         """At most this many blocks per pass of the kernels (0 = whatever fits); next configure()."""

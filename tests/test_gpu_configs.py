@@ -347,3 +347,27 @@ def test_device_candidates_equal_host_selection(eng, octs, pt, st):
     eng.select_candidates(pt, st, candidate_fraction=1e-9)
     small = eng.candidates_batch()
     assert all(np.array_equal(small[b]["rows"], cands[b]["rows"]) for b in range(3))
+
+
+@pytest.mark.parametrize("n,dpx", [(512, 200), (700, 900), (2000, 400)])
+def test_fused_equals_three_kernel_path(eng, n, dpx):
+    """khs_kernel (axis-1 + DoG + scoring fused, DoG levels in shared memory) against kh_kernel + ks_kernel: records and
+    exponential fits bit for bit, on band-limited tiles, a tile whose band is wider than the tile, and the CLI block shape."""
+    tiles = [gen.band_to_dense(gen.dense_band_tile(n, min(dpx, n), seed=270 + b, blob_seed=280 + b, nblobs=20, missing=0.1 * b), n)
+             for b in range(2)]
+    _set(eng, [1.6, 3.2])
+    out = {}
+    for fused in (True, False):
+        eng.set_fusion(fused)
+        eng.configure(n, dpx, 2)
+        for b, t in enumerate(tiles):
+            eng.upload_dense(b, t)
+        eng.run()
+        out[fused] = (eng.records_batch(), [eng.fits(b) for b in range(2)], eng.timing())
+    eng.set_fusion(True)
+    assert out[True][2]["ks_ms"] < 1e-3 < out[False][2]["ks_ms"]          # the two paths really are different kernels
+    for b in range(2):
+        assert out[True][0][b]["n_found"] > 100
+        _equal_records(out[True][0][b], out[False][0][b])
+        for k in ("loc", "scale"):
+            assert np.array_equal(out[True][1][b][k], out[False][1][b][k])

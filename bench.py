@@ -461,7 +461,7 @@ def roofline(cfg, name, m, peak, peaks_found):
     n_oct = len(cfg["octaves"])
     bytes_per_bin = BYTES_PER_BIN_PER_OCTAVE * n_oct
     ph = m["phases"]
-    fused = ph["ks_ms"] < 1e-3                          # khs_kernel: axis-1 pass, DoG and scoring in one kernel (2-octave chains)
+    fused = ph["ks_ms"] < 0.01                          # khs_kernel: axis-1 pass, DoG and scoring in one kernel (2-octave chains)
     khn = "khs_kernel" if fused else "kh_kernel"
     kern = {"kv_kernel": ph["kv_ms"], khn: ph["kh_ms"], "ks_kernel": ph["ks_ms"]}
     dom = max(kern, key=kern.get)
@@ -472,7 +472,7 @@ def roofline(cfg, name, m, peak, peaks_found):
     tr = (load_traffic() or {}).get(name, {})
     per_kernel = {}
     for kname, key in (("kv_kernel", "kv_ms"), (khn, "kh_ms"), ("ks_kernel", "ks_ms")):
-        if ph[key] < 1e-3:
+        if ph[key] < 0.01:
             continue
         ach = m["bins_rank"] * share[kname] / (ph[key] * 1e-3) / 1e9
         per_kernel[kname] = {"ms": ph[key], "algorithmic_bytes_per_bin": share[kname], "achieved": ach, "frac": ach / peak,

@@ -1068,16 +1068,19 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
     const int off_c = lane * PL + c0;                   // own pixel 0 inside a DoG stage
     const int cl = (c0 == 0) ? 0 : -1;                  // the column left of tile column 0 does not exist: clamp (halo only)
 
-    double gA[KS_K], gB[KS_K], dA[KS_K], dB[KS_K], vbest[KS_K];
+    double gprev[KS_K], vbest[KS_K];
 #pragma unroll
-    for (int k = 0; k < KS_K; ++k) { gA[k] = gB[k] = dA[k] = dB[k] = vbest[k] = 0.0; }
+    for (int k = 0; k < KS_K; ++k) { gprev[k] = vbest[k] = 0.0; }
+    double pend_min = kInf, pend_sum = 0.0;             // min / sum of |L| over the mask for the level scored at the next step
     unsigned long long lvl = 0;                         // 8 x uint8: scored index + 1 of the winning level, 0 = none
     unsigned e_cur = 0, e_prev = 0;                     // "L == max3x3(L)" bits of the two previous DoGs
     int nl = 0;                                         // DoG levels formed so far
 
-    // step s: Gaussian into gnew (gprev = step s-1); if the step forms a DoG: level nl = gprev - gnew into dnew (dprev = level
-    // nl-1), staged, and level nl-1 scored against its two neighbours
-    auto step = [&](const int s, const double (&gprev)[KS_K], double (&gnew)[KS_K], const double (&dprev)[KS_K], double (&dnew)[KS_K]) {
+    // step s: Gaussian of the step (gprev holds the previous one); if the step forms a DoG: level nl = gprev - gnew, staged,
+    // and level nl-1 scored against its two neighbours.  One copy of the code for every step (the Gaussian moves from gnew to
+    // gprev at the end: 16 moves against ~10^3 instructions per step, and half the instruction footprint of a role swap).
+    for (int s = 0; s < n_steps; ++s) {
+        double gnew[KS_K], dnew[KS_K];
         const int R = prog.st[s].radius;
         double* vst = vbuf + (border ? 0 : stg[s].off);
         const int bw = kh_box_width(R);
@@ -1114,7 +1117,11 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         const int flags = prog.st[s].flags;
-        if (flags & MB_FLAG_RESTART) return;                     // first Gaussian of a chain: no DoG yet
+        if (flags & MB_FLAG_RESTART) {                           // first Gaussian of a chain: no DoG yet
+#pragma unroll
+            for (int k = 0; k < KS_K; ++k) gprev[k] = gnew[k];
+            continue;
+        }
         // ---- DoG level nl into its stage ----
         double* st = lst + (nl % KF_LSTAGES) * (KS_TR * PL) + off_c;
         __syncthreads();                                         // everybody is done scoring with level nl-3 (same stage)
@@ -1123,12 +1130,16 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
         for (int k = 0; k < KS_K; ++k) {
             dnew[k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
             st[k] = dnew[k];
+            gprev[k] = gnew[k];
         }
         __syncthreads();                                         // level nl is visible
         // ---- score level nl-1 (ks_kernel's level(), own values from registers) ----
         const double* sp = lst + ((nl + KF_LSTAGES - 2) % KF_LSTAGES) * (KS_TR * PL) + off_c;    // level nl-2
+        const double* sc = lst + ((nl + KF_LSTAGES - 1) % KF_LSTAGES) * (KS_TR * PL) + off_c;    // level nl-1 (being scored)
         unsigned e_new = 0;
-        double tmin = kInf, tsum = 0.0;
+        const double tmin = pend_min, tsum = pend_sum;           // statistics of level nl-1, taken when it was formed
+        pend_min = kInf;
+        pend_sum = 0.0;
         const bool score = (flags & MB_FLAG_SCORE) != 0;
         const int sidx = prog.st[s].score_idx;
         if (row_scored) {
@@ -1148,30 +1159,38 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
                                 (x >= dn[k]) && (x >= dn[k + 1]) && (x >= dn[k + 2]);
                 if (en) e_new |= 1u << k;
             }
-            if (score) {
-                const unsigned cand = mask & e_cur & (e_prev | e_new);      // mustache.py:762-763
 #pragma unroll
-                for (int k = 0; k < KS_K; ++k) {
-                    const unsigned bit = 1u << k;
-                    const double x = dprev[k];
-                    if (mask & bit) {                                       // expon.fit over the mask, mustache.py:755
-                        const double a = fabs(x);
-                        tmin = dmin(tmin, a);
-                        tsum = __dadd_rn(tsum, a);
-                    }
-                    if ((cand & bit) && x > vbest[k]) {                     // mustache.py:761
-                        const double xl = k == 0 ? o0 : dnew[k - 1], xr = k == KS_K - 1 ? o9 : dnew[k + 1];
-                        // mustache.py:765  Lc > max3x3(Ln): the next level's 3x3 block is in registers
-                        bool ok = (x > xl) && (x > dnew[k]) && (x > xr) && (x > up[k]) && (x > up[k + 1]) && (x > up[k + 2]) &&
-                                  (x > dn[k]) && (x > dn[k + 1]) && (x > dn[k + 2]);
+            for (int k = 0; k < KS_K; ++k) {
+                if (mask & (1u << k)) {                                     // expon.fit over the mask (mustache.py:755), for the
+                    const double a = fabs(dnew[k]);                         // step that scores this level
+                    pend_min = dmin(pend_min, a);
+                    pend_sum = __dadd_rn(pend_sum, a);
+                }
+            }
+            if (score) {
+                unsigned cand = mask & e_cur & (e_prev | e_new);            // mustache.py:762-763 (few pixels get this far)
+                while (cand) {
+                    const int k = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const double x = sc[k];                                 // own value of level nl-1
+                    double vb = 0.0;
+#pragma unroll
+                    for (int q = 0; q < KS_K; ++q) vb = (q == k) ? vbest[q] : vb;
+                    if (x > vb) {                                           // mustache.py:761
+                        // mustache.py:765  Lc > max3x3(Ln): the level just staged
+                        const double* qn = st + k;
+                        const int ql = (k == 0) ? cl : -1;                 // left neighbour of own pixel 0: clamped like cl
+                        bool ok = (x > qn[ql]) && (x > qn[0]) && (x > qn[1]) && (x > qn[-PL + ql]) && (x > qn[-PL]) && (x > qn[-PL + 1]) &&
+                                  (x > qn[PL + ql]) && (x > qn[PL]) && (x > qn[PL + 1]);
                         if (ok) {
                             // mustache.py:764  Lc > max3x3(Lp): the previous level is still staged
                             const double* q = sp + k;
-                            const int ql = (k == 0) ? cl : -1;             // left neighbour of own pixel 0: clamped like cl
                             ok = (x > q[ql]) && (x > q[0]) && (x > q[1]) && (x > q[-PL + ql]) && (x > q[-PL]) && (x > q[-PL + 1]) &&
                                  (x > q[PL + ql]) && (x > q[PL]) && (x > q[PL + 1]);
                             if (ok) {
-                                vbest[k] = x;
+#pragma unroll
+                                for (int q2 = 0; q2 < KS_K; ++q2)
+                                    if (q2 == k) vbest[q2] = x;
                                 lvl = (lvl & ~(0xffULL << (8 * k))) | ((unsigned long long)(sidx + 1) << (8 * k));
                             }
                         }
@@ -1180,27 +1199,17 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
             }
         }
         if (score) {                                            // per-warp statistics, fixed order (deterministic)
-            tmin = warp_min(tmin);
-            tsum = warp_sum(tsum);
+            const double wmin = warp_min(tmin), wsum = warp_sum(tsum);
             if (lane == 0) {
-                pmin[sidx * NW + warp] = tmin;
-                psum[sidx * NW + warp] = tsum;
+                pmin[sidx * NW + warp] = wmin;
+                psum[sidx * NW + warp] = wsum;
             }
         }
         e_prev = e_cur;
         e_cur = e_new;
         ++nl;
-    };
-
-    // Two steps per trip so that the register arrays swap roles by name.  The DoG arrays follow the step parity too: a step
-    // that forms no DoG (first Gaussian of a chain) leaves `dprev` stale, but nothing is scored before a chain has formed
-    // three DoGs of its own (mb200_set_program checks), and from its second DoG on the parity is right again.
-    int p = 0;
-    for (; p + 1 < n_steps; p += 2) {
-        step(p, gB, gA, dB, dA);
-        step(p + 1, gA, gB, dA, dB);
     }
-    if (p < n_steps) step(p, gB, gA, dB, dA);
+
     __syncthreads();
     for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
         double mn = pmin[t * NW], sm = psum[t * NW];

@@ -365,7 +365,7 @@ def test_fused_equals_three_kernel_path(eng, n, dpx):
         eng.run()
         out[fused] = (eng.records_batch(), [eng.fits(b) for b in range(2)], eng.timing())
     eng.set_fusion(True)
-    assert out[True][2]["ks_ms"] < 1e-3 < out[False][2]["ks_ms"]          # the two paths really are different kernels
+    assert out[True][2]["ks_ms"] < 0.02 < out[False][2]["ks_ms"]          # the two paths really are different kernels
     for b in range(2):
         assert out[True][0][b]["n_found"] > 100
         _equal_records(out[True][0][b], out[False][0][b])

@@ -133,9 +133,11 @@ MB200_API int mb200_last_post_ms(mb200_engine* e, float* ms);
  * golden input (tests/test_gpu_fast_mode.py) but which is NOT the reference's arithmetic.  Takes effect at the next run. */
 MB200_API int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add);
 
-/* 1 (default): when the chain's widest axis-0 tile leaves room for three DoG levels in shared memory (the default two
- * octaves do), the axis-1 pass, the DoG and the scoring run as ONE kernel and the DoG levels never go to HBM; 0: always the
- * three-kernel path.  Results are bit-identical either way (tests/test_gpu_configs.py).  Takes effect at the next run. */
+/* 1: when the chain's widest axis-0 tile leaves room for three DoG levels in shared memory (the default two octaves do),
+ * the axis-1 pass, the DoG and the scoring run as ONE kernel (khs_kernel) and the DoG levels never go to HBM; 0 (default):
+ * always the three-kernel path, which measured 6 % faster on B200 (profiles/README.md: the fused kernel halves the DRAM
+ * traffic but pays two CTA barriers per level).  Results are bit-identical either way (tests/test_gpu_configs.py).
+ * Takes effect at the next run. */
 MB200_API int mb200_set_fusion(mb200_engine* e, int enable);
 
 /* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The

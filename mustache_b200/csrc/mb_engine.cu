@@ -69,7 +69,7 @@ struct mb200_engine {
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
     long long plane_v = 0, plane_l = 0;
-    int fusion = 1;                  // mb200_set_fusion: 1 = axis-1 + scoring fused (khs_kernel) whenever the chain fits, 0 = never
+    int fusion = 0;                  // mb200_set_fusion: 1 = axis-1 + scoring fused (khs_kernel) whenever the chain fits, 0 = never
     int fast = 0;                    // mb200_set_arithmetic: 0 = the reference's multiply-then-add, 1 = fused multiply-add
     int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
     int ndiff = 0;                   // MB_FLAG_DIFFREF steps of the difference chain

@@ -247,7 +247,7 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_set_arithmetic(self.h, 1 if fused_multiply_add else 0))
 
     def set_fusion(self, enable):
-        """True (default): fused axis-1 + scoring kernel whenever the chain fits; False: always three kernels."""
+        """True: fused axis-1 + scoring kernel whenever the chain fits; False (default): always three kernels."""
         self._chk(self.lib.mb200_set_fusion(self.h, 1 if enable else 0))
 
     def set_pass_limit(self, max_blocks):

@@ -352,7 +352,8 @@ def test_device_candidates_equal_host_selection(eng, octs, pt, st):
 @pytest.mark.parametrize("n,dpx", [(512, 200), (700, 900), (2000, 400)])
 def test_fused_equals_three_kernel_path(eng, n, dpx):
     """khs_kernel (axis-1 + DoG + scoring fused, DoG levels in shared memory) against kh_kernel + ks_kernel: records and
-    exponential fits bit for bit, on band-limited tiles, a tile whose band is wider than the tile, and the CLI block shape."""
+    coordinates, responses and scales bit for bit, p-values to 1e-12 (the two kernels sum |L| for the exponential fit in a
+    different order), on band-limited tiles, a tile whose band is wider than the tile, and the CLI block shape."""
     tiles = [gen.band_to_dense(gen.dense_band_tile(n, min(dpx, n), seed=270 + b, blob_seed=280 + b, nblobs=20, missing=0.1 * b), n)
              for b in range(2)]
     _set(eng, [1.6, 3.2])
@@ -368,6 +369,7 @@ def test_fused_equals_three_kernel_path(eng, n, dpx):
     assert out[True][2]["ks_ms"] < 0.02 < out[False][2]["ks_ms"]          # the two paths really are different kernels
     for b in range(2):
         assert out[True][0][b]["n_found"] > 100
-        _equal_records(out[True][0][b], out[False][0][b])
-        for k in ("loc", "scale"):
-            assert np.array_equal(out[True][1][b][k], out[False][1][b][k])
+        _equal_records(out[True][0][b], out[False][0][b], keys=("rows", "cols", "v", "score_id", "sigma"))
+        assert np.abs(out[True][0][b]["p"] - out[False][0][b]["p"]).max() <= 1e-12
+        assert np.array_equal(out[True][1][b]["loc"], out[False][1][b]["loc"])
+        assert np.abs(out[True][1][b]["scale"] / out[False][1][b]["scale"] - 1).max() <= 1e-13

@@ -196,6 +196,18 @@ MB200_API int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const in
  * instructions per output pixel the plan costs, sum over groups of R_group*(2n+1)+n.  Either output may be NULL. */
 MB200_API int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, int64_t* fp64_per_output);
 
+/* Native reader of the text contact format, the parse half of read_pd() (mustache.py:254-263: get_sep, pd.read_csv(header=None),
+ * dropna, the is_chr filter on both chromosome columns of a 5-column file).  Host only, multi-threaded over a memory map
+ * (threads <= 0: all cores).  Returns the rows of `chromosome` (all rows for a 3-column file) as the two position columns and
+ * the value column; value_is_int tells whether pandas would have inferred int64 for it (every token an integer).  Strict:
+ * MB200_PARSE_UNSUPPORTED (1) for anything pandas treats specially (quotes, ragged or missing fields, non-integer positions,
+ * NaN tokens, values with more than 15 significant digits), in which case the caller stays with its pandas reader. */
+#define MB200_PARSE_UNSUPPORTED 1
+MB200_API int mb200_contacts_open(const char* path, const char* chromosome, int threads, void** handle, int64_t* n_rows, int* n_cols,
+                                  int* value_is_int);
+MB200_API int mb200_contacts_read(void* handle, int64_t* pos1, int64_t* pos2, double* value);
+MB200_API void mb200_contacts_close(void* handle);
+
 /* Pinned host memory for callers that want full-speed uploads. */
 MB200_API int mb200_host_alloc(void** ptr, int64_t bytes);
 MB200_API int mb200_host_free(void* ptr);

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmustache_b200.so")
 SOURCES = ["mb_engine.cu"]
-HEADERS = ["mb_kernels.cuh", "mb_normalize.cuh", os.path.join("..", "..", "include", "mustache_b200.h")]
+HEADERS = ["mb_kernels.cuh", "mb_normalize.cuh", "mb_sort.cuh", "mb_post.cuh", "mb_parse.h", os.path.join("..", "..", "include", "mustache_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

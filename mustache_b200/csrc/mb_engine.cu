@@ -5,6 +5,7 @@
 #include "mb_normalize.cuh"
 #include "mb_sort.cuh"
 #include "mb_post.cuh"
+#include "mb_parse.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1457,6 +1458,36 @@ int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, in
     if (fp64_per_output) *fp64_per_output = cost;
     return MB200_OK;
 }
+
+int mb200_contacts_open(const char* path, const char* chromosome, int threads, void** handle, int64_t* n_rows, int* n_cols,
+                        int* value_is_int) {
+    if (!path || !handle) return MB200_ERR_ARG;
+    *handle = nullptr;
+    mb200_contacts* c = new mb200_contacts();
+    const int rc = mb200_parse_file(path, chromosome, threads, c);
+    if (rc != 0) {
+        delete c;
+        return rc < 0 ? MB200_ERR_ARG : rc;             // MB200_PARSE_UNSUPPORTED (1): the caller keeps its pandas reader
+    }
+    *handle = c;
+    if (n_rows) *n_rows = (int64_t)c->a.size();
+    if (n_cols) *n_cols = c->ncols;
+    if (value_is_int) *value_is_int = c->value_is_int ? 1 : 0;
+    return MB200_OK;
+}
+
+int mb200_contacts_read(void* handle, int64_t* a, int64_t* b, double* val) {
+    if (!handle || !a || !b || !val) return MB200_ERR_ARG;
+    const mb200_contacts* c = (const mb200_contacts*)handle;
+    if (!c->a.empty()) {
+        memcpy(a, c->a.data(), c->a.size() * sizeof(int64_t));
+        memcpy(b, c->b.data(), c->b.size() * sizeof(int64_t));
+        memcpy(val, c->val.data(), c->val.size() * sizeof(double));
+    }
+    return MB200_OK;
+}
+
+void mb200_contacts_close(void* handle) { delete (mb200_contacts*)handle; }
 
 int mb200_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return MB200_ERR_ARG;

@@ -62,6 +62,10 @@ SIGNATURES = {
     "mb200_normalize_sparse": (C.c_int, [_H, _i32p, _i32p, _f64p, C.c_int64, C.c_int, C.c_int, _f64p, C.c_int,
                                          C.POINTER(C.c_int)]),
     "mb200_kv_plan": (C.c_int, [C.c_int, _i32p, _i32p, _i64p]),
+    "mb200_contacts_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), _i64p, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]),
+    "mb200_contacts_read": (C.c_int, [C.c_void_p, _i64p, _i64p, _f64p]),
+    "mb200_contacts_close": (None, [C.c_void_p]),
     "mb200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "mb200_host_free": (C.c_int, [C.c_void_p]),
     "mb200_scale_space_dense": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, _i32p, _i32p,

@@ -4,6 +4,8 @@ package imports cleanly on images that lack them (this one does).
 
 Restates mustache.py:199-297 (`get_sep`, `read_bias`, `read_pd`).  Out of scope for kernels.
 """
+import os
+
 import numpy as np
 
 
@@ -66,6 +68,44 @@ def _chromosome_rows(column, chromosome):
     return column.isin(names).to_numpy(dtype=bool)
 
 
+def parse_contacts_native(path, chromosome):
+    """The parse half of read_pd() through the C ABI (mb200_contacts_open: multi-threaded native parser).  Returns
+    (pos1, pos2, value) for the rows of `chromosome`, the value column in the dtype pandas would infer, or None when the
+    file holds anything the strict native parser leaves to pandas."""
+    import ctypes as C
+    from .engine import load_library
+    lib = load_library()
+    h, n, ncols, is_int = C.c_void_p(), C.c_int64(0), C.c_int(0), C.c_int(0)
+    st = lib.mb200_contacts_open(str(path).encode(), str(chromosome).encode(), int(os.environ.get("MUSTACHE_PARSE_THREADS", "0")),
+                                 C.byref(h), C.byref(n), C.byref(ncols), C.byref(is_int))
+    if st != 0:
+        return None
+    try:
+        a, b, val = np.empty(n.value, np.int64), np.empty(n.value, np.int64), np.empty(n.value, np.float64)
+        lib.mb200_contacts_read(h, a.ctypes.data_as(C.POINTER(C.c_int64)), b.ctypes.data_as(C.POINTER(C.c_int64)),
+                                val.ctypes.data_as(C.POINTER(C.c_double)))
+    finally:
+        lib.mb200_contacts_close(h)
+    return a, b, (val.astype(np.int64) if is_int.value else val), ncols.value
+
+
+def _parse_contacts_pandas(path, chromosome):
+    """pd.read_csv + dropna + chromosome filter exactly as mustache.py:255-263 (the fallback of the native parser)."""
+    import pandas as pd
+    sep = guess_separator(path)
+    df = pd.read_csv(path, sep=sep, header=None)
+    df = df.dropna()
+    if df.shape[1] == 5:
+        df = df[_chromosome_rows(df[0], chromosome)]
+        if df.shape[0] == 0:
+            return None
+        df = df[_chromosome_rows(df[2], chromosome)]
+        return df[1].to_numpy(), df[3].to_numpy(), df[4].to_numpy(), 5
+    if df.shape[1] == 3:
+        return df[0].to_numpy(), df[1].to_numpy(), df[2].to_numpy(), 3
+    raise ValueError("expected a 3- or 5-column contact file, got %d columns" % df.shape[1])
+
+
 def read_text(path, distance_in_bp, bias_path, chromosome, res):
     """mustache.py:254-297 (`read_pd`): 5-column (chr pos chr pos count) or 3-column (pos pos count) text.
 
@@ -74,22 +114,19 @@ def read_text(path, distance_in_bp, bias_path, chromosome, res):
     reference: integer counts without a bias file stay int64, and normalize_sparse then writes its z-scores into that
     integer array, truncating them (mustache.py:668, 683) -- part of the reference's observable behaviour.
     """
-    import pandas as pd
-    sep = guess_separator(path)
-    df = pd.read_csv(path, sep=sep, header=None)
-    df = df.dropna()
     limit = (distance_in_bp / res + 1) * res
-    if df.shape[1] == 5:
-        df = df[_chromosome_rows(df[0], chromosome)]
-        if df.shape[0] == 0:
+    got = None
+    if os.environ.get("MUSTACHE_READER", "native") != "pandas":
+        got = parse_contacts_native(path, chromosome)
+    if got is None:
+        got = _parse_contacts_pandas(path, chromosome)
+        if got is None:
             print("Could't read any interaction for this chromosome!")
             return None
-        df = df[_chromosome_rows(df[2], chromosome)]
-        a, b, val = df[1].to_numpy(), df[3].to_numpy(), df[4].to_numpy()
-    elif df.shape[1] == 3:
-        a, b, val = df[0].to_numpy(), df[1].to_numpy(), df[2].to_numpy()
-    else:
-        raise ValueError("expected a 3- or 5-column contact file, got %d columns" % df.shape[1])
+    a, b, val, ncols = got
+    if ncols == 5 and len(a) == 0:
+        print("Could't read any interaction for this chromosome!")
+        return None
     near = np.abs(a - b) <= limit
     a, b, val = a[near] // res, b[near] // res, val[near]
     table = read_bias(bias_path, chromosome, res)

@@ -226,3 +226,53 @@ def test_candidate_postprocess_equals_record_postprocess(seed, n, dpx, missing, 
     finally:
         postprocess.MIN_MASK_FOR_BH = old
     assert len(a) > 0 and a == b
+
+
+def test_native_parser_equals_pandas(tmp_path):
+    """mb200_contacts_open (native multi-threaded parser) returns exactly what the pandas path of read_pd returns: same rows,
+    same order, same values, same inferred dtype -- on the bundled chr21 file, a multi-chromosome integer file (> 1 MB, so
+    that several threads split it), a 3-column file and CRLF input; and hands anything unusual back to pandas."""
+    from mustache_b200 import readers
+    raw, kr = synth.write_chr21_text(str(tmp_path))
+
+    def both(path, chrom):
+        a = readers.parse_contacts_native(path, chrom)
+        b = readers._parse_contacts_pandas(path, chrom)
+        return a, b
+    a, b = both(raw, "21")
+    assert a is not None and len(a[0]) == 677085 and a[3] == 5
+    for p, q in zip(a[:3], b[:3]):
+        assert p.dtype == q.dtype and np.array_equal(p, q)
+    rng = np.random.default_rng(0)
+    multi = str(tmp_path / "multi.txt")
+    with open(multi, "w") as f:
+        for i in range(90000):
+            c = "chr%d" % (1 + i % 3) if i % 2 else str(1 + i % 3)          # 'chr2' and '2' name the same chromosome
+            f.write("%s\t%d\t%s\t%d\t%d\n" % (c, 5000 * rng.integers(0, 4000), c, 5000 * rng.integers(0, 4000), rng.integers(1, 300)))
+    assert os.path.getsize(multi) > (1 << 20)
+    a, b = both(multi, "chr2")
+    assert a[2].dtype == np.int64 and len(a[0]) == 30000
+    for p, q in zip(a[:3], b[:3]):
+        assert p.dtype == q.dtype and np.array_equal(p, q)
+    three = str(tmp_path / "three.txt")
+    vals = ["0.125", "12.345678", "1e-3", "7", "3.0", "123456789012345", "0.000123456789", "2.5E2", "-4.75"]
+    with open(three, "w") as f:
+        for k, v in enumerate(vals):
+            f.write("%d %d %s\r\n" % (1000 * k, 1000 * k + 5000, v))
+    a, b = both(three, "1")
+    assert a[3] == 3 and a[2].dtype == np.float64
+    for p, q in zip(a[:3], b[:3]):
+        assert np.array_equal(p, q)
+    for bad in ("chr1\t100\tchr1\t200\n", "chr1\t100\tchr1\t200\tNaN\n", "chr1\t100.5\tchr1\t200\t3\n",
+                "chr1\t100\tchr1\t200\t0.12345678901234567\n", "\"chr1\"\t100\tchr1\t200\t3\n"):
+        p = str(tmp_path / "bad.txt")
+        open(p, "w").write("chr1\t0\tchr1\t5000\t2\n" + bad)
+        assert readers.parse_contacts_native(p, "chr1") is None
+    # the whole reader on both parsers
+    os.environ["MUSTACHE_READER"] = "pandas"
+    try:
+        ref = readers.read_text(raw, 2000000, kr, "21", 5000)
+    finally:
+        del os.environ["MUSTACHE_READER"]
+    got = readers.read_text(raw, 2000000, kr, "21", 5000)
+    assert all(np.array_equal(p, q) for p, q in zip(got, ref))

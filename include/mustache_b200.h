@@ -137,7 +137,7 @@ MB200_API int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add);
  * the axis-1 pass, the DoG and the scoring run as ONE kernel (khs_kernel) and the DoG levels never go to HBM; 0 (default):
  * always the three-kernel path, which measured 6 % faster on B200 (profiles/README.md: the fused kernel halves the DRAM
  * traffic but pays two CTA barriers per level).  Results are bit-identical either way (tests/test_gpu_configs.py).
- * Takes effect at the next run. */
+ * Takes effect at the next mb200_configure. */
 MB200_API int mb200_set_fusion(mb200_engine* e, int enable);
 
 /* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The

@@ -201,6 +201,12 @@ int encode_maps(mb200_engine* e, const MbProgram& pg, MbTensorMaps& tm, bool wit
         int st = encode_skewed(e, &tm.v[s], vbase, e->wv, e->plane_v, planes_v, kh_box_width(pg.st[s].radius));
         if (st) return st;
     }
+    if (with_l && pg.pad) {
+        for (int s = 0; s < pg.n_steps; ++s) {
+            int st = encode_skewed(e, &tm.vf[s], vbase, e->wv, e->plane_v, planes_v, kf_box_width(pg.st[s].radius, pg.pad));
+            if (st) return st;
+        }
+    }
     if (with_l) return encode_skewed(e, &tm.l, lbase, e->wl, e->plane_l, planes_v, KS_PITCH);
     return MB200_OK;
 }
@@ -258,6 +264,14 @@ dim3 ks_grid(const mb200_engine* e, int nblk) {
     return dim3((span + KS_SC - 1) / KS_SC, (e->n + KS_SR - 1) / KS_SR, nblk);
 }
 
+dim3 kf_grid(const mb200_engine* e, int nblk, int tc) {
+    const int span = (e->dhi - 4 + 1) + KS_SR - 1;
+    return dim3((span + (tc - 2) - 1) / (tc - 2), (e->n + KS_SR - 1) / KS_SR, nblk);
+}
+
+// tile columns of the fused kernel for this batch (0: three-kernel path)
+int fused_tc(const mb200_engine* e) { return (e->fusion && e->prog.n_scored > 0) ? e->prog.pad : 0; }
+
 int set_smem_limits(mb200_engine* e) {
     const size_t kvb = kv_smem_bytes(e->prog.rmax, KV_TH_WIDE), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
     if (kvb > 227 * 1024 || khb > 227 * 1024)
@@ -279,8 +293,10 @@ int set_smem_limits(mb200_engine* e) {
         e->kh_smem_set = khb;
     }
     if (!e->kf_smem_set) {
-        CU(e, cudaFuncSetAttribute(khs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes()));
-        CU(e, cudaFuncSetAttribute(khs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes()));
+        CU(e, cudaFuncSetAttribute(khs_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64)));
+        CU(e, cudaFuncSetAttribute(khs_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(64)));
+        CU(e, cudaFuncSetAttribute(khs_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128)));
+        CU(e, cudaFuncSetAttribute(khs_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128)));
         e->kf_smem_set = true;
     }
     const size_t ksb = ks_smem_bytes(e->prog.n_scored);
@@ -310,10 +326,17 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
     const int mode = g.dout != nullptr ? KH_DIFF : ((g.dbgG != nullptr || g.dbgL != nullptr) ? KH_DEBUG : KH_MAIN);
-    if (mode == KH_MAIN && e->fusion && pg.n_scored > 0 && kf_fits(pg.rmax, pg.n_scored)) {
+    const int ftc = (program == nullptr) ? fused_tc(e) : 0;
+    if (mode == KH_MAIN && ftc) {
         // axis-1 pass, DoG and scoring in one kernel: the DoG levels stay in shared memory
-        if (e->fast) khs_kernel<true><<<ks_grid(e, nblk), KS_THREADS, kf_smem_bytes(), e->stream>>>(pg, tm, g);
-        else khs_kernel<false><<<ks_grid(e, nblk), KS_THREADS, kf_smem_bytes(), e->stream>>>(pg, tm, g);
+        const dim3 gf = kf_grid(e, nblk, ftc);
+        if (ftc == 64) {
+            if (e->fast) khs_kernel<64, true><<<gf, 256, kf_smem_bytes(64), e->stream>>>(pg, tm, g);
+            else khs_kernel<64, false><<<gf, 256, kf_smem_bytes(64), e->stream>>>(pg, tm, g);
+        } else {
+            if (e->fast) khs_kernel<128, true><<<gf, 512, kf_smem_bytes(128), e->stream>>>(pg, tm, g);
+            else khs_kernel<128, false><<<gf, 512, kf_smem_bytes(128), e->stream>>>(pg, tm, g);
+        }
         CU(e, cudaGetLastError());
         if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
         e->launches += 2;
@@ -459,8 +482,11 @@ const char* mb200_last_error(const mb200_engine* e) { return e ? e->err : "null 
 
 // Placement of every step's staged box in kh_kernel's shared-memory ring (first fit, wrapping), and for each step the
 // latest earlier step whose box it overwrites.
-static void plan_ring(const MbProgram& p, int cap, MbStage* stage) {
-    auto size_of = [&](int s) { return (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15; };
+static void plan_ring(const MbProgram& p, int cap, MbStage* stage, int fused_tc = 0) {
+    auto size_of = [&](int s) {
+        const int w = fused_tc ? kf_box_width(p.st[s].radius, fused_tc) : kh_box_width(p.st[s].radius);
+        return (KH_TR * w + 15) & ~15;
+    };
     int cur = 0;
     for (int s = 0; s < p.n_steps; ++s) {
         const int size = size_of(s);
@@ -475,7 +501,10 @@ static void plan_ring(const MbProgram& p, int cap, MbStage* stage) {
 
 static void plan_kh_ring(MbProgram& p) {
     plan_ring(p, kh_ring_doubles(p.rmax), p.stage);
-    if (kf_fits(p.rmax, p.n_scored)) plan_ring(p, kf_ring_doubles(p.n_scored), p.stage_f);      // fused khs_kernel
+    // fused khs_kernel: the 64-column tile (two CTAs per SM) when its ring holds two of the widest boxes, else the
+    // 128-column tile (one CTA per SM), else not available (p.pad = tile columns, 0 = none)
+    p.pad = kf_fits(p.rmax, 64) ? 64 : (kf_fits(p.rmax, 128) ? 128 : 0);
+    if (p.pad) plan_ring(p, kf_ring_doubles(p.pad), p.stage_f, p.pad);
 }
 
 // kv_kernel's plan: steps sorted by radius and cut into groups of 1..KV_GMAX consecutive steps.  A group of n steps
@@ -611,6 +640,10 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->plane_l = ((long long)n * e->wl + 1) & ~1LL;
     dim3 gh = ks_grid(e, 1);
     e->ncta_h = gh.x * gh.y;
+    if (fused_tc(e)) {                                   // the fused kernel writes one partial per warp
+        dim3 gf = kf_grid(e, 1, fused_tc(e));
+        e->ncta_h = gf.x * gf.y * (fused_tc(e) / KS_K);
+    }
     if ((st = set_smem_limits(e))) return st;
     const size_t ns = (size_t)std::max(e->prog.n_scored, 1);
     const size_t B = nblocks;
@@ -907,6 +940,7 @@ int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add) {
 
 int mb200_set_fusion(mb200_engine* e, int enable) {
     if (!e || enable < 0 || enable > 1) return MB200_ERR_ARG;
+    if (e->fusion != enable) e->configured = false;     // the partial-statistics layout depends on the path
     e->fusion = enable;
     return MB200_OK;
 }

@@ -90,6 +90,7 @@ struct KvPlan {
 struct MbTensorMaps {
     CUtensorMap v[MB_MAX_STEPS];
     CUtensorMap l;
+    CUtensorMap vf[MB_MAX_STEPS];   // axis-0 boxes of the fused khs_kernel (its tile may be 128 columns wide)
 };
 
 struct MbGeom {
@@ -193,21 +194,25 @@ __host__ __device__ inline size_t ks_smem_bytes(int n_scored) {
            * sizeof(double);                                                       // stages + per-warp statistics + mbarriers
 }
 
-// khs_kernel (axis-1 pass + DoG + scoring fused, the DoG levels never leave the SM): tile and thread layout of ks_kernel
-// (30 x 62 scored pixels + halo, without the row stagger: every row must hold the same 64 columns because a pixel is
-// compared with the rows above and below), three DoG levels in shared memory written by the threads themselves (odd
-// pitch: the 16 lanes of a half warp hit 16 different bank pairs), the rest of the CTA's share of the SM is the ring of
-// axis-0 boxes.
-constexpr int KF_PL = KS_TC + 1;      // 65: tile columns 0..63 + the right neighbour of the last one; odd
+// khs_kernel<TC> (axis-1 pass + DoG + scoring fused, the DoG levels never leave the SM): tile of 30 x (TC - 2) scored pixels +
+// halo, without the row stagger (every row must hold the same columns because a pixel is compared with the rows above and
+// below), three DoG levels in shared memory written by the threads themselves (odd pitch TC + 1: the 16 lanes of a half
+// warp hit 16 different bank pairs), the rest of the CTA's shared memory is the ring of axis-0 boxes.
+//   TC = 64:  8 warps, two CTAs per SM, 112 KB each  -- chains up to radius ~20 (two octaves)
+//   TC = 128: 16 warps, one CTA per SM, 222 KB       -- up to radius 55 (four octaves): two boxes of 32 x 242 + 3 x 32 x 129
 constexpr int KF_LSTAGES = 3;
-__host__ __device__ inline int kf_ring_doubles(int n_scored) {
-    const int total = (112 * 1024) / 8;
-    return total - KF_LSTAGES * KS_TR * KF_PL - 2 * MB_MAX_STEPS - 2 * (n_scored > 0 ? n_scored : 1) * (KS_THREADS / 32);
+__host__ __device__ inline int kf_box_width(int R, int tc) {
+    const int p = tc + 2 * R + 2;             // filter support of the tile + 1 for the even start column (+ 1 spare)
+    return (p % 4 == 2) ? p : p + 2;
 }
-__host__ __device__ inline size_t kf_smem_bytes() { return (size_t)112 * 1024; }
+__host__ __device__ inline int kf_total_doubles(int tc) { return ((tc == 64 ? 112 : 222) * 1024) / 8; }
+__host__ __device__ inline int kf_ring_doubles(int tc) {
+    return kf_total_doubles(tc) - KF_LSTAGES * KS_TR * (tc + 1) - 2 * MB_MAX_STEPS;
+}
+__host__ __device__ inline size_t kf_smem_bytes(int tc) { return (size_t)kf_total_doubles(tc) * sizeof(double); }
 // the fused kernel needs at least two of the widest boxes in its ring
-__host__ __device__ inline bool kf_fits(int rmax, int n_scored) {
-    return 2 * ((KH_TR * kh_box_width(rmax) + 15) & ~15) <= kf_ring_doubles(n_scored);
+__host__ __device__ inline bool kf_fits(int rmax, int tc) {
+    return 2 * ((KS_TR * kf_box_width(rmax, tc) + 15) & ~15) <= kf_ring_doubles(tc);
 }
 
 // scipy 'reflect' = (d c b a | a b c d | d c b a); |overshoot| < n is guaranteed by the host (n > 2*rmax)
@@ -985,32 +990,32 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 // registers.  Two CTA barriers per level: one before a level overwrites the stage of level-3 (everybody is done
 // scoring with it), one after (the level is visible).  The axis-0 boxes arrive by TMA exactly as in kh_kernel.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FAST>
-__global__ void __launch_bounds__(KS_THREADS, 2)
+template <int TC, bool FAST>
+__global__ void __launch_bounds__((TC / KS_K) * 32, TC == 64 ? 2 : 1)
 khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int NW = KS_THREADS / 32;
-    constexpr int PL = KF_PL;
-    const int n_scored = max(prog.n_scored, 1);
+    constexpr int NW = TC / KS_K;                               // warps: 8 tile columns each
+    constexpr int NT = NW * 32;
+    constexpr int PL = TC + 1;
+    constexpr int SC = TC - 2;                                  // scored columns per CTA
     double* vbuf = smem;                                        // ring of staged axis-0 boxes (TMA destination)
-    double* lst = vbuf + kf_ring_doubles(prog.n_scored);        // [3][KS_TR][PL] DoG levels
-    double* pmin = lst + KF_LSTAGES * KS_TR * PL;               // [n_scored][NW]
-    double* psum = pmin + (size_t)n_scored * NW;
-    uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)n_scored * NW);    // [n_steps]
+    double* lst = vbuf + kf_ring_doubles(TC);                   // [3][KS_TR][PL] DoG levels
+    uint64_t* full = reinterpret_cast<uint64_t*>(lst + KF_LSTAGES * KS_TR * PL);   // [n_steps]
     uint64_t* empty = full + MB_MAX_STEPS;
 
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int is0 = blockIdx.y * KS_SR;                 // first scored row
     const int i0 = is0 - 1;                             // tile row 0 (halo)
-    const int js = is0 + 4 + blockIdx.x * KS_SC;        // first scored column of this CTA
+    const int js = is0 + 4 + blockIdx.x * SC;           // first scored column of this CTA
     const int jt = js - 1;                              // image column of tile column 0
     const int ilast = min(is0 + KS_SR, g.n) - 1;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    // per-warp statistics go straight to part_min / part_sum [b][scored][cta * NW + warp] (g.ncta_h = CTAs * NW)
     if (!((js < g.n) && (js <= ilast + g.dhi))) {       // nothing to score here
-        for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
-            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+        for (int t = threadIdx.x; t < prog.n_scored * NW; t += NT) {
+            const size_t o = ((size_t)b * prog.n_scored + t / NW) * g.ncta_h + cta * NW + t % NW;
             g.part_min[o] = kInf;
             g.part_sum[o] = 0.0;
         }
@@ -1023,10 +1028,10 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
     const int jc0 = jt + c0;                            // image column of its first pixel
     const bool row_in = (i >= 0) && (i < g.n);
     const bool row_scored = (lane >= 1) && (lane <= KS_SR) && row_in;
-    const bool border = (jt - rmax < 0) || (jt + KS_TC + 1 + rmax > g.n);
+    const bool border = (jt - rmax < 0) || (jt + TC + 1 + rmax > g.n);
     const int n_steps = prog.n_steps;
 
-    for (int t = threadIdx.x; t < n_steps; t += KS_THREADS) {
+    for (int t = threadIdx.x; t < n_steps; t += NT) {
         mbar_init(&full[t], 1);
         mbar_init(&empty[t], NW);
     }
@@ -1044,8 +1049,8 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
                 if (dep >= 0) mbar_wait(&empty[dep], 0);
                 const int s = next_issue;
                 const int R = prog.st[s].radius;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(KS_TR * kh_box_width(R)) * 8u);
-                tma_load_box3d(vbuf + stg[s].off, &tm->v[s], (jt - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(KS_TR * kf_box_width(R, TC)) * 8u);
+                tma_load_box3d(vbuf + stg[s].off, &tm->vf[s], (jt - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
             }
             ++next_issue;
         }
@@ -1061,7 +1066,7 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
     for (int k = 0; k < KS_K; ++k) {
         const int c = c0 + k, j = jc0 + k, d = j - i;
         if (row_in && j < g.n) zmask |= 1u << k;
-        if (row_scored && c >= 1 && c <= KS_SC && j < g.n && d >= 4 && d <= g.dhi) {
+        if (row_scored && c >= 1 && c <= SC && j < g.n && d >= 4 && d <= g.dhi) {
             if (rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
         }
     }
@@ -1083,7 +1088,7 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
         double gnew[KS_K], dnew[KS_K];
         const int R = prog.st[s].radius;
         double* vst = vbuf + (border ? 0 : stg[s].off);
-        const int bw = kh_box_width(R);
+        const int bw = kf_box_width(R, TC);
         const int shift = border ? 0 : ((jt - R - g.vlo) & 1);
         if (!border) {
             if (warp == 0) issue_ready(s);
@@ -1091,7 +1096,7 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
         } else {
             __syncthreads();
             const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
-            const int wlen = KS_TC + 1 + 2 * R;
+            const int wlen = TC + 1 + 2 * R;
             for (int r = warp; r < KS_TR; r += NW) {
                 const int ii = i0 + r;
                 for (int t = lane; t < wlen; t += 32) {
@@ -1201,8 +1206,9 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
         if (score) {                                            // per-warp statistics, fixed order (deterministic)
             const double wmin = warp_min(tmin), wsum = warp_sum(tsum);
             if (lane == 0) {
-                pmin[sidx * NW + warp] = wmin;
-                psum[sidx * NW + warp] = wsum;
+                const size_t o = ((size_t)b * prog.n_scored + sidx) * g.ncta_h + cta * NW + warp;
+                g.part_min[o] = wmin;
+                g.part_sum[o] = wsum;
             }
         }
         e_prev = e_cur;
@@ -1210,17 +1216,6 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
         ++nl;
     }
 
-    __syncthreads();
-    for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
-        double mn = pmin[t * NW], sm = psum[t * NW];
-        for (int w = 1; w < NW; ++w) {
-            mn = dmin(mn, pmin[t * NW + w]);
-            sm = __dadd_rn(sm, psum[t * NW + w]);
-        }
-        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
-        g.part_min[o] = mn;
-        g.part_sum[o] = sm;
-    }
     if (lvl != 0) {                                     // the pixels that were ever updated (pAll != 2, mustache.py:774)
 #pragma unroll
         for (int k = 0; k < KS_K; ++k) {

@@ -349,14 +349,15 @@ def test_device_candidates_equal_host_selection(eng, octs, pt, st):
     assert all(np.array_equal(small[b]["rows"], cands[b]["rows"]) for b in range(3))
 
 
-@pytest.mark.parametrize("n,dpx", [(512, 200), (700, 900), (2000, 400)])
-def test_fused_equals_three_kernel_path(eng, n, dpx):
+@pytest.mark.parametrize("n,dpx,octs", [(512, 200, (1.6, 3.2)), (700, 900, (1.6, 3.2)), (2000, 400, (1.6, 3.2)),
+                                        (1300, 500, (1.6, 3.2, 6.4, 12.8)), (640, 700, (1.6, 3.2, 6.4, 12.8))])
+def test_fused_equals_three_kernel_path(eng, n, dpx, octs):
     """khs_kernel (axis-1 + DoG + scoring fused, DoG levels in shared memory) against kh_kernel + ks_kernel: records and
     coordinates, responses and scales bit for bit, p-values to 1e-12 (the two kernels sum |L| for the exponential fit in a
     different order), on band-limited tiles, a tile whose band is wider than the tile, and the CLI block shape."""
     tiles = [gen.band_to_dense(gen.dense_band_tile(n, min(dpx, n), seed=270 + b, blob_seed=280 + b, nblobs=20, missing=0.1 * b), n)
              for b in range(2)]
-    _set(eng, [1.6, 3.2])
+    _set(eng, list(octs))                                 # two octaves: 64-column tiles; four: 128-column tiles, one CTA per SM
     out = {}
     for fused in (True, False):
         eng.set_fusion(fused)

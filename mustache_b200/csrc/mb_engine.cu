@@ -808,6 +808,8 @@ int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int6
     double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
     // Row i of the band starts at tile[i*ld + i + 4]: a pitched copy with source pitch (ld+1) moves exactly the band.
     // Rows whose band segment would run past the end of the host array are copied one by one, clipped.
+    // rows near the bottom of the tile are clipped below: the slot may hold an older tile there
+    CU(e, cudaMemsetAsync(rawb, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));
     const int64_t total = (int64_t)(e->n - 1) * ld + e->n;                 // elements addressable in the host tile
     int64_t safe_rows = (total - 4 - e->wc) / (ld + 1) + 1;               // rows i with i*(ld+1) + 4 + wc <= total
     safe_rows = std::max<int64_t>(0, std::min<int64_t>(safe_rows, e->n));

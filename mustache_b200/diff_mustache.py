@@ -90,17 +90,19 @@ def diff_mustache(c1, c2, chromosome, chromosome2, res, start, end, mask_size, d
     d = np.subtract.outer(np.arange(n), np.arange(n)) * -1
     masks = []
     for c in (c1, c2):
-        r, cc = np.nonzero((c != 0) & (d >= 4))
+        nzmask = (c != 0) & (d >= 4)
+        if (nzmask & (d > distance_in_px + 1)).any():
+            raise ValueError("tile holds contacts beyond distance_in_px + 1 diagonals; not supported by the banded engine")
+        r, cc = np.nonzero(nzmask)
         masks.append((r, cc, c[r, cc]))
     if any(len(m[0]) < 50 for m in masks):
         return [], [], [], []
     eng = get_engine()
     _set_octaves_diff(eng, octave_values)
-    eng.configure(n, distance_in_px, 2)
-    eng.upload_dense(0, np.ascontiguousarray(c1, dtype=np.float64))
-    eng.upload_dense(1, np.ascontiguousarray(c2, dtype=np.float64))
-    eng.run_differential()
-    recs = [eng.records(0, pair=True), eng.records(1, pair=True)]
+    from . import blockrun
+    task = blockrun.BlockTask(0, 0, [(m[0], m[1], np.ascontiguousarray(m[2], dtype=np.float64)) for m in masks])
+    (_, recs), = blockrun.run_batches(eng, [task], n, distance_in_px, differential=True)
+    assert [r["nz_count"] for r in recs] == [len(m[0]) for m in masks]
     for c in (c1, c2):
         c[d <= 4] = 2
         c[d >= distance_in_px + 1] = 2

@@ -265,10 +265,12 @@ class ScaleSpaceEngine:
             self._chk(self.lib.mb200_upload_dense_dev(self.h, int(block), C.c_void_p(tile.data_ptr()), int(tile.stride(0))))
             return
         assert tile.dtype == np.float64 and tile.ndim == 2 and tile.strides[1] == 8
+        self._keep.append(tile)                               # the copy is asynchronous: the host buffer must outlive it
         self._chk(self.lib.mb200_upload_dense_host(self.h, int(block), C.c_void_p(tile.ctypes.data), tile.strides[0] // 8))
 
     def upload_band(self, block, band):
         assert band.dtype == np.float64 and band.ndim == 2 and band.strides[1] == 8 and band.shape[0] == self.n
+        self._keep.append(band)
         self._chk(self.lib.mb200_upload_band_host(self.h, int(block), C.c_void_p(band.ctypes.data), band.strides[0] // 8))
 
     def run(self, sync=False):

@@ -25,11 +25,12 @@ _DIFF_KEY = {}
 
 
 def _set_octaves_diff(eng, octave_values):
+    from . import mustache as _m
     key = tuple(float(o) for o in octave_values)
-    if _DIFF_KEY.get(id(eng)) != key:
+    # the difference chain must belong to the main chain the engine holds NOW (mustache() may have re-programmed it)
+    if _DIFF_KEY.get(id(eng)) != key or _m._PROGRAM_KEY.get(id(eng)) != key:
         eng.set_octaves(key, differential=True)
         _DIFF_KEY[id(eng)] = key
-        from . import mustache as _m
         _m._PROGRAM_KEY[id(eng)] = key
 
 

@@ -20,7 +20,7 @@ DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over 
            are independent; `wall_ms_per_step` is the host clock around the same region).
 `e2e`    : same metric through the public API with HOST buffers, the sequence the CLI runs: host -> device upload of every
            tile (dense pinned tile for config 2, block COO for the chromosome configs), all kernels, BH + `o < pt` + sparsity
-           filter on the device, device -> host read of the selected candidates (config 5: of both maps' records), and for
+           filter on the device, device -> host read of the selected candidates, and for
            N > 1 the gather of the per-block result rows on the rank that writes the TSV.
 `--impl reference` times the UNMODIFIED reference (baseline/_ref, mustache.py:697-778 up to the intercepted
 multipletests call) on all host cores over a bounded sample of the same workload; when baseline/_ref is absent, the
@@ -386,11 +386,10 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     def e2e_step():
         run()
         upload()
-        if nmaps == 2:                                   # differential selection needs both maps' full records on the host
-            recs = eng.records_batch(sort=False, pair=True)
-        else:                                            # the CLI's path: BH + o < pt + sparsity filter on the device
-            eng.select_candidates(0.1, 0.88)
-            recs = eng.candidates_batch()
+        # the CLI's path: BH + o < pt + sparsity filter on the device, only the selected candidates (with the neighbourhoods
+        # the clustering and, for config 5, the differential selection read) come back
+        eng.select_candidates(0.05 if nmaps == 2 else 0.1, 0.88)
+        recs = eng.candidates_batch(pair=(nmaps == 2))
         rows = np.array([[rank, b, r["n_found"], r["nz_count"]] for b, r in enumerate(recs)], dtype=np.float64).reshape(-1, 4)
         got = sharding.gather_loops(rows, rank, world, dev) if world > 1 else rows
         return recs, got
@@ -409,13 +408,10 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     total_found = h.sum_over_ranks(n_found)
     if rank == 0:
         assert int(got[:, 2].sum()) == int(total_found), "rank 0 did not receive every block's result row"
-    if nmaps == 2:
-        d2h = n_found * 44 + nblk * 16                   # rows, cols, score id (int32), v, p, sigma, pPair (float64) + counters
-        post_ms, n_cand = None, None
-    else:
-        n_cand = int(sum(len(r["rows"]) for r in recs))
-        d2h = n_cand * (4 * 4 + 3 * 8 + 18 * 8) + nblk * 16 + 8      # block, row, col, flags; q, sigma, cval; o9, so9
-        post_ms = eng.post_ms()
+    n_cand = int(sum(len(r["rows"]) for r in recs))
+    # block, row, col, flags; q, sigma, cval; o9, so9 (+ pair9, vself9, vother9 for the differential path); counters
+    d2h = n_cand * (4 * 4 + 3 * 8 + (45 if nmaps == 2 else 18) * 8) + nblk * 16 + 8
+    post_ms = eng.post_ms()
     out.update(e2e_ms=e2e_ms, e2e_value=bins_all / (e2e_ms * 1e-3), h2d=int(h.sum_over_ranks(h2d)),
                d2h=int(h.sum_over_ranks(d2h)), n_found=int(total_found), post_ms=post_ms,
                n_candidates=None if n_cand is None else int(h.sum_over_ranks(n_cand)))

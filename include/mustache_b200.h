@@ -119,10 +119,14 @@ MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, voi
  * of the dense `o` and `so` matrices (:789-795; row-major, 1 off the mask, 2 / 1 on the mask but never updated), which is all
  * the clustering step (:830-848) reads.  candidate_fraction: capacity as a fraction of the batch's found records (<= 0: 1/16);
  * mb200_fetch_candidates returns MB200_ERR_CAPACITY when it was exceeded.  Order of the entries is unspecified.
- * mb200_fetch_q: q of every record of a block in the order of mb200_fetch_records (parity hook). */
+ * mb200_fetch_q: q of every record of a block in the order of mb200_fetch_records (parity hook).
+ * After mb200_run_differential (blocks 2k / 2k+1 = the two maps of pair k) three more neighbourhoods are available per
+ * selected pixel, those the differential selection reads (diff_mustache.py:445-453, 567-568): `pair` and `v` of its own map
+ * and `v` of the other map (1 off that map's mask, pPair / vAll where found, 2 / 0 on the mask but never updated); NULL skips. */
 MB200_API int mb200_select_candidates(mb200_engine* e, double pt, double st, double candidate_fraction);
 MB200_API int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, int32_t* row, int32_t* col, int32_t* flags,
-                                     double* q, double* sigma, double* cval, double* o9, double* so9, int64_t* n_out);
+                                     double* q, double* sigma, double* cval, double* o9, double* so9, double* pair9,
+                                     double* vself9, double* vother9, int64_t* n_out);
 MB200_API int mb200_fetch_q(mb200_engine* e, int block, int64_t capacity, double* q, int64_t* n_out);
 MB200_API int mb200_last_post_ms(mb200_engine* e, float* ms);
 

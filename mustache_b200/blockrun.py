@@ -105,7 +105,7 @@ def run_batches(eng, tasks, chunk, dpx, differential=False, verbose=False, timin
             try:
                 if select is not None:
                     eng.select_candidates(*select)
-                    recs = eng.candidates_batch()
+                    recs = eng.candidates_batch(pair=differential)
                 else:
                     recs = eng.records_batch(pair=differential)
                 break

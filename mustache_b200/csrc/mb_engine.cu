@@ -50,7 +50,8 @@ struct mb200_engine {
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
         nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist,
-        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot;
+        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot, cd_pair9, cd_vs9, cd_vo9;
+    bool post_diff = false;
     long long cand_cap = 0;
     bool post_done = false;
     cudaEvent_t ev_post0 = nullptr, ev_post1 = nullptr;
@@ -462,7 +463,7 @@ void mb200_destroy(mb200_engine* e) {
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
                      &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
                      &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
-                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot};
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -1095,6 +1096,12 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     if ((st = ensure(e, e->cd_so9, cc * 9 * sizeof(double)))) return st;
     if ((st = ensure(e, e->cd_count, sizeof(unsigned long long)))) return st;
     if ((st = ensure(e, e->cd_slot, cc * sizeof(int)))) return st;
+    e->post_diff = e->ran_diff;
+    if (e->post_diff) {
+        if ((st = ensure(e, e->cd_pair9, cc * 9 * sizeof(double)))) return st;
+        if ((st = ensure(e, e->cd_vs9, cc * 9 * sizeof(double)))) return st;
+        if ((st = ensure(e, e->cd_vo9, cc * 9 * sizeof(double)))) return st;
+    }
     CU(e, cudaEventRecord(e->ev_post0, sq));
     const unsigned long long* cnt = (const unsigned long long*)e->rec_count.p;
     const int gx = B >= 8 ? 16 : 148 * 2;
@@ -1115,11 +1122,13 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
                                                      (int*)e->slotmap.p);
     PostOut po = {(int*)e->cd_block.p, (int*)e->cd_row.p, (int*)e->cd_col.p, (int*)e->cd_flags.p, (double*)e->cd_q.p,
                   (double*)e->cd_sigma.p, (double*)e->cd_cval.p, (double*)e->cd_o9.p, (double*)e->cd_so9.p,
-                  (unsigned long long*)e->cd_count.p, e->cand_cap};
+                  e->post_diff ? (double*)e->cd_pair9.p : nullptr, e->post_diff ? (double*)e->cd_vs9.p : nullptr,
+                  e->post_diff ? (double*)e->cd_vo9.p : nullptr, (unsigned long long*)e->cd_count.p, e->cand_cap};
     post_select_kernel<<<dim3(gx, B), 256, 0, sq>>>(cnt, e->rec_cap, (const double*)e->rec_q.p, pt, po, (int*)e->cd_slot.p);
     post_candidates_kernel<<<148 * 4, 256, 0, sq>>>(
         e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p, (const double*)e->rec_q.p, (const double*)e->rec_sigma.p,
-        raw_slot(e, e->slot_run), (const int*)e->slotmap.p, (const int*)e->cd_slot.p, e->n, e->wc, e->dhi, e->dpx, st_thr, po);
+        (const double*)e->rec_v.p, (const double*)e->rec_pair.p, raw_slot(e, e->slot_run), (const int*)e->slotmap.p,
+        (const int*)e->cd_slot.p, e->n, e->wc, e->dhi, e->dpx, st_thr, po);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_post1, sq));
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));          // the candidate kernel reads the tile slot too
@@ -1129,7 +1138,8 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
 }
 
 int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, int32_t* row, int32_t* col, int32_t* flags, double* q,
-                           double* sigma, double* cval, double* o9, double* so9, int64_t* n_out) {
+                           double* sigma, double* cval, double* o9, double* so9, double* pair9, double* vself9, double* vother9,
+                           int64_t* n_out) {
     if (!e) return MB200_ERR_ARG;
     if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
     int st = use_device(e);
@@ -1158,6 +1168,12 @@ int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, in
     if (cval) CU(e, cudaMemcpyAsync(cval, e->cd_cval.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (o9) CU(e, cudaMemcpyAsync(o9, e->cd_o9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (so9) CU(e, cudaMemcpyAsync(so9, e->cd_so9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (pair9 || vself9 || vother9) {
+        if (!e->post_diff) return fail(e, MB200_ERR_ARG, "the batch was not run with mb200_run_differential");
+        if (pair9) CU(e, cudaMemcpyAsync(pair9, e->cd_pair9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (vself9) CU(e, cudaMemcpyAsync(vself9, e->cd_vs9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (vother9) CU(e, cudaMemcpyAsync(vother9, e->cd_vo9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    }
     CU(e, cudaStreamSynchronize(e->stream));
     return MB200_OK;
 }

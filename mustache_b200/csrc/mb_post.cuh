@@ -137,6 +137,9 @@ struct PostOut {
     double* cval;          // value of the pixel in the 2-filled tile (mustache.py:703-706)
     double* o9;            // [cand][9] dense `o` over the 3 x 3 neighbourhood, row-major
     double* so9;           // [cand][9] dense `so`
+    double* pair9;         // differential runs only (else nullptr): [cand][9] dense `pair` of the candidate's own map,
+    double* vself9;        //   `v` of its own map and `v` of the other map of the block pair (diff_mustache.py:445-453):
+    double* vother9;       //   1 off that map's mask, pPair / vAll where found, 2 / 0 on the mask but never updated
     unsigned long long* count;     // candidates emitted (may exceed cap: only cap are written)
     long long cap;
 };
@@ -178,9 +181,9 @@ post_select_kernel(const unsigned long long* __restrict__ rec_count, long long r
 // one warp per selected record: sparsity filter, neighbourhood patches
 __global__ void __launch_bounds__(256)
 post_candidates_kernel(long long rec_cap, const int* __restrict__ rec_row, const int* __restrict__ rec_col,
-                       const double* __restrict__ rec_q, const double* __restrict__ rec_sigma, const double* __restrict__ raw,
-                       const int* __restrict__ slot, const int* __restrict__ cand_slot, int n, int wc, int dhi, int dpx, double st,
-                       PostOut out) {
+                       const double* __restrict__ rec_q, const double* __restrict__ rec_sigma, const double* __restrict__ rec_v,
+                       const double* __restrict__ rec_pair, const double* __restrict__ raw, const int* __restrict__ slot,
+                       const int* __restrict__ cand_slot, int n, int wc, int dhi, int dpx, double st, PostOut out) {
     const int lane = threadIdx.x & 31;
     unsigned long long total = *out.count;
     if (total > (unsigned long long)out.cap) total = out.cap;
@@ -227,6 +230,25 @@ post_candidates_kernel(long long rec_cap, const int* __restrict__ rec_row, const
             }
             out.o9[pos * 9 + lane] = ov;
             out.so9[pos * 9 + lane] = sv;
+            if (out.pair9 != nullptr) {                           // blocks 2k / 2k+1 are the two maps of pair k
+                const int bo = b ^ 1;
+                const double* rawo = raw + (size_t)bo * n * wc;
+                const int* sloto = slot + (size_t)bo * n * wc;
+                double pv = 1.0, vs = 1.0, vo = 1.0;              // np.ones_like off the masks
+                const bool inside = rr >= 0 && rr < n && cc >= 0 && cc < n && d >= 4 && d <= dhi;
+                if (inside && rawb[(size_t)rr * wc + (d - 4)] != 0.0) {
+                    const int sl = slotb[(size_t)rr * wc + (d - 4)];
+                    pv = sl >= 0 ? rec_pair[(size_t)b * rec_cap + sl] : 2.0;          // pPair initialised to 2 (:290)
+                    vs = sl >= 0 ? rec_v[(size_t)b * rec_cap + sl] : 0.0;             // vAll initialised to 0 (:292)
+                }
+                if (inside && rawo[(size_t)rr * wc + (d - 4)] != 0.0) {
+                    const int sl = sloto[(size_t)rr * wc + (d - 4)];
+                    vo = sl >= 0 ? rec_v[(size_t)bo * rec_cap + sl] : 0.0;
+                }
+                out.pair9[pos * 9 + lane] = pv;
+                out.vself9[pos * 9 + lane] = vs;
+                out.vother9[pos * 9 + lane] = vo;
+            }
         }
     }
 }

@@ -83,6 +83,25 @@ def select_differential(n, dpx, start, masks, recs, st, pt, pt2):
     return outs[0], diffs[0], outs[1], diffs[1]
 
 
+def select_differential_from_candidates(n, dpx, start, masks, cands, pt2):
+    """diff_mustache.py:428-569 for one block pair when the device already did BH, `o < pt` and the sparsity filter per map
+    (mb200_select_candidates after mb200_run_differential): cands = the two entries of candidates_batch(pair=True)."""
+    if any(len(m[0]) < 50 for m in masks):                              # diff_mustache.py:266-267
+        return [], [], [], []
+    if any(len(m[0]) < postprocess.MIN_MASK_FOR_BH for m in masks):      # diff_mustache.py:430-431
+        return [], [], [], []
+    outs = []
+    for m, c in zip(masks, cands):
+        loops, vals, emptied = postprocess.call_loops_from_candidates(n, dpx, start, m[0], m[1], m[2], c,
+                                                                      extra=("pair9", "vself9", "vother9"))
+        if emptied:                                                      # diff_mustache.py:507-508, 519-520, 526-527
+            return [], [], [], []
+        outs.append((loops, vals))
+    diffs = [[l for l, v in zip(loops, vals) if v["pair9"] < pt2 and v["vself9"] > v["vother9"]]     # diff_mustache.py:567-568
+             for loops, vals in outs]
+    return outs[0][0], diffs[0], outs[1][0], diffs[1]
+
+
 def diff_mustache(c1, c2, chromosome, chromosome2, res, start, end, mask_size, distance_in_px, octave_values, st, pt, pt2):
     """Same contract as the reference's diff_mustache() (diff_mustache.py:260-569) for one pair of dense tiles."""
     if chromosome != chromosome2:
@@ -102,20 +121,20 @@ def diff_mustache(c1, c2, chromosome, chromosome2, res, start, end, mask_size, d
     _set_octaves_diff(eng, octave_values)
     from . import blockrun
     task = blockrun.BlockTask(0, 0, [(m[0], m[1], np.ascontiguousarray(m[2], dtype=np.float64)) for m in masks])
-    (_, recs), = blockrun.run_batches(eng, [task], n, distance_in_px, differential=True)
-    assert [r["nz_count"] for r in recs] == [len(m[0]) for m in masks]
+    (_, cands), = blockrun.run_batches(eng, [task], n, distance_in_px, differential=True, select=(pt, st))
+    assert [r["nz_count"] for r in cands] == [len(m[0]) for m in masks]
     for c in (c1, c2):
         c[d <= 4] = 2
         c[d >= distance_in_px + 1] = 2
-    return select_differential(n, distance_in_px, start, masks, recs, st, pt, pt2)
+    return select_differential_from_candidates(n, distance_in_px, start, masks, cands, pt2)
 
 
 def _pair_calls(dpx, st, pt, pt2):
     """Selection of one block pair where it was computed (diff_mustache.py:428-569): calls carry the tag of the output
     they belong to, 1/2/3/4 = loops1 / diffloops1 / loops2 / diffloops2 (diff_mustache.py:704-715)."""
-    def fn(task, recs, chunk, start):
+    def fn(task, cands, chunk, start):
         out = []
-        for tag, loops in zip((1, 2, 3, 4), select_differential(chunk, dpx, start, task.maps, recs, st, pt, pt2)):
+        for tag, loops in zip((1, 2, 3, 4), select_differential_from_candidates(chunk, dpx, start, task.maps, cands, pt2)):
             out += [[l[0], l[1], l[2], l[3], tag] for l in loops]
         return out
     return fn
@@ -129,7 +148,7 @@ def call_chromosome_pairs(preps, n_chrom, dpx, octave_values, st, pt, pt2, verbo
     eng = get_engine()
     _set_octaves_diff(eng, octave_values)
     return blockrun.shard_and_call(preps, n_chrom, dpx, 2, eng, _pair_calls(dpx, st, pt, pt2), rank=rank, world=world,
-                                   verbose=verbose, owners=owners, width=5)
+                                   verbose=verbose, owners=owners, width=5, select=(pt, st))
 
 
 def call_block_pairs(xyv1, xyv2, n, dpx, octave_values, st, pt, pt2, verbose=True, rank=0, world=1):

@@ -43,7 +43,8 @@ SIGNATURES = {
     "mb200_fetch_packed": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _f64p, _f64p]),
     "mb200_packed_device": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 8),
     "mb200_select_candidates": (C.c_int, [_H, C.c_double, C.c_double, C.c_double]),
-    "mb200_fetch_candidates": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, _i64p]),
+    "mb200_fetch_candidates": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p,
+                                         _f64p, _f64p, _i64p]),
     "mb200_fetch_q": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
     "mb200_last_post_ms": (C.c_int, [_H, _f32p]),
     "mb200_set_arithmetic": (C.c_int, [_H, C.c_int]),
@@ -373,33 +374,40 @@ class ScaleSpaceEngine:
         self._post_args = (float(pt), float(st))
         self._chk(self.lib.mb200_select_candidates(self.h, float(pt), float(st), float(candidate_fraction)))
 
-    def candidates_batch(self):
+    def candidates_batch(self, pair=False):
         """One dict per block: rows, cols, q, sigma, cval, keep (sparsity filter passed), o9 / so9 ([m, 9] neighbourhoods of
-        the dense o / so matrices), nz_count, n_found; entries sorted row-major.  Only the selected pixels (q < pt) cross
-        the bus; a capacity overflow re-runs the selection with room for every record."""
+        the dense o / so matrices), nz_count, n_found; entries sorted row-major.  pair=True (after run_differential): also
+        pair9 / vself9 / vother9, the neighbourhoods the differential selection reads.  Only the selected pixels (q < pt)
+        cross the bus; a capacity overflow re-runs the selection with room for every record."""
         n_out = C.c_int64(0)
-        st = self.lib.mb200_fetch_candidates(self.h, 0, None, None, None, None, None, None, None, None, None, C.byref(n_out))
+        nul = [None] * 12
+        st = self.lib.mb200_fetch_candidates(self.h, 0, *nul, C.byref(n_out))
         if st == -3 and n_out.value > 0 and "candidates" in self.lib.mb200_last_error(self.h).decode():
             self._chk(self.lib.mb200_select_candidates(self.h, self._post_args[0], self._post_args[1], 1.0))
-            st = self.lib.mb200_fetch_candidates(self.h, 0, None, None, None, None, None, None, None, None, None, C.byref(n_out))
+            st = self.lib.mb200_fetch_candidates(self.h, 0, *nul, C.byref(n_out))
         self._chk(st)
         m = n_out.value
         blk, rows, cols, flg = (self._pinned("c_" + k, m, np.int32) for k in ("blk", "rows", "cols", "flg"))
         q, sg, cv = (self._pinned("c_" + k, m, np.float64) for k in ("q", "sg", "cv"))
         o9, so9 = (self._pinned("c_" + k, 9 * m, np.float64) for k in ("o9", "so9"))
+        extra = [self._pinned("c_" + k, 9 * m, np.float64) for k in ("pair9", "vs9", "vo9")] if pair else []
         self._chk(self.lib.mb200_fetch_candidates(self.h, m, _ptr(blk, _i32p), _ptr(rows, _i32p), _ptr(cols, _i32p), _ptr(flg, _i32p),
                                                   _ptr(q, _f64p), _ptr(sg, _f64p), _ptr(cv, _f64p), _ptr(o9, _f64p), _ptr(so9, _f64p),
-                                                  C.byref(n_out)))
+                                                  *([_ptr(a, _f64p) for a in extra] if pair else [None, None, None]), C.byref(n_out)))
         nz, nf = self.batch_counts()
         order = np.lexsort((cols, rows, blk))
         blk, rows, cols, flg, q, sg, cv = (a[order] for a in (blk, rows, cols, flg, q, sg, cv))
         o9, so9 = o9.reshape(-1, 9)[order], so9.reshape(-1, 9)[order]
+        extra = [a.reshape(-1, 9)[order] for a in extra]
         bounds = np.searchsorted(blk, np.arange(self.nblocks + 1))
         out = []
         for b in range(self.nblocks):
             a, z = int(bounds[b]), int(bounds[b + 1])
-            out.append(dict(rows=rows[a:z], cols=cols[a:z], q=q[a:z], sigma=sg[a:z], cval=cv[a:z], keep=flg[a:z] != 0,
-                            o9=o9[a:z], so9=so9[a:z], nz_count=int(nz[b]), n_found=int(nf[b])))
+            d = dict(rows=rows[a:z], cols=cols[a:z], q=q[a:z], sigma=sg[a:z], cval=cv[a:z], keep=flg[a:z] != 0,
+                     o9=o9[a:z], so9=so9[a:z], nz_count=int(nz[b]), n_found=int(nf[b]))
+            if pair:
+                d.update(pair9=extra[0][a:z], vself9=extra[1][a:z], vother9=extra[2][a:z])
+            out.append(d)
         return out
 
     def q_values(self, block, sort=True):

@@ -210,18 +210,23 @@ def call_loops(n, dpx, start, mask_rows, mask_cols, mask_vals, rec_rows, rec_col
     return loops, aux
 
 
-def call_loops_from_candidates(n, dpx, start, mask_rows, mask_cols, mask_vals, cand, intra=True):
+def call_loops_from_candidates(n, dpx, start, mask_rows, mask_cols, mask_vals, cand, intra=True, extra=None):
     """The rest of mustache.py:774-850 for one block when the device already did BH, the `o < pt` cut and the sparsity
     filter (mb200_select_candidates): `cand` is one entry of ScaleSpaceEngine.candidates_batch().  Enrichment filter
     (:816-828) from the block's mask pixels, clustering (:830-848) from the candidates' 3 x 3 neighbourhoods of `o` / `so`.
-    Same loops as call_loops() on the full record list."""
+    Same loops as call_loops() on the full record list.  extra: names of further [m, 9] neighbourhood arrays of `cand`
+    (pair9, vself9, vother9 of a differential run); the function then returns (loops, [{name: value at the loop}], emptied)
+    where `emptied` tells that a filter left nothing (diff_mustache.py:507-527 abandons the whole block pair then)."""
+    def done(loops, vals=(), emptied=False):
+        return loops if extra is None else (loops, list(vals), emptied)
     if len(mask_rows) < MIN_MASK_FOR_BH:                     # mustache.py:775: `len(pFound)` is the MASK size
-        return []
+        return done([])
     keep = cand["keep"]
     x, y = cand["rows"][keep].astype(np.int64), cand["cols"][keep].astype(np.int64)
     if len(x) == 0:
-        return []
+        return done([], emptied=True)
     o9, so9 = cand["o9"][keep], cand["so9"][keep]
+    more = {k: cand[k][keep] for k in (extra or ())}
     if intra:
         d = y - x
         means = diagonal_means(np.asarray(mask_rows), np.asarray(mask_cols), np.asarray(mask_vals), dpx, d, intra)
@@ -229,16 +234,20 @@ def call_loops_from_candidates(n, dpx, start, mask_rows, mask_cols, mask_vals, c
         with np.errstate(invalid="ignore"):
             passing = cand["cval"][keep] > 2 * mvec
         if passing.sum() == 0:
-            return []
+            return done([], emptied=True)
         x, y, o9, so9 = x[passing], y[passing], o9[passing], so9[passing]
-    o_at, so_at = {}, {}
-    for a, b, ov, sv in zip(x.tolist(), y.tolist(), o9, so9):
+        more = {k: v[passing] for k, v in more.items()}
+    o_at, so_at, more_at = {}, {}, {k: {} for k in more}
+    for i, (a, b, ov, sv) in enumerate(zip(x.tolist(), y.tolist(), o9, so9)):
         for k in range(9):
             key = (a + k // 3 - 1, b + k % 3 - 1)
             o_at[key] = ov[k]
             so_at[key] = sv[k]
+            for name, arr in more.items():
+                more_at[name][key] = arr[i, k]
 
     def o_of(r, c):
         return np.array([o_at[(int(a), int(b))] for a, b in zip(r, c)])
     reps = cluster_representatives(x, y, o_of)
-    return [[a + start, b + start, float(o_at[(a, b)]), float(so_at[(a, b)])] for a, b in reps]
+    loops = [[a + start, b + start, float(o_at[(a, b)]), float(so_at[(a, b)])] for a, b in reps]
+    return done(loops, [{name: float(more_at[name][(a, b)]) for name in more} for a, b in reps])

@@ -70,47 +70,79 @@ class OracleEngine:
     def select_candidates(self, pt, st, candidate_fraction=-1.0):
         self.post = (pt, st)
 
-    def candidates_batch(self):
-        """What mb200_select_candidates + mb200_fetch_candidates deliver, restated densely on the oracle's output
-        (mustache.py:774-811 literally: BH, o < pt, numpy-slice sparsity windows, dense o / so neighbourhoods)."""
-        from mustache_b200.engine import EngineError
+    def _dense_candidates(self, c, nz, filled, st, pt, sthr, other=None):
+        """Dense restatement of mustache.py:774-811 (and diff_mustache.py:428-500) for one map: BH, o < pt, numpy-slice
+        sparsity windows, 3 x 3 neighbourhoods of the dense o / so (/ pair / v / v of the other map) matrices."""
         from oracle import postprocess as opost
+        found = st["p"] != 2
+        p_all = st["p"].copy()
+        p_all[found] = opost.bh_statsmodels_form(st["p"][found])
+        n = c.shape[0]
+
+        def dense(mask, vals, fill=1.0):
+            m = np.full((n + 2, n + 2), fill)                 # one-pixel apron of "off the tile" = 1
+            m[1:-1, 1:-1][mask] = vals
+            return m
+        o, so = dense(nz, p_all), dense(nz, st["scale"])
+        sel = found & (p_all < pt)
+        x, y, sc = st["rows"][sel], st["cols"][sel], st["scale"][sel]
+        keep = x != 0
+        for i in range(len(x)):
+            s = int(np.ceil(sc[i]))
+            c1 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
+            s *= 2
+            c2 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
+            if c1 < sthr or c2 < 0.6:
+                keep[i] = False
+
+        def patches(m):
+            return np.array([m[a:a + 3, bb:bb + 3].ravel() for a, bb in zip(x, y)]).reshape(-1, 9)
+        out = dict(rows=x.astype(np.int32), cols=y.astype(np.int32), q=p_all[sel], sigma=sc, cval=filled[x, y], keep=keep,
+                   o9=patches(o), so9=patches(so), nz_count=int(nz.sum()), n_found=int(found.sum()))
+        if other is not None:
+            nz_o, st_o = other
+            out.update(pair9=patches(dense(nz, st["pair"])), vself9=patches(dense(nz, st["v"])),
+                       vother9=patches(dense(nz_o, st_o["v"])))
+        return out
+
+    @staticmethod
+    def _no_candidates(nz_count, pair):
+        e = np.zeros(0)
+        d = dict(rows=e.astype(np.int32), cols=e.astype(np.int32), q=e, sigma=e, cval=e, keep=e.astype(bool),
+                 o9=np.zeros((0, 9)), so9=np.zeros((0, 9)), nz_count=nz_count, n_found=0)
+        if pair:
+            d.update(pair9=np.zeros((0, 9)), vself9=np.zeros((0, 9)), vother9=np.zeros((0, 9)))
+        return d
+
+    def candidates_batch(self, pair=False):
+        """What mb200_select_candidates + mb200_fetch_candidates deliver, restated densely on the oracle's output."""
+        from mustache_b200.engine import EngineError
         from oracle import scalespace as osc
         if self.capacity_errors > 0:
             self.capacity_errors -= 1
             raise EngineError(-3, "block 0 produced too many records")
-        pt, st = self.post
+        pt, sthr = self.post
         out = []
-        for b in range(self.nblocks):
-            c = self.tiles[b]
-            res = osc.scale_space(c, self.dpx, self.octs, use_scipy=True)
+        if not self.diff:
+            for b in range(self.nblocks):
+                c = self.tiles[b]
+                res = osc.scale_space(c, self.dpx, self.octs, use_scipy=True)
+                if res["skipped"]:
+                    out.append(self._no_candidates(res["nz_count"], False))
+                    continue
+                nz, filled = osc.mask_and_fill(c, self.dpx)
+                out.append(self._dense_candidates(c, nz, filled, res, pt, sthr))
+            return out
+        for k in range(self.nblocks // 2):
+            c1, c2 = self.tiles[2 * k], self.tiles[2 * k + 1]
+            res = osc.scale_space_diff(c1, c2, self.dpx, self.octs, use_scipy=True)
             if res["skipped"]:
-                e = np.zeros(0)
-                out.append(dict(rows=e.astype(np.int32), cols=e.astype(np.int32), q=e, sigma=e, cval=e, keep=e.astype(bool),
-                                o9=np.zeros((0, 9)), so9=np.zeros((0, 9)), nz_count=res["nz_count"], n_found=0))
+                out += [self._no_candidates(res["nz1_count"], True), self._no_candidates(res["nz2_count"], True)]
                 continue
-            nz, filled = osc.mask_and_fill(c, self.dpx)
-            found = res["p"] != 2
-            p_all = res["p"].copy()
-            p_all[found] = opost.bh_statsmodels_form(res["p"][found])
-            n = c.shape[0]
-            o, so = np.ones((n + 2, n + 2)), np.ones((n + 2, n + 2))          # one-pixel apron of "off the tile" = 1
-            o[1:-1, 1:-1][nz] = p_all
-            so[1:-1, 1:-1][nz] = res["scale"]
-            sel = found & (p_all < pt)
-            x, y, sc = res["rows"][sel], res["cols"][sel], res["scale"][sel]
-            keep = x != 0
-            for i in range(len(x)):
-                s = int(np.ceil(sc[i]))
-                c1 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
-                s *= 2
-                c2 = np.sum(nz[x[i] - s:x[i] + s + 1, y[i] - s:y[i] + s + 1]) / ((2 * s + 1) ** 2)
-                if c1 < st or c2 < 0.6:
-                    keep[i] = False
-            o9 = np.array([o[a:a + 3, bb:bb + 3].ravel() for a, bb in zip(x, y)]).reshape(-1, 9)
-            so9 = np.array([so[a:a + 3, bb:bb + 3].ravel() for a, bb in zip(x, y)]).reshape(-1, 9)
-            out.append(dict(rows=x.astype(np.int32), cols=y.astype(np.int32), q=p_all[sel], sigma=sc, cval=filled[x, y], keep=keep,
-                            o9=o9, so9=so9, nz_count=res["nz_count"], n_found=int(found.sum())))
+            nz1, f1 = osc.mask_and_fill(c1, self.dpx)
+            nz2, f2 = osc.mask_and_fill(c2, self.dpx)
+            out.append(self._dense_candidates(c1, nz1, f1, res["map1"], pt, sthr, other=(nz2, res["map2"])))
+            out.append(self._dense_candidates(c2, nz2, f2, res["map2"], pt, sthr, other=(nz1, res["map1"])))
         return out
 
     def records_batch(self, sort=True, pair=False, pinned=True):

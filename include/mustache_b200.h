@@ -165,7 +165,8 @@ MB200_API int mb200_records_device(mb200_engine* e, int block, void** rows, void
 MB200_API int mb200_fetch_fits(mb200_engine* e, int block, double* loc, double* scale, int32_t* score_id, int capacity, int* n_scored);
 
 /* Device time of the last mb200_run in milliseconds (CUDA events on the engine's stream):
- * prep (mask count), axis-0 kernel, axis-1 + DoG kernel, extremum/scoring kernel, statistics + p-values, total. */
+ * prep (mask count), axis-0 kernel, axis-1 + DoG kernel, extremum/scoring kernel, statistics + p-values (after
+ * mb200_run_differential: + the difference stack and pPair), total. */
 MB200_API int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_ms, float* ks_ms, float* fin_ms,
                                 float* total_ms);
 /* Kernel launches issued by the last mb200_run. */

@@ -54,7 +54,7 @@ struct mb200_engine {
     bool post_diff = false;
     long long cand_cap = 0;
     bool post_done = false;
-    cudaEvent_t ev_post0 = nullptr, ev_post1 = nullptr;
+    cudaEvent_t ev_post0 = nullptr, ev_post1 = nullptr, ev_diff = nullptr;   // ev_diff: end of the difference-stack kernels
     float t_post = 0;
     std::vector<long long> h_offsets;
     std::vector<unsigned long long> h_nz, h_rec;
@@ -442,7 +442,7 @@ int mb200_create(int device, mb200_engine** out) {
         cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_prep) != cudaSuccess ||
         cudaEventCreate(&e->ev_end) != cudaSuccess || cudaEventCreate(&e->ev_post0) != cudaSuccess ||
-        cudaEventCreate(&e->ev_post1) != cudaSuccess) {
+        cudaEventCreate(&e->ev_post1) != cudaSuccess || cudaEventCreate(&e->ev_diff) != cudaSuccess) {
         delete e;
         return MB200_ERR_CUDA;
     }
@@ -471,6 +471,7 @@ void mb200_destroy(mb200_engine* e) {
     if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->ev_post0) cudaEventDestroy(e->ev_post0);
     if (e->ev_post1) cudaEventDestroy(e->ev_post1);
+    if (e->ev_diff) cudaEventDestroy(e->ev_diff);
     if (e->ev_up) cudaEventDestroy(e->ev_up);
     for (int k = 0; k < 2; ++k)
         if (e->ev_run[k]) cudaEventDestroy(e->ev_run[k]);
@@ -1273,11 +1274,14 @@ int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_m
         CU(e, cudaEventElapsedTime(&t, e->ev_pass[4 * p + 2], e->ev_pass[4 * p + 3]));
         ks += t;
     }
+    // a differential run ends with the difference stack (its kernels are reported with the statistics phase)
+    cudaEvent_t last = e->ran_diff ? e->ev_diff : e->ev_end;
+    CU(e, cudaEventSynchronize(last));
     CU(e, cudaEventElapsedTime(&e->t_prep, e->ev_begin, e->ev_prep));
-    CU(e, cudaEventElapsedTime(&e->t_fin, e->ev_pass[4 * (npass - 1) + 3], e->ev_end));
+    CU(e, cudaEventElapsedTime(&e->t_fin, e->ev_pass[4 * (npass - 1) + 3], last));
     e->t_ks = ks;
     if (ks_ms) *ks_ms = ks;
-    CU(e, cudaEventElapsedTime(&e->t_total, e->ev_begin, e->ev_end));
+    CU(e, cudaEventElapsedTime(&e->t_total, e->ev_begin, last));
     e->t_kv = kv;
     e->t_kh = kh;
     if (prep_ms) *prep_ms = e->t_prep;
@@ -1364,6 +1368,7 @@ int mb200_run_differential(mb200_engine* e) {
         (const double*)e->dsd.p, e->n, e->wc, ndiff, (double*)e->rec_pair.p);
     CU(e, cudaGetLastError());
     e->launches += 3;
+    CU(e, cudaEventRecord(e->ev_diff, e->stream));
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], e->stream));   // the difference kernels read the tile slot too
     e->ran_diff = true;
     return MB200_OK;

@@ -435,8 +435,12 @@ int mb200_create(int device, mb200_engine** out) {
     mb200_engine* e = new mb200_engine();
     e->device = device;
     memset(&e->prog, 0, sizeof(e->prog));
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the upload stream gets the highest priority: its small memset / scatter kernels are placed as soon as an SM has room
+    // instead of queueing behind the compute stream's large grids
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_up, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -810,8 +814,9 @@ int mb200_upload_dense_host(mb200_engine* e, int block, const double* tile, int6
     double* rawb = raw_slot(e, e->slot_up) + (size_t)block * e->n * e->wc;
     // Row i of the band starts at tile[i*ld + i + 4]: a pitched copy with source pitch (ld+1) moves exactly the band.
     // Rows whose band segment would run past the end of the host array are copied one by one, clipped.
-    // rows near the bottom of the tile are clipped below: the slot may hold an older tile there
-    CU(e, cudaMemsetAsync(rawb, 0, (size_t)e->n * e->wc * sizeof(double), e->up_stream));
+    // The band tails of the clipped rows below (columns >= n) are never written by ANY upload path (the scatter kernels
+    // check c < n), so they still hold the zeros mb200_configure put there; every other band element is overwritten here.
+    // No memset: a memset kernel queued behind the compute stream's grids would delay the copies that follow it.
     const int64_t total = (int64_t)(e->n - 1) * ld + e->n;                 // elements addressable in the host tile
     int64_t safe_rows = (total - 4 - e->wc) / (ld + 1) + 1;               // rows i with i*(ld+1) + 4 + wc <= total
     safe_rows = std::max<int64_t>(0, std::min<int64_t>(safe_rows, e->n));

@@ -8,6 +8,9 @@
 //   K_S  (ks_kernel)   zero-padded 3x3 maxima + 5-clause extremum test + running best + per-level |L| min/sum
 //                      mustache.py:740-743,757 (maximum_filter) :760-768 (test + state update)
 //   reduce / finalise  expon.fit (loc = min, scale = mean - min) and 1 - expon.cdf for the winners only   mustache.py:755-756
+//   K_HS (khs_kernel)  opt-in: K_H and K_S in one kernel, DoG levels in shared memory (mb200_set_fusion)
+// Companion headers: mb_sort.cuh (device radix sort), mb_post.cuh (BH per block, o < pt, sparsity filter: mustache.py:774-811),
+// mb_normalize.cuh (normalize_sparse, mustache.py:622-686), mb_parse.h (native text reader, mustache.py:254-263).
 //
 // Data layout in HBM ("band layout"): a block is an N x N tile but only diagonals d = j - i in [4, dhi] can hold data
 // (reader keeps |j-i| <= dpx+1, mask needs j-i >= 4), so a tile is stored as raw[i][d-4], i in [0,N), wc = dhi-3 doubles per

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256, CTAS) k(const __grid_constant__ Taps tp, 
         double acc[8];
         for (int r = 0; r < reps; ++r)
             for (int s = 0; s < nr; ++s) {
-                conv_slide<8, 1>(sm + lane * 178 + ((lane >> 3) & 1) + warp * 8 + 56, tp.R[s], tp.w[s], acc);
+                conv_slide<8, 1, false>(sm + lane * 178 + ((lane >> 3) & 1) + warp * 8 + 56, tp.R[s], tp.w[s], acc);
                 tot += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             }
     } else if (MODE == 2) {     // same, software-pipelined taps
@@ -83,11 +83,11 @@ __global__ void __launch_bounds__(256, CTAS) k(const __grid_constant__ Taps tp, 
                 double* vrow = sink + warp * (KV_K * 32) + lane;
                 const unsigned vm = pad_smem ? 0xfu : 0x7u;
                 switch (gr.n) {
-                    case 1: kv_group<1>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
-                    case 2: kv_group<2>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
-                    case 3: kv_group<3>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
-                    case 4: kv_group<4>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
-                    default: kv_group<5>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
+                    case 1: kv_group<1, false>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
+                    case 2: kv_group<2, false>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
+                    case 3: kv_group<3, false>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
+                    case 4: kv_group<4, false>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
+                    default: kv_group<5, false>(ctr, plan.tapsT + gr.tap_off, gr.rmax, gr.step, vrow, 8 * KV_K * 32, 32, vm); break;
                 }
             }
         tot = sink[threadIdx.x];

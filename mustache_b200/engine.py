@@ -382,9 +382,17 @@ class ScaleSpaceEngine:
         n_out = C.c_int64(0)
         nul = [None] * 12
         st = self.lib.mb200_fetch_candidates(self.h, 0, *nul, C.byref(n_out))
-        if st == -3 and n_out.value > 0 and "candidates" in self.lib.mb200_last_error(self.h).decode():
-            self._chk(self.lib.mb200_select_candidates(self.h, self._post_args[0], self._post_args[1], 1.0))
-            st = self.lib.mb200_fetch_candidates(self.h, 0, *nul, C.byref(n_out))
+        if st == -3:
+            # MB200_ERR_CAPACITY is either a block with more records than the record capacity (the caller re-runs the
+            # batch, blockrun.run_batches) or more selected pixels than the candidate capacity (re-select here, with room
+            # for every record)
+            msg = self.lib.mb200_last_error(self.h).decode()
+            _, found = self.batch_counts()
+            if n_out.value > 0 and n_out.value <= int(found.sum()):
+                self._chk(self.lib.mb200_select_candidates(self.h, self._post_args[0], self._post_args[1], 1.0))
+                st = self.lib.mb200_fetch_candidates(self.h, 0, *nul, C.byref(n_out))
+            else:
+                raise EngineError(st, msg)
         self._chk(st)
         m = n_out.value
         blk, rows, cols, flg = (self._pinned("c_" + k, m, np.int32) for k in ("blk", "rows", "cols", "flg"))

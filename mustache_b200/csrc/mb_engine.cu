@@ -50,7 +50,7 @@ struct mb200_engine {
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
         nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist,
-        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot, cd_pair9, cd_vs9, cd_vo9;
+        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot, cd_pair9, cd_vs9, cd_vo9, dpart;
     bool post_diff = false;
     long long cand_cap = 0;
     bool post_done = false;
@@ -467,7 +467,7 @@ void mb200_destroy(mb200_engine* e) {
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
                      &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
                      &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
-                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9};
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9, &e->dpart};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -1364,9 +1364,20 @@ int mb200_run_differential(mb200_engine* e) {
         g.dout = (double*)e->dout.p + (size_t)first * ndiff * tile;
         if ((st = launch_pass(e, 0, nb, &g, nullptr, &e->dprog))) return st;
     }
-    diff_stats_kernel<<<dim3(ndiff, npairs), 1024, 0, e->stream>>>(raw_slot(e, e->slot_run), (const double*)e->dout.p, e->n, e->wc,
-                                                                  npairs, (double*)e->dmu.p, (double*)e->dsd.p);
-    CU(e, cudaGetLastError());
+    {
+        const int items = ndiff * npairs;
+        if ((st = ensure(e, e->dpart, (size_t)items * (DIFF_NCH * 2 + 1) * sizeof(double)))) return st;
+        double* part = (double*)e->dpart.p;
+        double* cntv = part + (size_t)items * DIFF_NCH * 2;
+        const dim3 gp(DIFF_NCH, ndiff, npairs);
+        diff_partial_kernel<0><<<gp, 256, 0, e->stream>>>(raw_slot(e, e->slot_run), (const double*)e->dout.p, e->n, e->wc, nullptr, part);
+        diff_finish_kernel<0><<<(items + 63) / 64, 64, 0, e->stream>>>(part, items, (double*)e->dmu.p, (double*)e->dsd.p, cntv);
+        diff_partial_kernel<1><<<gp, 256, 0, e->stream>>>(raw_slot(e, e->slot_run), (const double*)e->dout.p, e->n, e->wc,
+                                                          (const double*)e->dmu.p, part);
+        diff_finish_kernel<1><<<(items + 63) / 64, 64, 0, e->stream>>>(part, items, (double*)e->dmu.p, (double*)e->dsd.p, cntv);
+        CU(e, cudaGetLastError());
+        e->launches += 3;
+    }
     diff_pair_kernel<<<dim3(32, e->nblocks), 256, 0, e->stream>>>(
         (const unsigned long long*)e->rec_count.p, e->rec_cap, (const int*)e->rec_row.p, (const int*)e->rec_col.p,
         (const int*)e->rec_sidx.p, (const int*)e->d_score_id.p, (const double*)e->dout.p, (const double*)e->dmu.p,

@@ -1403,48 +1403,79 @@ diff_tile_kernel(const double* __restrict__ raw, double* __restrict__ rawd, int 
     }
 }
 
-__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+// norm.fit over the common mask (diff_mustache.py:371): mean and population std (ddof 0), two passes.  Each pass is split
+// over DIFF_NCH CTAs per (octave, pair) -- contiguous chunks, fixed-order tree inside a CTA, partials summed in chunk order
+// by diff_finish_kernel -- so the result is deterministic and the pass runs at HBM speed instead of on 26 CTAs.
+constexpr int DIFF_NCH = 64;
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
     if (threadIdx.x < 32) {
-        t = sh[threadIdx.x];
+        t = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
         t = warp_sum(t);
-        if (threadIdx.x == 0) sh[32] = t;
+        if (threadIdx.x == 0) sh[8] = t;
     }
     __syncthreads();
-    return sh[32];
+    return sh[8];
 }
 
-// norm.fit over the common mask (diff_mustache.py:371): mean and population std, two passes, one CTA per (octave, pair).
-__global__ void __launch_bounds__(1024)
-diff_stats_kernel(const double* __restrict__ raw, const double* __restrict__ dout, int n, int wc, int npairs,
-                  double* __restrict__ mu, double* __restrict__ sd) {
-    __shared__ double sh[33];
-    const int o = blockIdx.x, pr = blockIdx.y;
+// PASS 0: partial (sum, count) of the difference DoG over the common mask; PASS 1: partial sum of squared deviations from
+// mu.  grid = (DIFF_NCH, ndiff, npairs); part[((pr * ndiff + o) * DIFF_NCH + chunk) * 2 + {0, 1}]
+template <int PASS>
+__global__ void __launch_bounds__(256)
+diff_partial_kernel(const double* __restrict__ raw, const double* __restrict__ dout, int n, int wc, const double* __restrict__ mu,
+                    double* __restrict__ part) {
+    __shared__ double sh[9];
+    const int ch = blockIdx.x, o = blockIdx.y, pr = blockIdx.z, ndiff = gridDim.y;
     const double* r1 = raw + (size_t)(2 * pr) * n * wc;
     const double* r2 = raw + (size_t)(2 * pr + 1) * n * wc;
-    const double* dd = dout + ((size_t)pr * gridDim.x + o) * n * wc;
+    const double* dd = dout + ((size_t)pr * ndiff + o) * n * wc;
     const long long total = (long long)n * wc;
+    const long long lo = total * ch / DIFF_NCH, hi = total * (ch + 1) / DIFF_NCH;
+    const double mean = PASS == 1 ? mu[(size_t)pr * ndiff + o] : 0.0;
     double s = 0.0, cnt = 0.0;
-    for (long long e = threadIdx.x; e < total; e += 1024) {
+    for (long long e = lo + threadIdx.x; e < hi; e += 256) {
         const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
-        if (i + 4 + k < n && r1[e] != 0.0 && r2[e] != 0.0) { s += dd[e]; cnt += 1.0; }
+        if (i + 4 + k < n && r1[e] != 0.0 && r2[e] != 0.0) {
+            if (PASS == 0) {
+                s = __dadd_rn(s, dd[e]);
+                cnt += 1.0;
+            } else {
+                const double t = __dsub_rn(dd[e], mean);
+                s = __dadd_rn(s, __dmul_rn(t, t));
+            }
+        }
     }
-    const double tot = block_sum_1024(s, sh);
-    const double num = block_sum_1024(cnt, sh);
-    const double mean = tot / num;
-    double q = 0.0;
-    for (long long e = threadIdx.x; e < total; e += 1024) {
-        const int i = (int)(e / wc), k = (int)(e - (long long)i * wc);
-        if (i + 4 + k < n && r1[e] != 0.0 && r2[e] != 0.0) { const double t = dd[e] - mean; q += t * t; }
-    }
-    const double ss = block_sum_1024(q, sh);
+    const double tot = block_sum_256(s, sh);
+    const double num = PASS == 0 ? block_sum_256(cnt, sh) : 0.0;
     if (threadIdx.x == 0) {
-        mu[(size_t)pr * gridDim.x + o] = mean;
-        sd[(size_t)pr * gridDim.x + o] = sqrt(ss / num);
+        double* p = part + (((size_t)pr * ndiff + o) * DIFF_NCH + ch) * 2;
+        p[0] = tot;
+        p[1] = num;
+    }
+}
+
+// PASS 0: mu = sum / count (count kept in cntv); PASS 1: sd = sqrt(sum_sq / count).  One thread per (octave, pair).
+template <int PASS>
+__global__ void __launch_bounds__(64)
+diff_finish_kernel(const double* __restrict__ part, int nitems, double* __restrict__ mu, double* __restrict__ sd,
+                   double* __restrict__ cntv) {
+    const int t = blockIdx.x * 64 + threadIdx.x;
+    if (t >= nitems) return;
+    double s = 0.0, c = 0.0;
+    for (int ch = 0; ch < DIFF_NCH; ++ch) {
+        s = __dadd_rn(s, part[((size_t)t * DIFF_NCH + ch) * 2]);
+        c = __dadd_rn(c, part[((size_t)t * DIFF_NCH + ch) * 2 + 1]);
+    }
+    if (PASS == 0) {
+        cntv[t] = c;
+        mu[t] = s / c;
+    } else {
+        sd[t] = sqrt(s / cntv[t]);
     }
 }
 

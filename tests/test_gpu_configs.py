@@ -286,6 +286,17 @@ def test_batched_coo_upload_equals_per_block(eng):
     assert ref[0]["n_found"] == 0 and ref[2]["n_found"] == 0 and ref[1]["n_found"] > 100
     for a, b in zip(ref, got):
         _equal_records(a, b)
+    # and from COO that already lives on the device (mb200_upload_coo_dev: torch tensors as device buffers)
+    import torch
+    eng.configure(n, dpx, 5)
+    for b, m in enumerate(order):
+        dev = [torch.as_tensor(np.ascontiguousarray(a, dt), device="cuda:%d" % eng.device)
+               for a, dt in zip(m, (np.int32, np.int32, np.float64))]
+        torch.cuda.synchronize()
+        eng.upload_coo_dev(b + 1, *dev)
+    eng.run()
+    for a, b in zip(ref, eng.records_batch()):
+        _equal_records(a, b)
 
 
 def _host_candidates(n, dpx, mask, rec, pt, st):

@@ -500,6 +500,7 @@ def main():
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 strong-scaling object of multi-GPU lines")
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--fusion", action="store_true", help="opt-in fused axis-1 + scoring kernel (mb200_set_fusion)")
+    ap.add_argument("--overlap", action="store_true", help="two half-batches on two streams (mb200_set_overlap)")
     ap.add_argument("--no-fast", action="store_true", help="skip the extra device-resident measurement in the opt-in FMA mode")
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
     args = ap.parse_args()
@@ -544,6 +545,9 @@ def main():
     from mustache_b200.engine import ScaleSpaceEngine
     h = Harness(rank, local_rank, world)
     eng = ScaleSpaceEngine(local_rank)
+    if args.overlap:
+        eng.set_overlap(True)
+        config["overlap"] = "two half-batches on two streams"
     if args.fusion:
         eng.set_fusion(True)
         config["fusion"] = "khs_kernel (axis-1 + DoG + scoring in one kernel)"

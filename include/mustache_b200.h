@@ -144,6 +144,11 @@ MB200_API int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add);
  * Takes effect at the next mb200_configure. */
 MB200_API int mb200_set_fusion(mb200_engine* e, int enable);
 
+/* 1: batches of two or more blocks run as two half-batches on two streams (own halves of the scratch), so that the scoring
+ * kernel of one half overlaps the Gaussian passes of the other; 0 (default): one stream.  Same results either way.  With
+ * overlap the per-kernel times of mb200_last_timing overlap too (their sum exceeds the total).  Next mb200_run. */
+MB200_API int mb200_set_overlap(mb200_engine* e, int enable);
+
 /* Upper bound on the blocks one pass of the kernels handles (0 = as many as fit in device memory, the default).  The
  * reference's analogue is `-p`, the number of block processes alive at a time (mustache.py:931-934).  Takes effect at the
  * next mb200_configure. */

@@ -46,6 +46,7 @@ struct mb200_engine {
     int n = 0, dpx = 0, intra = 1, dhi = 0, wc = 0, vlo = 0, wv = 0, wl = 0, nblocks = 0, pass_blocks = 0;
     long long rec_cap = 0;
     int ncta_h = 0;
+    int npass_run = 1;                // passes of the last mb200_run
     DevBuf raw, V, Lb, part_min, part_sum, rec_count, nz_count, nonfinite, rec_row, rec_col, rec_v, rec_sidx, rec_p,
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
@@ -71,6 +72,10 @@ struct mb200_engine {
     MbTensorMaps dtmaps;             // difference chain (V boxes follow its radii)
     DevBuf d_tmaps, d_dtmaps;        // device copies the kernels read the descriptors from
     long long plane_v = 0, plane_l = 0;
+    int overlap = 0;                 // mb200_set_overlap: 1 = two passes in flight on two streams (scoring of one half of the
+                                     // batch overlaps the Gaussian passes of the other half)
+    cudaStream_t stream2 = nullptr;  // second compute stream of the overlapped mode
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int fusion = 0;                  // mb200_set_fusion: 1 = axis-1 + scoring fused (khs_kernel) whenever the chain fits, 0 = never
     int fast = 0;                    // mb200_set_arithmetic: 0 = the reference's multiply-then-add, 1 = fused multiply-add
     int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
@@ -105,6 +110,7 @@ int ensure(mb200_engine* e, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return MB200_OK;
     if (b.p) {
         CU(e, cudaStreamSynchronize(e->stream));
+        if (e->stream2) CU(e, cudaStreamSynchronize(e->stream2));
         CU(e, cudaStreamSynchronize(e->up_stream));
         CU(e, cudaFree(b.p));
         b.p = nullptr;
@@ -244,6 +250,8 @@ MbGeom make_geom(mb200_engine* e, int first_block, int nblk) {
     g.fill = 2.0;                      // mustache.py:703-706
     g.dout = nullptr;
     g.ndiff = e->ndiff;
+    g.zstride = e->pass_blocks;
+    g.zoff = 0;
     return g;
 }
 
@@ -309,8 +317,10 @@ int set_smem_limits(mb200_engine* e) {
 }
 
 int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cudaEvent_t after_kv,
-                const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr) {
+                const MbProgram* program = nullptr, cudaEvent_t after_kh = nullptr, cudaStream_t sq = nullptr, int zoff = 0) {
     MbGeom g = dbg_geom ? *dbg_geom : make_geom(e, first_block, nblk);
+    if (!sq) sq = e->stream;
+    g.zoff = zoff;
     const MbProgram& pg = program ? *program : e->prog;
     const int th = kv_tile_rows(e);
     const size_t kvb = kv_smem_bytes(pg.rmax, th), khb = kh_smem_bytes(pg.rmax, pg.n_scored);
@@ -318,46 +328,46 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     const KvPlan& kp = program ? e->dkvplan : e->kvplan;
     const dim3 gv = kv_grid(e, nblk), gh = kh_grid(e, nblk);
     if (e->fast) {
-        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
-        else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
     } else {
-        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, false><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
-        else kv_kernel<KV_TH_NARROW, false><<<gv, KV_THREADS, kvb, e->stream>>>(kp, g);
+        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        else kv_kernel<KV_TH_NARROW, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
     }
     CU(e, cudaGetLastError());
-    if (after_kv) CU(e, cudaEventRecord(after_kv, e->stream));
+    if (after_kv) CU(e, cudaEventRecord(after_kv, sq));
     const int mode = g.dout != nullptr ? KH_DIFF : ((g.dbgG != nullptr || g.dbgL != nullptr) ? KH_DEBUG : KH_MAIN);
     const int ftc = (program == nullptr) ? fused_tc(e) : 0;
     if (mode == KH_MAIN && ftc) {
         // axis-1 pass, DoG and scoring in one kernel: the DoG levels stay in shared memory
         const dim3 gf = kf_grid(e, nblk, ftc);
         if (ftc == 64) {
-            if (e->fast) khs_kernel<64, true><<<gf, 256, kf_smem_bytes(64), e->stream>>>(pg, tm, g);
-            else khs_kernel<64, false><<<gf, 256, kf_smem_bytes(64), e->stream>>>(pg, tm, g);
+            if (e->fast) khs_kernel<64, true><<<gf, 256, kf_smem_bytes(64), sq>>>(pg, tm, g);
+            else khs_kernel<64, false><<<gf, 256, kf_smem_bytes(64), sq>>>(pg, tm, g);
         } else {
-            if (e->fast) khs_kernel<128, true><<<gf, 512, kf_smem_bytes(128), e->stream>>>(pg, tm, g);
-            else khs_kernel<128, false><<<gf, 512, kf_smem_bytes(128), e->stream>>>(pg, tm, g);
+            if (e->fast) khs_kernel<128, true><<<gf, 512, kf_smem_bytes(128), sq>>>(pg, tm, g);
+            else khs_kernel<128, false><<<gf, 512, kf_smem_bytes(128), sq>>>(pg, tm, g);
         }
         CU(e, cudaGetLastError());
-        if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
+        if (after_kh) CU(e, cudaEventRecord(after_kh, sq));
         e->launches += 2;
         return MB200_OK;
     }
     // KH_DIFF: difference stack, only the DIFFREF DoGs are kept; KH_DEBUG: dense dumps of mb200_debug_level
     if (e->fast) {
-        if (mode == KH_DIFF) kh_kernel<KH_DIFF, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
-        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
-        else kh_kernel<KH_MAIN, true><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        if (mode == KH_DIFF) kh_kernel<KH_DIFF, true><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
+        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, true><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
+        else kh_kernel<KH_MAIN, true><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
     } else {
-        if (mode == KH_DIFF) kh_kernel<KH_DIFF, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
-        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
-        else kh_kernel<KH_MAIN, false><<<gh, KH_THREADS, khb, e->stream>>>(pg, tm, g);
+        if (mode == KH_DIFF) kh_kernel<KH_DIFF, false><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
+        else if (mode == KH_DEBUG) kh_kernel<KH_DEBUG, false><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
+        else kh_kernel<KH_MAIN, false><<<gh, KH_THREADS, khb, sq>>>(pg, tm, g);
     }
     CU(e, cudaGetLastError());
-    if (after_kh) CU(e, cudaEventRecord(after_kh, e->stream));
+    if (after_kh) CU(e, cudaEventRecord(after_kh, sq));
     e->launches += 2;
     if (pg.n_scored > 0) {
-        ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(pg.n_scored), e->stream>>>(pg, tm, g);
+        ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(pg.n_scored), sq>>>(pg, tm, g);
         CU(e, cudaGetLastError());
         e->launches += 1;
     }
@@ -441,6 +451,9 @@ int mb200_create(int device, mb200_engine** out) {
     if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_up, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -479,6 +492,9 @@ void mb200_destroy(mb200_engine* e) {
     if (e->ev_up) cudaEventDestroy(e->ev_up);
     for (int k = 0; k < 2; ++k)
         if (e->ev_run[k]) cudaEventDestroy(e->ev_run[k]);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->up_stream) cudaStreamDestroy(e->up_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -856,7 +872,15 @@ int mb200_run(mb200_engine* e) {
     e->packed = false;
     e->post_done = false;
     if ((st = adopt_uploads(e))) return st;
-    const int npass = (B + e->pass_blocks - 1) / e->pass_blocks;
+    // Passes: as many blocks as the scratch holds.  Overlapped mode: the scratch is split into two regions and the passes
+    // alternate between two streams, so that the (issue-bound) scoring of one half of the batch runs while the (FP64 /
+    // HBM-bound) Gaussian passes of the other half do.
+    const bool two = e->overlap && B >= 2 && e->pass_blocks >= 2;
+    // overlapped: up to 8 passes, pipelined -- pass p+1 starts its axis-0 kernel when pass p has finished its axis-1
+    // kernel, so the scoring of pass p runs next to the Gaussian passes of pass p+1
+    const int per_pass = two ? std::max(1, std::min(e->pass_blocks / 2, (B + 7) / 8)) : e->pass_blocks;
+    const int npass = (B + per_pass - 1) / per_pass;
+    e->npass_run = npass;
     while ((int)e->ev_pass.size() < 4 * npass) {
         cudaEvent_t ev;
         CU(e, cudaEventCreate(&ev));
@@ -871,11 +895,22 @@ int mb200_run(mb200_engine* e) {
     CU(e, cudaGetLastError());
     e->launches += 1;
     CU(e, cudaEventRecord(e->ev_prep, e->stream));
+    if (two) {
+        CU(e, cudaEventRecord(e->ev_fork, e->stream));
+        CU(e, cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+    }
     for (int p = 0; p < npass; ++p) {
-        const int first = p * e->pass_blocks, nb = std::min(e->pass_blocks, B - first);
-        CU(e, cudaEventRecord(e->ev_pass[4 * p], e->stream));
-        if ((st = launch_pass(e, first, nb, nullptr, e->ev_pass[4 * p + 1], nullptr, e->ev_pass[4 * p + 2]))) return st;
-        CU(e, cudaEventRecord(e->ev_pass[4 * p + 3], e->stream));
+        const int first = p * per_pass, nb = std::min(per_pass, B - first);
+        cudaStream_t sq = (two && (p & 1)) ? e->stream2 : e->stream;
+        const int zoff = (two && (p & 1)) ? e->pass_blocks / 2 : 0;
+        if (two && p > 0) CU(e, cudaStreamWaitEvent(sq, e->ev_pass[4 * (p - 1) + 2], 0));
+        CU(e, cudaEventRecord(e->ev_pass[4 * p], sq));
+        if ((st = launch_pass(e, first, nb, nullptr, e->ev_pass[4 * p + 1], nullptr, e->ev_pass[4 * p + 2], sq, zoff))) return st;
+        CU(e, cudaEventRecord(e->ev_pass[4 * p + 3], sq));
+    }
+    if (two) {
+        CU(e, cudaEventRecord(e->ev_join, e->stream2));
+        CU(e, cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     }
     if (e->prog.n_scored > 0) {
         reduce_stats_kernel<<<dim3(e->prog.n_scored, B), 256, 0, e->stream>>>(
@@ -905,6 +940,7 @@ int mb200_sync(mb200_engine* e) {
     int st = use_device(e);
     if (st) return st;
     CU(e, cudaStreamSynchronize(e->up_stream));
+    CU(e, cudaStreamSynchronize(e->stream2));
     CU(e, cudaStreamSynchronize(e->stream));
     return MB200_OK;
 }
@@ -951,6 +987,12 @@ int mb200_set_fusion(mb200_engine* e, int enable) {
     if (!e || enable < 0 || enable > 1) return MB200_ERR_ARG;
     if (e->fusion != enable) e->configured = false;     // the partial-statistics layout depends on the path
     e->fusion = enable;
+    return MB200_OK;
+}
+
+int mb200_set_overlap(mb200_engine* e, int enable) {
+    if (!e || enable < 0 || enable > 1) return MB200_ERR_ARG;
+    e->overlap = enable;
     return MB200_OK;
 }
 
@@ -1269,7 +1311,7 @@ int mb200_last_timing(mb200_engine* e, float* prep_ms, float* kv_ms, float* kh_m
     int st = use_device(e);
     if (st) return st;
     CU(e, cudaEventSynchronize(e->ev_end));
-    const int npass = (e->nblocks + e->pass_blocks - 1) / e->pass_blocks;
+    const int npass = e->npass_run;
     float kv = 0, kh = 0, ks = 0, t = 0;
     for (int p = 0; p < npass; ++p) {
         CU(e, cudaEventElapsedTime(&t, e->ev_pass[4 * p], e->ev_pass[4 * p + 1]));

@@ -126,6 +126,8 @@ struct MbGeom {
     double fill;                    // value of the constant regions (2.0; 0.0 for the difference stack of diff_mustache)
     double* dout;                   // [nblk][ndiff][n][wc]: DoG of every MB_FLAG_DIFFREF step (difference stack) or nullptr
     int ndiff;                      // MB_FLAG_DIFFREF steps of the difference chain (octaves)
+    int zstride;                    // planes per step of the V / L scratch (its capacity in blocks): plane = step * zstride + zoff + b
+    int zoff;                       // first plane of this pass inside a step (two passes may be in flight in two regions)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -448,8 +450,8 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     }
     __syncthreads();
 
-    const long long step_stride = (long long)g.nblk * g.plane_v;
-    double* const vblock = g.V + (long long)b * g.plane_v;
+    const long long step_stride = (long long)g.zstride * g.plane_v;
+    double* const vblock = g.V + (long long)(g.zoff + b) * g.plane_v;
     const int kstride = g.wv - 1;                   // output k + 1 sits kstride elements after output k
     for (int sub = 0; sub < KV_TH / 32; ++sub) {
         const int rb = sub * 32 + warp * KV_K;      // first tile row of this thread's KV_K outputs
@@ -642,7 +644,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             while (next_prefetch < n_steps && next_prefetch <= p_now + KH_LOOKAHEAD + KH_PREFETCH) {
                 if (next_prefetch > p_now + KH_LOOKAHEAD && elect_one())
                     tma_prefetch_box3d(&tm->v[next_prefetch], (js - prog.st[next_prefetch].radius - g.vlo) & ~1, i0,
-                                       next_prefetch * g.nblk + b);
+                                       next_prefetch * g.zstride + g.zoff + b);
                 ++next_prefetch;
             }
         }
@@ -655,7 +657,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 const int R = prog.st[s].radius;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
                 // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
-                tma_load_box3d(vbuf + stg[next_issue].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+                tma_load_box3d(vbuf + stg[next_issue].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.zstride + g.zoff + b, &full[s]);
             }
             ++next_issue;
         }
@@ -677,7 +679,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             mbar_wait(&full[s], 0);
         } else {
             __syncthreads();                                     // previous step's readers are done with the buffer
-            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
+            const double* vin = g.V + ((size_t)s * g.zstride + g.zoff + b) * g.plane_v;
             const int wlen = KH_TC + 1 + 2 * R;
             for (int r = warp; r < KH_TR; r += NW) {
                 const int ii = i0 + r;
@@ -718,7 +720,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
         if (keep && chunk_live) {
             double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)b * g.ndiff + prog.st[sl].score_idx) * g.n * g.wc
-                                            : g.L + ((size_t)sl * g.nblk + b) * g.plane_l;
+                                            : g.L + ((size_t)sl * g.zstride + g.zoff + b) * g.plane_l;
             dst += qoff0;
             const double* xrd = xbuf + (8 * r0) * KH_XP + kk;
             if (MODE != KH_DEBUG && interior) {
@@ -847,9 +849,9 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     auto issue = [&](int nl) {
         const int st = nl % D;
         mbar_arrive_expect_tx(&full[st], (uint32_t)(KS_TR * PL) * 8u);
-        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.nblk + b, &full[st]);
+        tma_load_box3d(lst + st * (KS_TR * PL), &tm->l, x_first & ~1, i0, lvl_step[nl] * g.zstride + g.zoff + b, &full[st]);
         if (KS_PREFETCH > 0 && nl + KS_PREFETCH < n_levels_s)       // the level that will take this stage's successor: into L2
-            tma_prefetch_box3d(&tm->l, x_first & ~1, i0, lvl_step[nl + KS_PREFETCH] * g.nblk + b);
+            tma_prefetch_box3d(&tm->l, x_first & ~1, i0, lvl_step[nl + KS_PREFETCH] * g.zstride + g.zoff + b);
     };
 
     if (threadIdx.x == 0)                                       // prologue: every stage starts loading (before the mask
@@ -1053,7 +1055,7 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
                 const int s = next_issue;
                 const int R = prog.st[s].radius;
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(KS_TR * kf_box_width(R, TC)) * 8u);
-                tma_load_box3d(vbuf + stg[s].off, &tm->vf[s], (jt - R - g.vlo) & ~1, i0, s * g.nblk + b, &full[s]);
+                tma_load_box3d(vbuf + stg[s].off, &tm->vf[s], (jt - R - g.vlo) & ~1, i0, s * g.zstride + g.zoff + b, &full[s]);
             }
             ++next_issue;
         }
@@ -1098,7 +1100,7 @@ khs_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restric
             mbar_wait(&full[s], 0);
         } else {
             __syncthreads();
-            const double* vin = g.V + ((size_t)s * g.nblk + b) * g.plane_v;
+            const double* vin = g.V + ((size_t)s * g.zstride + g.zoff + b) * g.plane_v;
             const int wlen = TC + 1 + 2 * R;
             for (int r = warp; r < KS_TR; r += NW) {
                 const int ii = i0 + r;

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mb200_last_post_ms": (C.c_int, [_H, _f32p]),
     "mb200_set_arithmetic": (C.c_int, [_H, C.c_int]),
     "mb200_set_fusion": (C.c_int, [_H, C.c_int]),
+    "mb200_set_overlap": (C.c_int, [_H, C.c_int]),
     "mb200_set_pass_limit": (C.c_int, [_H, C.c_int]),
     "mb200_set_score_sigmas": (C.c_int, [_H, _f64p, C.c_int]),
     "mb200_fetch_sigma": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
@@ -254,6 +255,10 @@ class ScaleSpaceEngine:
     def set_fusion(self, enable):
         """True: fused axis-1 + scoring kernel whenever the chain fits; False (default): always three kernels."""
         self._chk(self.lib.mb200_set_fusion(self.h, 1 if enable else 0))
+
+    def set_overlap(self, enable):
+        """True: two half-batches in flight on two streams (scoring of one overlaps the Gaussian passes of the other)."""
+        self._chk(self.lib.mb200_set_overlap(self.h, 1 if enable else 0))
 
     def set_pass_limit(self, max_blocks):
         """At most this many blocks per pass of the kernels (0 = whatever fits); next configure()."""

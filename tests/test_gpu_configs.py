@@ -385,3 +385,25 @@ def test_fused_equals_three_kernel_path(eng, n, dpx, octs):
         assert np.abs(out[True][0][b]["p"] - out[False][0][b]["p"]).max() <= 1e-12
         assert np.array_equal(out[True][1][b]["loc"], out[False][1][b]["loc"])
         assert np.abs(out[True][1][b]["scale"] / out[False][1][b]["scale"] - 1).max() <= 1e-13
+
+
+def test_overlapped_passes_equal_single_stream(eng):
+    """mb200_set_overlap: half-batches pipelined on two streams (own halves of the scratch) give the records of the
+    single-stream run bit for bit, for an odd number of blocks too."""
+    n, dpx = 512, 200
+    tiles = [gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=370 + b, blob_seed=380 + b, nblobs=12, missing=0.05 * b), n)
+             for b in range(5)]
+    _set(eng, [1.6, 3.2])
+    out = {}
+    for overlap in (False, True):
+        eng.set_overlap(overlap)
+        eng.configure(n, dpx, 5)
+        for b, t in enumerate(tiles):
+            eng.upload_dense(b, t)
+        eng.run()
+        out[overlap] = (eng.records_batch(), [eng.fits(b) for b in range(5)])
+    eng.set_overlap(False)
+    for b in range(5):
+        assert out[True][0][b]["n_found"] > 100
+        _equal_records(out[True][0][b], out[False][0][b])
+        assert np.array_equal(out[True][1][b]["scale"], out[False][1][b]["scale"])

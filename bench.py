@@ -499,7 +499,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 strong-scaling object of multi-GPU lines")
     ap.add_argument("--cpu-steps", type=int, default=1)
-    ap.add_argument("--fusion", action="store_true", help="opt-in fused axis-1 + scoring kernel (mb200_set_fusion)")
+    ap.add_argument("--fusion", type=int, default=0, help="mb200_set_fusion: 1 = axis-1 + scoring fused, 2 = axis-0 + axis-1 fused")
     ap.add_argument("--overlap", action="store_true", help="two half-batches on two streams (mb200_set_overlap)")
     ap.add_argument("--no-fast", action="store_true", help="skip the extra device-resident measurement in the opt-in FMA mode")
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
@@ -549,8 +549,8 @@ def main():
         eng.set_overlap(True)
         config["overlap"] = "two half-batches on two streams"
     if args.fusion:
-        eng.set_fusion(True)
-        config["fusion"] = "khs_kernel (axis-1 + DoG + scoring in one kernel)"
+        eng.set_fusion(args.fusion)
+        config["fusion"] = {1: "khs_kernel (axis-1 + DoG + scoring in one kernel)", 2: "kvh_kernel (axis-0 + axis-1 + DoG in one kernel)"}[args.fusion]
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -137,7 +137,10 @@ MB200_API int mb200_last_post_ms(mb200_engine* e, float* ms);
  * golden input (tests/test_gpu_fast_mode.py) but which is NOT the reference's arithmetic.  Takes effect at the next run. */
 MB200_API int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add);
 
-/* 1: when the chain's widest axis-0 tile leaves room for three DoG levels in shared memory (the default two octaves do),
+/* Kernel fusion, opt-in (0 = default: axis-0, axis-1 + DoG and scoring as three kernels).
+ * 2: chains up to radius 14 (the default two octaves) run the axis-0 and the axis-1 pass as ONE kernel (kvh_kernel): the
+ *    axis-0 results stay in shared memory instead of going through HBM, at 1.24 x the FP64 instructions.
+ * 1: when the chain's widest axis-0 tile leaves room for three DoG levels in shared memory (the default two octaves do),
  * the axis-1 pass, the DoG and the scoring run as ONE kernel (khs_kernel) and the DoG levels never go to HBM; 0 (default):
  * always the three-kernel path, which measured 6 % faster on B200 (profiles/README.md: the fused kernel halves the DRAM
  * traffic but pays two CTA barriers per level).  Results are bit-identical either way (tests/test_gpu_configs.py).

@@ -38,6 +38,9 @@ struct mb200_engine {
     MbProgram prog;
     MbProgram dprog;                 // difference-stack chain (diff_mustache): G_2, G_3 of every octave
     KvPlan kvplan, dkvplan;          // kv_kernel's grouping of the two chains
+    KvPlan pairplan;                 // kvh_kernel: the main chain in consecutive pairs
+    DevBuf d_pairplan;
+    bool kvh_smem_set = false;
     bool have_prog = false;
     bool have_dprog = false;
     bool ran_diff = false;
@@ -279,7 +282,10 @@ dim3 kf_grid(const mb200_engine* e, int nblk, int tc) {
 }
 
 // tile columns of the fused kernel for this batch (0: three-kernel path)
-int fused_tc(const mb200_engine* e) { return (e->fusion && e->prog.n_scored > 0) ? e->prog.pad : 0; }
+int fused_tc(const mb200_engine* e) { return (e->fusion == 1 && e->prog.n_scored > 0) ? e->prog.pad : 0; }
+
+// axis-0 + axis-1 in one kernel (kvh_kernel) for this batch?
+bool fused_vh(const mb200_engine* e) { return e->fusion == 2 && e->pairplan.n_groups > 0; }
 
 int set_smem_limits(mb200_engine* e) {
     const size_t kvb = kv_smem_bytes(e->prog.rmax, KV_TH_WIDE), khb = kh_smem_bytes(e->prog.rmax, e->prog.n_scored);
@@ -308,6 +314,11 @@ int set_smem_limits(mb200_engine* e) {
         CU(e, cudaFuncSetAttribute(khs_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kf_smem_bytes(128)));
         e->kf_smem_set = true;
     }
+    if (!e->kvh_smem_set) {
+        CU(e, cudaFuncSetAttribute(kvh_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvh_smem_bytes()));
+        CU(e, cudaFuncSetAttribute(kvh_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvh_smem_bytes()));
+        e->kvh_smem_set = true;
+    }
     const size_t ksb = ks_smem_bytes(e->prog.n_scored);
     if (ksb != e->ks_smem_set) {
         CU(e, cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksb));
@@ -327,6 +338,22 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
     const MbTensorMaps* tm = (const MbTensorMaps*)(program ? e->d_dtmaps.p : e->d_tmaps.p);
     const KvPlan& kp = program ? e->dkvplan : e->kvplan;
     const dim3 gv = kv_grid(e, nblk), gh = kh_grid(e, nblk);
+    const bool plain = program == nullptr && g.dout == nullptr && g.dbgG == nullptr && g.dbgL == nullptr;
+    if (plain && fused_vh(e)) {
+        // axis-0 and axis-1 pass in one kernel: the axis-0 results stay in shared memory; scoring as usual
+        if (e->fast) kvh_kernel<true><<<gh, KH_THREADS, kvh_smem_bytes(), sq>>>(pg, (const KvPlan*)e->d_pairplan.p, g);
+        else kvh_kernel<false><<<gh, KH_THREADS, kvh_smem_bytes(), sq>>>(pg, (const KvPlan*)e->d_pairplan.p, g);
+        CU(e, cudaGetLastError());
+        if (after_kv) CU(e, cudaEventRecord(after_kv, sq));
+        if (after_kh) CU(e, cudaEventRecord(after_kh, sq));
+        e->launches += 1;
+        if (pg.n_scored > 0) {
+            ks_kernel<<<ks_grid(e, nblk), KS_THREADS, ks_smem_bytes(pg.n_scored), sq>>>(pg, tm, g);
+            CU(e, cudaGetLastError());
+            e->launches += 1;
+        }
+        return MB200_OK;
+    }
     if (e->fast) {
         if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
         else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
@@ -480,7 +507,7 @@ void mb200_destroy(mb200_engine* e) {
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
                      &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
                      &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
-                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9, &e->dpart};
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9, &e->dpart, &e->d_pairplan};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -571,6 +598,33 @@ static int plan_kv(mb200_engine* e, const MbProgram& p, KvPlan& kp) {
     return MB200_OK;
 }
 
+// kvh_kernel's plan: the chain in consecutive pairs (radii never decrease along a chain), each pair sharing its folded pair
+// sums over the larger radius, weights transposed and zero-padded as in plan_kv.  kp.n_groups = 0 when the chain does not
+// qualify (radius beyond KVH_RMAX, radii not monotone, too many taps).
+static void plan_pairs(const MbProgram& p, KvPlan& kp) {
+    memset(&kp, 0, sizeof(kp));
+    if (p.rmax > KVH_RMAX || (p.n_steps + 1) / 2 > KV_MAX_GROUPS) return;
+    int off = 0;
+    for (int pos = 0; pos < p.n_steps; pos += 2) {
+        const int cnt = std::min(2, p.n_steps - pos);
+        KvGroup& gr = kp.grp[kp.n_groups];
+        gr.n = cnt;
+        gr.rmax = 0;
+        for (int slot = 0; slot < cnt; ++slot) gr.rmax = std::max(gr.rmax, p.st[pos + slot].radius);
+        gr.tap_off = off;
+        const int need = (gr.rmax + 1) * cnt;
+        if (off + need > KVH_MAX_TAPS) { kp.n_groups = 0; return; }
+        for (int slot = 0; slot < cnt; ++slot) {
+            const MbStep& st = p.st[pos + slot];
+            gr.step[slot] = pos + slot;
+            for (int j = 0; j <= st.radius; ++j) kp.tapsT[off + j * cnt + slot] = p.taps[st.tap_off + j];
+        }
+        off += need;
+        ++kp.n_groups;
+    }
+    kp.rmax = p.rmax;
+}
+
 static int parse_program(mb200_engine* e, MbProgram& p, int n_steps, const int32_t* radius, const int32_t* flags,
                          const int32_t* score_id, const int32_t* tap_off, const double* half_taps, int n_taps) {
     if (!e || !radius || !flags || !score_id || !tap_off || !half_taps) return fail(e, MB200_ERR_ARG, "null argument");
@@ -609,6 +663,7 @@ int mb200_set_program(mb200_engine* e, int n_steps, const int32_t* radius, const
     int st = parse_program(e, e->prog, n_steps, radius, flags, score_id, tap_off, half_taps, n_taps);
     if (st) return st;
     if ((st = plan_kv(e, e->prog, e->kvplan))) return st;
+    plan_pairs(e->prog, e->pairplan);
     memset(e->score_sigma, 0, sizeof(e->score_sigma));
     e->have_prog = true;
     e->configured = false;
@@ -721,6 +776,8 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
         if ((st = ensure(e, e->d_dtmaps, sizeof(MbTensorMaps)))) return st;
         CU(e, cudaMemcpyAsync(e->d_dtmaps.p, &e->dtmaps, sizeof(MbTensorMaps), cudaMemcpyHostToDevice, e->stream));
     }
+    if ((st = ensure(e, e->d_pairplan, sizeof(KvPlan)))) return st;
+    CU(e, cudaMemcpyAsync(e->d_pairplan.p, &e->pairplan, sizeof(KvPlan), cudaMemcpyHostToDevice, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));      // the host copies may be re-encoded by the next configure; tiles are zeroed
     e->configured = true;
     e->ran = false;
@@ -984,7 +1041,7 @@ int mb200_set_arithmetic(mb200_engine* e, int fused_multiply_add) {
 }
 
 int mb200_set_fusion(mb200_engine* e, int enable) {
-    if (!e || enable < 0 || enable > 1) return MB200_ERR_ARG;
+    if (!e || enable < 0 || enable > 2) return MB200_ERR_ARG;
     if (e->fusion != enable) e->configured = false;     // the partial-statistics layout depends on the path
     e->fusion = enable;
     return MB200_OK;

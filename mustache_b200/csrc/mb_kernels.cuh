@@ -352,28 +352,28 @@ __device__ __forceinline__ void conv_slide(const double* __restrict__ ctr, const
 // bit-identical to scipy's; the FP64 instruction count per output drops from sum(3R+1) = 2415 to 1987 for 4 octaves
 // (532 -> 431 for 2).  The tap loop has no step-dependent control flow: four taps per trip from windows loaded once.
 // ---------------------------------------------------------------------------------------------------------------
-template <int N, bool FAST>
+template <int N, bool FAST, int PITCH = KV_TW>
 __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const double* __restrict__ tp, const int rtop,
                                          const int* __restrict__ steps, double* __restrict__ vrow, const long long step_stride,
                                          const int kstride, const unsigned vmask) {
     double acc[N][KV_K];
 #pragma unroll
     for (int k = 0; k < KV_K; ++k) {
-        const double x = ctr[k * KV_TW];
+        const double x = ctr[k * PITCH];
 #pragma unroll
         for (int s = 0; s < N; ++s) acc[s][k] = __dmul_rn(x, tp[s]);
     }
     // windows of a trip: xl[m] = x[m - jc], xr[m] = x[jc - 3 + m]; tap j = jc - u pairs xl[k + u] with xr[k + 3 - u].
     // Running pointers keep every access of the trip at [pointer + compile-time offset].
-    const double* pl = ctr - rtop * KV_TW;
-    const double* pr = ctr + (rtop - 3) * KV_TW;
+    const double* pl = ctr - rtop * PITCH;
+    const double* pr = ctr + (rtop - 3) * PITCH;
     const double* pw = tp + rtop * N;
     for (int jc = rtop; jc > 0; jc -= 4) {
         double xl[KV_K + 3], xr[KV_K + 3];
 #pragma unroll
         for (int m = 0; m < KV_K + 3; ++m) {
-            xl[m] = pl[m * KV_TW];
-            xr[m] = pr[m * KV_TW];
+            xl[m] = pl[m * PITCH];
+            xr[m] = pr[m * PITCH];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -389,8 +389,8 @@ __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const d
                 }
             }
         }
-        pl += 4 * KV_TW;
-        pr -= 4 * KV_TW;
+        pl += 4 * PITCH;
+        pr -= 4 * PITCH;
         pw -= 4 * N;
     }
 #pragma unroll
@@ -983,6 +983,149 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_VH (kvh_kernel, opt-in: mb200_set_fusion bit 1): kv_kernel and kh_kernel in one, for chains up to radius KVH_RMAX
+// (the default two octaves): the axis-0 results never go to HBM.  A CTA owns kh_kernel's 32 x 64 tile, stages the filled
+// input tile with its +/- rmax halo once ('reflect' rows AND columns, so there is no separate border path), and then walks
+// the chain two steps at a time:
+//   phase A  axis-0 pass of both steps for the 32 rows x (64 + 2R) columns the axis-1 pass will read, into two
+//            shared-memory tiles; the two steps share scipy's folded pair sums exactly as kv_kernel's groups do
+//            (lanes = columns, 4 outputs per thread down a column);
+//   barrier; phase B  kh_kernel's axis-1 pass + DoG + transposed store for each of the two steps (lanes = rows, odd
+//            pitch: conflict-free); barrier.
+// Per output the axis-0 work is done (64 + 2R) / 64 times over (the column halo every tile recomputes) and in groups of 2
+// instead of up to 5: 1.24 x the FP64 instructions of kv + kh, against 8 B written + ~10 B read per bin and step less.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KVH_RMAX = 14;
+constexpr int KVH_RP = KH_TC + 2 * KVH_RMAX;          // 92: pitch of the staged input tile (lanes = columns)
+constexpr int KVH_VP = KH_TC + 2 * KVH_RMAX + 1;      // 93: pitch of the axis-0 tiles (odd: lanes = rows in phase B)
+constexpr int KVH_MAX_TAPS = 512;
+__host__ __device__ inline size_t kvh_smem_bytes() {
+    return ((size_t)(KH_TR + 2 * KVH_RMAX) * KVH_RP + 2 * KH_TR * KVH_VP + (KH_THREADS / 32) * KH_TR * KH_XP + KVH_MAX_TAPS) * sizeof(double);
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(KH_THREADS, 2)
+kvh_kernel(const __grid_constant__ MbProgram prog, const KvPlan* __restrict__ pairs, const MbGeom g) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NW = KH_THREADS / 32;
+    double* rawt = smem;                                               // [32 + 2 rmax][KVH_RP]
+    double* vb = rawt + (KH_TR + 2 * KVH_RMAX) * KVH_RP;               // [2][32][KVH_VP]
+    double* xbuf = vb + 2 * KH_TR * KVH_VP + (threadIdx.x >> 5) * (KH_TR * KH_XP);
+    double* tapsA = vb + 2 * KH_TR * KVH_VP + NW * KH_TR * KH_XP;      // the pair plan's transposed taps
+
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rmax = prog.rmax;
+    const int i0 = blockIdx.y * KH_TR;
+    const int js = i0 + 2 + blockIdx.x * KH_TC;
+    const int ilast = min(i0 + KH_TR, g.n) - 1;
+    if (js >= g.n || js > ilast + g.dhi + 2) return;
+
+    // ---- stage the filled tile (mustache.py:703-706), rows i0 - rmax .., columns js - rmax .., scipy 'reflect' both ways ----
+    {
+        const double* rawb = g.raw + (size_t)b * g.n * g.wc;
+        const int rows = KH_TR + 2 * rmax, cols = KH_TC + 2 * rmax;
+        for (int r = warp; r < rows; r += NW) {
+            // rows past n - 1 + rmax feed no stored output: clamped so that the reflection stays inside the tile
+            const int ii = reflect_idx(min(i0 - rmax + r, g.n - 1 + rmax), g.n);
+            for (int c = lane; c < cols; c += 32) {
+                const int jj = reflect_idx(min(js - rmax + c, g.n - 1 + rmax), g.n);
+                const int d = jj - ii;
+                double val = g.fill;                                    // d <= 4, or intra and d >= dpx + 1
+                if (d > 4 && !(g.intra && d >= g.dpx + 1)) val = d <= g.dhi ? rawb[(size_t)ii * g.wc + (d - 4)] : 0.0;
+                rawt[r * KVH_RP + c] = val;
+            }
+        }
+        const int ntap = pairs->grp[pairs->n_groups - 1].tap_off + (pairs->grp[pairs->n_groups - 1].rmax + 1) * pairs->grp[pairs->n_groups - 1].n;
+        for (int t = threadIdx.x; t < ntap; t += KH_THREADS) tapsA[t] = pairs->tapsT[t];
+    }
+    __syncthreads();
+
+    const int i = i0 + lane;
+    const int c0 = warp * KH_K;
+    const int jc0 = js + c0;
+    const bool row_in = i < g.n;
+    const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
+                            (js + warp * KH_K < g.n);
+    // DoG store geometry, as in kh_kernel (no row stagger here: the axis-0 tiles have an odd pitch)
+    unsigned zmask = 0;
+#pragma unroll
+    for (int k = 0; k < KH_K; ++k)
+        if (row_in && jc0 + k < g.n) zmask |= 1u << k;
+    const int kk = lane & 7, r0 = lane >> 3;
+    const int pitch = g.wl;
+    const int jst = js + warp * KH_K + kk;
+    unsigned qmask = 0;
+#pragma unroll
+    for (int q = 0; q < KH_TR / 4; ++q) {
+        const int ii = i0 + q + 8 * r0, d = jst - ii;
+        if (ii < g.n && d >= 2 && d <= g.dhi + 2) qmask |= 1u << q;
+    }
+    const long long qoff0 = (long long)(i0 + 8 * r0) * (pitch - 1) + jst - 2;
+    const int qstride = pitch - 1;
+    const bool interior = __all_sync(0xffffffffu, zmask == (1u << KH_K) - 1u && qmask == (1u << (KH_TR / 4)) - 1u);
+
+    double gprev[KH_K];
+#pragma unroll
+    for (int k = 0; k < KH_K; ++k) gprev[k] = 0.0;
+
+    for (int gi = 0; gi < pairs->n_groups; ++gi) {
+        const KvGroup& gr = pairs->grp[gi];
+        const int R = gr.rmax;                                  // both steps run over the pair's larger radius
+        // ---- phase A: axis-0 pass of the pair, V[slot][row][c], c = 0 .. 64 + 2R - 1  <->  image column js - R + c ----
+        {
+            const int W = KH_TC + 2 * R;
+            const double* tp = tapsA + gr.tap_off;
+            for (int c = lane; c < W; c += 32) {
+                const double* ctr = rawt + (warp * KV_K + rmax) * KVH_RP + (rmax - R) + c;
+                double* vrow = vb + (warp * KV_K) * KVH_VP + c;
+                const int slots[2] = {0, 1};
+                if (gr.n == 2) kv_group<2, FAST, KVH_RP>(ctr, tp, R, slots, vrow, (long long)KH_TR * KVH_VP, KVH_VP, 0xfu);
+                else kv_group<1, FAST, KVH_RP>(ctr, tp, R, slots, vrow, (long long)KH_TR * KVH_VP, KVH_VP, 0xfu);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: axis-1 pass + DoG of each step of the pair ----
+        for (int slot = 0; slot < gr.n; ++slot) {
+            const int s = gr.step[slot];
+            const int Rs = prog.st[s].radius;
+            double gnew[KH_K];
+            if (chunk_live && row_in) {
+                conv_slide<KH_K, 1, FAST>(vb + slot * (KH_TR * KVH_VP) + lane * KVH_VP + c0 + R, Rs, prog.taps + prog.st[s].tap_off, gnew);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
+            }
+            const int flags = prog.st[s].flags;
+            if (!(flags & MB_FLAG_RESTART) && chunk_live) {
+                double* dst = g.L + ((size_t)s * g.zstride + g.zoff + b) * g.plane_l + qoff0;
+                const double* xrd = xbuf + (8 * r0) * KH_XP + kk;
+                if (interior) {
+#pragma unroll
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = __dsub_rn(gprev[k], gnew[k]);
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < KH_TR / 4; ++q) dst[(long long)q * qstride] = xrd[q * KH_XP];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KH_K; ++k) xbuf[lane * KH_XP + k] = (zmask & (1u << k)) ? __dsub_rn(gprev[k], gnew[k]) : 0.0;
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < KH_TR / 4; ++q) {
+                        if (qmask & (1u << q)) *dst = xrd[q * KH_XP];
+                        dst += qstride;
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < KH_K; ++k) gprev[k] = gnew[k];
+        }
+        __syncthreads();                                        // the pair's tiles are free for the next pair
     }
 }
 

@@ -252,9 +252,10 @@ class ScaleSpaceEngine:
         """False: scipy's multiply-then-add (bit-exact Gaussians, default).  True: opt-in FMA fast mode."""
         self._chk(self.lib.mb200_set_arithmetic(self.h, 1 if fused_multiply_add else 0))
 
-    def set_fusion(self, enable):
-        """True: fused axis-1 + scoring kernel whenever the chain fits; False (default): always three kernels."""
-        self._chk(self.lib.mb200_set_fusion(self.h, 1 if enable else 0))
+    def set_fusion(self, mode):
+        """0 / False (default): three kernels.  1 / True: fused axis-1 + scoring kernel (khs_kernel) whenever the chain
+        fits.  2: fused axis-0 + axis-1 kernel (kvh_kernel) for chains up to radius 14."""
+        self._chk(self.lib.mb200_set_fusion(self.h, int(mode)))
 
     def set_overlap(self, enable):
         """True: two half-batches in flight on two streams (scoring of one overlaps the Gaussian passes of the other)."""

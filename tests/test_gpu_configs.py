@@ -370,21 +370,24 @@ def test_fused_equals_three_kernel_path(eng, n, dpx, octs):
              for b in range(2)]
     _set(eng, list(octs))                                 # two octaves: 64-column tiles; four: 128-column tiles, one CTA per SM
     out = {}
-    for fused in (True, False):
-        eng.set_fusion(fused)
+    for mode in (1, 2, 0):                                # 1: khs_kernel, 2: kvh_kernel + ks_kernel, 0: kv + kh + ks
+        eng.set_fusion(mode)
         eng.configure(n, dpx, 2)
         for b, t in enumerate(tiles):
             eng.upload_dense(b, t)
         eng.run()
-        out[fused] = (eng.records_batch(), [eng.fits(b) for b in range(2)], eng.timing())
-    eng.set_fusion(False)
-    assert out[True][2]["ks_ms"] < 0.02 < out[False][2]["ks_ms"]          # the two paths really are different kernels
+        out[mode] = (eng.records_batch(), [eng.fits(b) for b in range(2)], eng.timing())
+    assert out[1][2]["ks_ms"] < 0.02 < out[0][2]["ks_ms"]          # the paths really are different kernels
+    if len(octs) == 2:
+        assert out[2][2]["kh_ms"] < 0.02 < out[0][2]["kh_ms"]      # kvh_kernel is timed in the axis-0 slot
     for b in range(2):
-        assert out[True][0][b]["n_found"] > 100
-        _equal_records(out[True][0][b], out[False][0][b], keys=("rows", "cols", "v", "score_id", "sigma"))
-        assert np.abs(out[True][0][b]["p"] - out[False][0][b]["p"]).max() <= 1e-12
-        assert np.array_equal(out[True][1][b]["loc"], out[False][1][b]["loc"])
-        assert np.abs(out[True][1][b]["scale"] / out[False][1][b]["scale"] - 1).max() <= 1e-13
+        assert out[1][0][b]["n_found"] > 100
+        _equal_records(out[1][0][b], out[0][0][b], keys=("rows", "cols", "v", "score_id", "sigma"))
+        assert np.abs(out[1][0][b]["p"] - out[0][0][b]["p"]).max() <= 1e-12
+        assert np.array_equal(out[1][1][b]["loc"], out[0][1][b]["loc"])
+        assert np.abs(out[1][1][b]["scale"] / out[0][1][b]["scale"] - 1).max() <= 1e-13
+        _equal_records(out[2][0][b], out[0][0][b])                   # same scoring kernel: everything bit for bit
+        assert np.array_equal(out[2][1][b]["scale"], out[0][1][b]["scale"])
 
 
 def test_overlapped_passes_equal_single_stream(eng):

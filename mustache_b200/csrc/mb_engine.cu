@@ -715,9 +715,9 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     e->wl = (e->dhi + 1) | 1;                            // diagonals 2..dhi+2, odd row length (skewed TMA view)
     e->plane_v = ((long long)n * e->wv + 1) & ~1LL;      // plane strides: multiples of 16 bytes
     e->plane_l = ((long long)n * e->wl + 1) & ~1LL;
-    dim3 gh = kh_grid(e, 1);                             // the axis-1 kernel writes one statistics partial per warp
-    e->ncta_h = gh.x * gh.y * (KH_THREADS / 32);
-    if (fused_tc(e)) {                                   // so does the fused kernel, on its own grid
+    dim3 gh = ks_grid(e, 1);
+    e->ncta_h = gh.x * gh.y;
+    if (fused_tc(e)) {                                   // the fused kernel writes one partial per warp
         dim3 gf = kf_grid(e, 1, fused_tc(e));
         e->ncta_h = gf.x * gf.y * (fused_tc(e) / KS_K);
     }

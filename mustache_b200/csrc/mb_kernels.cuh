@@ -195,8 +195,8 @@ __host__ __device__ inline size_t kh_smem_bytes(int rmax, int n_scored) {
 }
 
 __host__ __device__ inline size_t ks_smem_bytes(int n_scored) {
-    (void)n_scored;
-    return ((size_t)KS_DEPTH * KS_TR * KS_PITCH + 2 * KS_DEPTH) * sizeof(double);   // stages + mbarriers
+    return ((size_t)KS_DEPTH * KS_TR * KS_PITCH + 2 * (size_t)(n_scored > 0 ? n_scored : 1) * (KS_THREADS / 32) + 2 * KS_DEPTH)
+           * sizeof(double);                                                       // stages + per-warp statistics + mbarriers
 }
 
 // khs_kernel<TC> (axis-1 pass + DoG + scoring fused, the DoG levels never leave the SM): tile of 30 x (TC - 2) scored pixels +
@@ -582,20 +582,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     const int i0 = blockIdx.y * KH_TR;                  // first row of the tile
     const int js = i0 + 2 + blockIdx.x * KH_TC;         // first column: diagonal 2 of the first row
     const int ilast = min(i0 + KH_TR, g.n) - 1;
-    // MODE == KH_MAIN also takes the statistics of every scored DoG level over the mask (expon.fit's min and sum of |L|,
-    // mustache.py:755) while the DoG values are in registers: one partial per warp and scored level, straight to
-    // part_min / part_sum [b][scored][cta * NW + warp] (g.ncta_h = CTAs of this grid * NW), reduced in a fixed order later
-    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    if (js >= g.n || js > ilast + g.dhi + 2) {          // tile entirely right of the band / of the image
-        if (MODE == KH_MAIN) {
-            for (int t = threadIdx.x; t < prog.n_scored * NW; t += KH_THREADS) {
-                const size_t o = ((size_t)b * prog.n_scored + t / NW) * g.ncta_h + cta * NW + t % NW;
-                g.part_min[o] = __longlong_as_double(0x7ff0000000000000LL);
-                g.part_sum[o] = 0.0;
-            }
-        }
-        return;
-    }
+    if (js >= g.n || js > ilast + g.dhi + 2) return;    // tile entirely right of the band / of the image
     const int i = i0 + lane;                            // this thread's image row
     // Rows 8-15 and 24-31 of every tile are shifted one column to the right: with the even row pitch of the dense TMA box,
     // lanes (= rows) r and r+8 would hit the same 8-byte bank pair; the one-column stagger puts them on the odd pairs.
@@ -627,15 +614,6 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 #pragma unroll
     for (int k = 0; k < KH_K; ++k)
         if (row_in && jc0 + k < g.n) zmask |= 1u << k;
-    unsigned mask = 0;                                  // mask bits (mustache.py:699: c != 0 and j - i >= 4, before the fills)
-    if (MODE == KH_MAIN && row_in) {
-        const double* rawb = g.raw + (size_t)b * g.n * g.wc;
-#pragma unroll
-        for (int k = 0; k < KH_K; ++k) {
-            const int j = jc0 + k, d = j - i;
-            if (j < g.n && d >= 4 && d <= g.dhi && rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
-        }
-    }
     const int kk = lane & 7;
     const int r0 = lane >> 3;                                   // this lane writes tile rows q + 8*r0
     const int pitch = (MODE == KH_DIFF) ? g.wc : g.wl;          // row length of the destination band
@@ -740,28 +718,6 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const int flags = prog.st[sl].flags;
         const bool formed = !(flags & MB_FLAG_RESTART);
         const bool keep = (MODE == KH_DIFF) ? (formed && (flags & MB_FLAG_DIFFREF)) : formed;
-        // this DoG is scored when the NEXT step's DoG exists (that step carries MB_FLAG_SCORE and the scored index)
-        const bool stat = MODE == KH_MAIN && formed && sl + 1 < n_steps && (prog.st[sl + 1].flags & MB_FLAG_SCORE);
-        double tmin = __longlong_as_double(0x7ff0000000000000LL), tsum = 0.0;
-        if (stat && chunk_live && mask) {
-#pragma unroll
-            for (int k = 0; k < KH_K; ++k) {
-                if (mask & (1u << k)) {
-                    const double a = fabs(__dsub_rn(gprev[k], gnew[k]));
-                    tmin = dmin(tmin, a);
-                    tsum = __dadd_rn(tsum, a);
-                }
-            }
-        }
-        if (stat) {                                              // per-warp partial, fixed order (deterministic)
-            tmin = warp_min(tmin);
-            tsum = warp_sum(tsum);
-            if (lane == 0) {
-                const size_t o = ((size_t)b * prog.n_scored + prog.st[sl + 1].score_idx) * g.ncta_h + cta * NW + warp;
-                g.part_min[o] = tmin;
-                g.part_sum[o] = tsum;
-            }
-        }
         if (keep && chunk_live) {
             double* dst = (MODE == KH_DIFF) ? g.dout + ((size_t)b * g.ndiff + prog.st[sl].score_idx) * g.n * g.wc
                                             : g.L + ((size_t)sl * g.zstride + g.zoff + b) * g.plane_l;
@@ -827,7 +783,9 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     constexpr int PL = KS_PITCH;                                // even, == 2 (mod 4)
     constexpr int D = KS_DEPTH;
     double* lst = smem;                                         // [D][KS_TR][PL]   staged DoG tiles
-    uint64_t* full = reinterpret_cast<uint64_t*>(lst + D * KS_TR * PL);   // [D]
+    double* pmin = lst + D * KS_TR * PL;                        // [n_scored][NW] per-warp min of |L|
+    double* psum = pmin + (size_t)max(prog.n_scored, 1) * NW;   // [n_scored][NW] per-warp sum of |L|
+    uint64_t* full = reinterpret_cast<uint64_t*>(psum + (size_t)max(prog.n_scored, 1) * NW);   // [D]
     uint64_t* empty = full + D;                                 // [D] every warp released the stage's tile
     __shared__ int stage_lvl[KS_DEPTH];                         // level the stage holds or is loading (claims reloads)
     __shared__ int lvl_step[MB_MAX_STEPS];                      // chain step of the nl-th DoG of the stream
@@ -839,7 +797,17 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     const int i0 = is0 - 1;                             // tile row 0 (halo)
     const int js = is0 + 4 + blockIdx.x * KS_SC;        // first scored column of this CTA
     const int ilast = min(is0 + KS_SR, g.n) - 1;
-    if (!((js < g.n) && (js <= ilast + g.dhi))) return;        // nothing to score here
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+    const bool active = (js < g.n) && (js <= ilast + g.dhi);
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    if (!active) {
+        for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+            const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+            g.part_min[o] = kInf;
+            g.part_sum[o] = 0.0;
+        }
+        return;
+    }
     const double* rawb = g.raw + (size_t)b * g.n * g.wc;
     const int i = i0 + lane;                            // this thread's image row
     // Rows 8-15 and 24-31 of every tile are shifted one column to the right (as in kh_kernel): with the even row pitch of
@@ -918,6 +886,7 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         if (sp_i < 0) sp_i += D;
         const double* sp = lst + sp_i * (KS_TR * PL) + off_c;                           // level nl-2, own pixel 0
         unsigned e_new = 0;
+        double tmin = kInf, tsum = 0.0;
         const bool score = (flags & MB_FLAG_SCORE) != 0;
         const int sidx = prog.st[s].score_idx;
         if (row_scored) {
@@ -944,6 +913,11 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
                 for (int k = 0; k < KS_K; ++k) {
                     const unsigned bit = 1u << k;
                     const double x = lcur[k];
+                    if (mask & bit) {                                       // expon.fit over the mask, mustache.py:755
+                        const double a = fabs(x);
+                        tmin = dmin(tmin, a);
+                        tsum = __dadd_rn(tsum, a);
+                    }
                     if ((cand & bit) && x > vbest[k]) {                     // mustache.py:761
                         // mustache.py:765  Lc > max3x3(Ln): the next level's 3x3 block is in registers
                         bool ok = (x > o[k]) && (x > o[k + 1]) && (x > o[k + 2]) && (x > up[k]) && (x > up[k + 1]) &&
@@ -966,6 +940,14 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         if (nl >= 2 && lane == 0 && mbar_arrive_is_last(&empty[sp_i])) {     // level nl-2 is released by every warp:
             if (nl - 2 + D < n_levels && atomicCAS(&stage_lvl[sp_i], nl - 2, nl - 2 + D) == nl - 2) issue(nl - 2 + D);   // reload
         }
+        if (score) {                                            // per-warp statistics, fixed order (deterministic)
+            tmin = warp_min(tmin);
+            tsum = warp_sum(tsum);
+            if (lane == 0) {
+                pmin[sidx * NW + warp] = tmin;
+                psum[sidx * NW + warp] = tsum;
+            }
+        }
         e_prev = e_cur;
         e_cur = e_new;
     };
@@ -973,6 +955,17 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     for (int nl = 0; nl < n_levels; nl += 2) {
         level(lvl_step[nl], nl, lB, lA);        // even level: own values into lA
         if (nl + 1 < n_levels) level(lvl_step[nl + 1], nl + 1, lA, lB);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < prog.n_scored; t += KS_THREADS) {
+        double mn = pmin[t * NW], sm = psum[t * NW];
+        for (int w = 1; w < NW; ++w) {
+            mn = dmin(mn, pmin[t * NW + w]);
+            sm = __dadd_rn(sm, psum[t * NW + w]);
+        }
+        const size_t o = ((size_t)b * prog.n_scored + t) * g.ncta_h + cta;
+        g.part_min[o] = mn;
+        g.part_sum[o] = sm;
     }
     // ---- emit the pixels that were ever updated (pAll != 2, mustache.py:774) ----
     if (lvl != 0) {
@@ -1030,15 +1023,7 @@ kvh_kernel(const __grid_constant__ MbProgram prog, const KvPlan* __restrict__ pa
     const int i0 = blockIdx.y * KH_TR;
     const int js = i0 + 2 + blockIdx.x * KH_TC;
     const int ilast = min(i0 + KH_TR, g.n) - 1;
-    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
-    if (js >= g.n || js > ilast + g.dhi + 2) {          // statistics partials as in kh_kernel<KH_MAIN>
-        for (int t = threadIdx.x; t < prog.n_scored * NW; t += KH_THREADS) {
-            const size_t o = ((size_t)b * prog.n_scored + t / NW) * g.ncta_h + cta * NW + t % NW;
-            g.part_min[o] = __longlong_as_double(0x7ff0000000000000LL);
-            g.part_sum[o] = 0.0;
-        }
-        return;
-    }
+    if (js >= g.n || js > ilast + g.dhi + 2) return;
 
     // ---- stage the filled tile (mustache.py:703-706), rows i0 - rmax .., columns js - rmax .., scipy 'reflect' both ways ----
     {
@@ -1071,15 +1056,6 @@ kvh_kernel(const __grid_constant__ MbProgram prog, const KvPlan* __restrict__ pa
 #pragma unroll
     for (int k = 0; k < KH_K; ++k)
         if (row_in && jc0 + k < g.n) zmask |= 1u << k;
-    unsigned mask = 0;                                  // mask bits (mustache.py:699), for the statistics of the scored levels
-    if (row_in) {
-        const double* rawb = g.raw + (size_t)b * g.n * g.wc;
-#pragma unroll
-        for (int k = 0; k < KH_K; ++k) {
-            const int j = jc0 + k, d = j - i;
-            if (j < g.n && d >= 4 && d <= g.dhi && rawb[(size_t)i * g.wc + (d - 4)] != 0.0) mask |= 1u << k;
-        }
-    }
     const int kk = lane & 7, r0 = lane >> 3;
     const int pitch = g.wl;
     const int jst = js + warp * KH_K + kk;
@@ -1125,27 +1101,6 @@ kvh_kernel(const __grid_constant__ MbProgram prog, const KvPlan* __restrict__ pa
                 for (int k = 0; k < KH_K; ++k) gnew[k] = 0.0;
             }
             const int flags = prog.st[s].flags;
-            const bool stat = !(flags & MB_FLAG_RESTART) && s + 1 < prog.n_steps && (prog.st[s + 1].flags & MB_FLAG_SCORE);
-            if (stat) {                                         // expon.fit's min / sum of |L| over the mask (mustache.py:755)
-                double tmin = __longlong_as_double(0x7ff0000000000000LL), tsum = 0.0;
-                if (chunk_live && mask) {
-#pragma unroll
-                    for (int k = 0; k < KH_K; ++k) {
-                        if (mask & (1u << k)) {
-                            const double a = fabs(__dsub_rn(gprev[k], gnew[k]));
-                            tmin = dmin(tmin, a);
-                            tsum = __dadd_rn(tsum, a);
-                        }
-                    }
-                }
-                tmin = warp_min(tmin);
-                tsum = warp_sum(tsum);
-                if (lane == 0) {
-                    const size_t o = ((size_t)b * prog.n_scored + prog.st[s + 1].score_idx) * g.ncta_h + cta * NW + warp;
-                    g.part_min[o] = tmin;
-                    g.part_sum[o] = tsum;
-                }
-            }
             if (!(flags & MB_FLAG_RESTART) && chunk_live) {
                 double* dst = g.L + ((size_t)s * g.zstride + g.zoff + b) * g.plane_l + qoff0;
                 const double* xrd = xbuf + (8 * r0) * KH_XP + kk;

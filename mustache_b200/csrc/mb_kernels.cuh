@@ -159,7 +159,13 @@ constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
 constexpr int KS_PITCH = KS_TC + 6;   // 70: box width of the staged DoG tile (tile + even start column + row stagger); with
                                       // 70 = 6 (mod 16) and the one-column stagger of rows 8-15 / 24-31 the 16 lanes (= rows) of a
                                       // half warp read 16 different 8-byte bank pairs
-constexpr int KS_DEPTH = 6;           // ring stages per CTA: level being scored, the two before it, three in flight
+#ifndef MB_KS_DEPTH
+#define MB_KS_DEPTH 6
+#endif
+#ifndef MB_KS_CTAS
+#define MB_KS_CTAS 2
+#endif
+constexpr int KS_DEPTH = MB_KS_DEPTH;           // ring stages per CTA: level being scored, the two before it, three in flight
 
 // width of the staged box of a step with radius R: the filter support of the tile plus one element (the box must start
 // on an even column: TMA needs 16-byte aligned box rows), padded to 2 (mod 4) elements so that the dense rows the TMA
@@ -776,7 +782,7 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
 // clauses first; for those the 9 values of the next level are already in registers and the 9 of the previous level are
 // still in its ring stage (a stage is released two levels after it was filled).  Everything is exact FP64 comparison.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KS_THREADS, 2)
+__global__ void __launch_bounds__(KS_THREADS, MB_KS_CTAS)
 ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict__ tm, const MbGeom g) {
     extern __shared__ __align__(128) double smem[];
     constexpr int NW = KS_THREADS / 32;

@@ -115,7 +115,7 @@ MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, voi
  * block of the batch, Benjamini-Hochberg over its found p-values (mustache.py:778; statsmodels' fdrcorrection formula, same
  * IEEE operations), selection `o < pt` (:791), the sparsity filter with numpy's slice semantics and threshold st (:800-811).
  * What leaves the GPU is one entry per SELECTED pixel: block, tile row / column, q (FDR), sigma (Scales), flags (bit 0: passed
- * the sparsity filter), cval (its value in the 2-filled tile, for the enrichment filter :822-828) and the 3 x 3 neighbourhoods
+ * the sparsity filter; bits 1-2: see mb200_enrich_candidates), cval (its value in the 2-filled tile, for the enrichment filter :822-828) and the 3 x 3 neighbourhoods
  * of the dense `o` and `so` matrices (:789-795; row-major, 1 off the mask, 2 / 1 on the mask but never updated), which is all
  * the clustering step (:830-848) reads.  candidate_fraction: capacity as a fraction of the batch's found records (<= 0: 1/16);
  * mb200_fetch_candidates returns MB200_ERR_CAPACITY when it was exceeded.  Order of the entries is unspecified.
@@ -124,6 +124,11 @@ MB200_API int mb200_packed_device(mb200_engine* e, void** rows, void** cols, voi
  * selected pixel, those the differential selection reads (diff_mustache.py:445-453, 567-568): `pair` and `v` of its own map
  * and `v` of the other map (1 off that map's mask, pPair / vAll where found, 2 / 0 on the mask but never updated); NULL skips. */
 MB200_API int mb200_select_candidates(mb200_engine* e, double pt, double st, double candidate_fraction);
+/* Enrichment filter of the selected candidates, mustache.py:816-828 (diff_mustache.py:511-527): c[x, y] > 2 * np.mean(non-zero
+ * entries of the (y - x)-th diagonal of the 2-filled tile); np.mean's pairwise summation over the compacted diagonal is
+ * reproduced bit for bit.  Optional, after mb200_select_candidates: sets flags bit 1 (passed) and bit 2 (decided) of every
+ * candidate that passed the sparsity filter.  Synchronises (it sizes its scratch from the candidate count). */
+MB200_API int mb200_enrich_candidates(mb200_engine* e);
 MB200_API int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, int32_t* row, int32_t* col, int32_t* flags,
                                      double* q, double* sigma, double* cval, double* o9, double* so9, double* pair9,
                                      double* vself9, double* vother9, int64_t* n_out);

@@ -54,7 +54,7 @@ struct mb200_engine {
         fit_loc, fit_scale, st_rows, st_cols, st_vals, st_dense, dbgG, dbgL, rawD, dout, dmu, dsd, rec_pair, d_score_id, d_score_sigma, rec_sid, rec_sigma,
         nz_xs, nz_ds, nz_perm, nz_vs, nz_out, nz_seg, nz_mean, nz_sd, nz_w, nz_lines, st_offsets,
         nz_x, nz_y, nz_v, sort_keys[2], sort_vals[2], sort_hist,
-        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot, cd_pair9, cd_vs9, cd_vo9, dpart;
+        rec_q, bh_tmin, slotmap, cd_block, cd_row, cd_col, cd_flags, cd_q, cd_sigma, cd_cval, cd_o9, cd_so9, cd_count, cd_slot, cd_pair9, cd_vs9, cd_vo9, dpart, en_need, en_lines, en_nlist, en_mean, en_scratch;
     bool post_diff = false;
     long long cand_cap = 0;
     bool post_done = false;
@@ -507,7 +507,8 @@ void mb200_destroy(mb200_engine* e) {
                      &e->pk_row, &e->pk_col, &e->pk_v, &e->pk_sid, &e->pk_p, &e->pk_sigma, &e->pk_pair, &e->pk_sidx, &e->pk_offsets, &e->st_offsets,
                      &e->nz_x, &e->nz_y, &e->nz_v, &e->sort_keys[0], &e->sort_keys[1], &e->sort_vals[0], &e->sort_vals[1], &e->sort_hist,
                      &e->rec_q, &e->bh_tmin, &e->slotmap, &e->cd_block, &e->cd_row, &e->cd_col, &e->cd_flags, &e->cd_q, &e->cd_sigma,
-                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9, &e->dpart, &e->d_pairplan};
+                     &e->cd_cval, &e->cd_o9, &e->cd_so9, &e->cd_count, &e->cd_slot, &e->cd_pair9, &e->cd_vs9, &e->cd_vo9, &e->dpart, &e->d_pairplan, &e->en_need, &e->en_lines, &e->en_nlist, &e->en_mean,
+                     &e->en_scratch};
     for (DevBuf* b : all) release(*b);
     for (cudaEvent_t ev : e->ev_pass) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -1239,6 +1240,58 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));          // the candidate kernel reads the tile slot too
     e->launches += 7;
     e->post_done = true;
+    return MB200_OK;
+}
+
+// Enrichment filter of the selected candidates on the device (mb_post.cuh): flags bit 1 = c[x, y] > 2 * mean of the
+// non-zero entries of its diagonal (mustache.py:816-828), np.mean reproduced bit for bit; bit 2 = decided.
+int mb200_enrich_candidates(mb200_engine* e) {
+    if (!e) return MB200_ERR_ARG;
+    if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
+    int st = use_device(e);
+    if (st) return st;
+    cudaStream_t sq = e->stream;
+    unsigned long long tot = 0;
+    CU(e, cudaMemcpyAsync(&tot, e->cd_count.p, sizeof(tot), cudaMemcpyDeviceToHost, sq));
+    CU(e, cudaStreamSynchronize(sq));
+    if (tot == 0) return MB200_OK;
+    if ((long long)tot > e->cand_cap)
+        return fail(e, MB200_ERR_CAPACITY, "%llu candidates, capacity %lld: raise candidate_fraction and call mb200_select_candidates again", tot, e->cand_cap);
+    const int nlines = e->nblocks * e->wc;
+    // scratch for the compacted diagonals; MB200_ENRICH_POOL_KB shrinks it (tests: forces several rounds)
+    const char* pool_kb = std::getenv("MB200_ENRICH_POOL_KB");
+    const size_t pool = pool_kb ? (size_t)std::max(1, atoi(pool_kb)) << 10 : (size_t)256 << 20;
+    const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(tot, (size_t)nlines),
+                                                                             pool / ((size_t)e->n * sizeof(double))));
+    if ((st = ensure(e, e->en_need, (size_t)nlines * sizeof(int)))) return st;
+    if ((st = ensure(e, e->en_lines, (size_t)max_slots * sizeof(int)))) return st;
+    if ((st = ensure(e, e->en_nlist, sizeof(unsigned)))) return st;
+    if ((st = ensure(e, e->en_mean, (size_t)max_slots * sizeof(double)))) return st;
+    if ((st = ensure(e, e->en_scratch, (size_t)max_slots * e->n * sizeof(double)))) return st;
+    const int gc = (int)std::min<unsigned long long>((tot + 255) / 256, 148 * 8);
+    const int gl = std::min((nlines + 255) / 256, 148 * 8);
+    CU(e, cudaMemsetAsync(e->en_need.p, 0, (size_t)nlines * sizeof(int), sq));
+    enrich_mark_kernel<<<gc, 256, 0, sq>>>((const unsigned long long*)e->cd_count.p, e->cand_cap, (const int*)e->cd_block.p,
+                                           (const int*)e->cd_row.p, (const int*)e->cd_col.p, (const int*)e->cd_flags.p, e->wc, e->dpx,
+                                           (int*)e->en_need.p);
+    for (int round = 0; round < 1 + nlines; ++round) {
+        CU(e, cudaMemsetAsync(e->en_nlist.p, 0, sizeof(unsigned), sq));
+        enrich_list_kernel<<<gl, 256, 0, sq>>>(nlines, (int*)e->en_need.p, (int*)e->en_lines.p, (unsigned*)e->en_nlist.p, max_slots);
+        enrich_mean_kernel<<<(int)std::min<unsigned>((max_slots + 7) / 8, 148 * 8), 256, 0, sq>>>(
+            raw_slot(e, e->slot_run), e->n, e->wc, (const int*)e->en_lines.p, (const unsigned*)e->en_nlist.p, max_slots,
+            (double*)e->en_scratch.p, (double*)e->en_mean.p);
+        enrich_apply_kernel<<<gc, 256, 0, sq>>>((const unsigned long long*)e->cd_count.p, e->cand_cap, (const int*)e->cd_block.p,
+                                                (const int*)e->cd_row.p, (const int*)e->cd_col.p, (const double*)e->cd_cval.p, e->wc,
+                                                e->dpx, (const int*)e->en_need.p, (const double*)e->en_mean.p, (int*)e->cd_flags.p);
+        CU(e, cudaGetLastError());
+        e->launches += 3;
+        unsigned nl = 0;
+        CU(e, cudaMemcpyAsync(&nl, e->en_nlist.p, sizeof(nl), cudaMemcpyDeviceToHost, sq));
+        CU(e, cudaStreamSynchronize(sq));
+        if (nl <= max_slots) break;
+        enrich_next_round_kernel<<<gl, 256, 0, sq>>>(nlines, (int*)e->en_need.p);
+    }
+    CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));              // the mean kernel reads the tile slot
     return MB200_OK;
 }
 

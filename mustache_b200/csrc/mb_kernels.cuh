@@ -1016,7 +1016,7 @@ __host__ __device__ inline size_t kvh_smem_bytes() {
 template <bool FAST>
 __global__ void __launch_bounds__(KH_THREADS, 2)
 kvh_kernel(const __grid_constant__ MbProgram prog, const KvPlan* __restrict__ pairs, const MbGeom g) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     constexpr int NW = KH_THREADS / 32;
     double* rawt = smem;                                               // [32 + 2 rmax][KVH_RP]
     double* vb = rawt + (KH_TR + 2 * KVH_RMAX) * KVH_RP;               // [2][32][KVH_VP]

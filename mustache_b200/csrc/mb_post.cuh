@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "mb_sort.cuh"
+#include "mb_normalize.cuh"
 
 // keys = bit patterns of the p-values (positive doubles order like their bits), payload = record slot in the block
 __global__ void __launch_bounds__(256)
@@ -251,4 +252,93 @@ post_candidates_kernel(long long rec_cap, const int* __restrict__ rec_row, const
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Enrichment filter (mustache.py:816-828): keep a candidate iff c[x, y] > 2 * mean(non-zero entries of the (y - x)-th
+// diagonal of the 2-filled tile).  Diagonals <= 4 and >= dpx + 1 are constant 2 (mean exactly 2); for the others the
+// non-zero entries are the mask pixels of that diagonal in row order, and np.mean is numpy's pairwise sum over that
+// compacted sequence divided by its length -- reproduced bit for bit: a warp compacts the diagonal into a scratch line
+// (ballot + prefix, row order), then eight lanes run numpy's pairwise summation (mb_normalize.cuh) over it.
+// ---------------------------------------------------------------------------------------------------------------
+// marks the (block, diagonal) lines the sparsity-passing candidates need: need[b * wc + (d - 4)] = 1
+__global__ void __launch_bounds__(256)
+enrich_mark_kernel(const unsigned long long* __restrict__ count, long long cap, const int* __restrict__ cblock,
+                   const int* __restrict__ crow, const int* __restrict__ ccol, const int* __restrict__ cflags, int wc, int dpx,
+                   int* __restrict__ need) {
+    unsigned long long total = *count;
+    if (total > (unsigned long long)cap) total = cap;
+    for (unsigned long long c = blockIdx.x * 256ULL + threadIdx.x; c < total; c += (unsigned long long)gridDim.x * 256ULL) {
+        const int d = ccol[c] - crow[c];
+        if ((cflags[c] & 1) && d > 4 && d < dpx + 1) need[(size_t)cblock[c] * wc + (d - 4)] = 1;
+    }
+}
+
+// gives every marked line (need == 1) a slot in the scratch pool: need[line] becomes slot + 2, lines[slot] = line
+__global__ void __launch_bounds__(256)
+enrich_list_kernel(int nlines, int* __restrict__ need, int* __restrict__ lines, unsigned* __restrict__ nlist, unsigned max_slots) {
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < nlines; l += gridDim.x * 256) {
+        if (need[l]) {
+            const unsigned slot = atomicAdd(nlist, 1u);
+            if (slot < max_slots) {
+                lines[slot] = l;
+                need[l] = (int)slot + 2;                     // >= 2: slot + 2
+            } else {
+                need[l] = -1;                                // no room in this round: handled by the next one
+            }
+        }
+    }
+}
+
+// one warp per listed line: compaction of the diagonal's non-zero values in row order, then numpy's pairwise mean
+__global__ void __launch_bounds__(256)
+enrich_mean_kernel(const double* __restrict__ raw, int n, int wc, const int* __restrict__ lines, const unsigned* __restrict__ nlist,
+                   unsigned max_slots, double* __restrict__ scratch, double* __restrict__ mean) {
+    const int lane = threadIdx.x & 31;
+    unsigned total = *nlist;
+    if (total > max_slots) total = max_slots;
+    for (unsigned slot = blockIdx.x * 8 + (threadIdx.x >> 5); slot < total; slot += gridDim.x * 8) {
+        const int line = lines[slot], b = line / wc, kidx = line - b * wc, k = kidx + 4;
+        const double* col = raw + (size_t)b * n * wc + kidx;
+        double* out = scratch + (size_t)slot * n;
+        const int rows = n - k;                                  // entries (i, i + k), i = 0 .. n - k - 1
+        int m = 0;
+        for (int i0 = 0; i0 < rows; i0 += 32) {
+            const int i = i0 + lane;
+            const double v = i < rows ? col[(size_t)i * wc] : 0.0;
+            const unsigned nzb = __ballot_sync(0xffffffffu, v != 0.0);
+            if (v != 0.0) out[m + __popc(nzb & ((1u << lane) - 1u))] = v;
+            m += __popc(nzb);
+        }
+        __syncwarp();
+        double mu = 0.0;
+        if (lane < 8) mu = __ddiv_rn(nz_pairwise8(out, (long long)m, NzIdentity(), lane, 0xffu), (double)m);   // 0 / 0 = NaN as np.mean
+        if (lane == 0) mean[slot] = mu;
+    }
+}
+
+// flags bit 1: the candidate passes the enrichment filter
+__global__ void __launch_bounds__(256)
+enrich_apply_kernel(const unsigned long long* __restrict__ count, long long cap, const int* __restrict__ cblock,
+                    const int* __restrict__ crow, const int* __restrict__ ccol, const double* __restrict__ cval, int wc, int dpx,
+                    const int* __restrict__ need, const double* __restrict__ mean, int* __restrict__ cflags) {
+    unsigned long long total = *count;
+    if (total > (unsigned long long)cap) total = cap;
+    for (unsigned long long c = blockIdx.x * 256ULL + threadIdx.x; c < total; c += (unsigned long long)gridDim.x * 256ULL) {
+        if (!(cflags[c] & 1) || (cflags[c] & 4)) continue;       // failed the sparsity filter, or already decided
+        const int d = ccol[c] - crow[c];
+        double mu = 2.0;                                         // diagonals <= 4 and >= dpx + 1 are constant 2
+        if (d > 4 && d < dpx + 1) {
+            const int s = need[(size_t)cblock[c] * wc + (d - 4)];
+            if (s < 2) continue;                                 // its line is computed in a later round
+            mu = mean[s - 2];
+        }
+        cflags[c] |= 4 | ((cval[c] > __dmul_rn(2.0, mu)) ? 2 : 0);
+    }
+}
+
+// between rounds: lines served in this round are done, deferred ones become pending again
+__global__ void __launch_bounds__(256)
+enrich_next_round_kernel(int nlines, int* __restrict__ need) {
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < nlines; l += gridDim.x * 256) need[l] = need[l] == -1 ? 1 : 0;
 }

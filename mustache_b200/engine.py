@@ -43,6 +43,7 @@ SIGNATURES = {
     "mb200_fetch_packed": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _f64p, _f64p]),
     "mb200_packed_device": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 8),
     "mb200_select_candidates": (C.c_int, [_H, C.c_double, C.c_double, C.c_double]),
+    "mb200_enrich_candidates": (C.c_int, [_H]),
     "mb200_fetch_candidates": (C.c_int, [_H, C.c_int64, _i32p, _i32p, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p,
                                          _f64p, _f64p, _i64p]),
     "mb200_fetch_q": (C.c_int, [_H, C.c_int, C.c_int64, _f64p, _i64p]),
@@ -401,6 +402,8 @@ class ScaleSpaceEngine:
                 raise EngineError(st, msg)
         self._chk(st)
         m = n_out.value
+        if m:
+            self._chk(self.lib.mb200_enrich_candidates(self.h))       # enrichment filter on the device (flags bits 1-2)
         blk, rows, cols, flg = (self._pinned("c_" + k, m, np.int32) for k in ("blk", "rows", "cols", "flg"))
         q, sg, cv = (self._pinned("c_" + k, m, np.float64) for k in ("q", "sg", "cv"))
         o9, so9 = (self._pinned("c_" + k, 9 * m, np.float64) for k in ("o9", "so9"))
@@ -417,7 +420,8 @@ class ScaleSpaceEngine:
         out = []
         for b in range(self.nblocks):
             a, z = int(bounds[b]), int(bounds[b + 1])
-            d = dict(rows=rows[a:z], cols=cols[a:z], q=q[a:z], sigma=sg[a:z], cval=cv[a:z], keep=flg[a:z] != 0,
+            d = dict(rows=rows[a:z], cols=cols[a:z], q=q[a:z], sigma=sg[a:z], cval=cv[a:z], keep=(flg[a:z] & 1) != 0,
+                     enriched=(flg[a:z] & 2) != 0,
                      o9=o9[a:z], so9=so9[a:z], nz_count=int(nz[b]), n_found=int(nf[b]))
             if pair:
                 d.update(pair9=extra[0][a:z], vself9=extra[1][a:z], vother9=extra[2][a:z])

@@ -228,11 +228,14 @@ def call_loops_from_candidates(n, dpx, start, mask_rows, mask_cols, mask_vals, c
     o9, so9 = cand["o9"][keep], cand["so9"][keep]
     more = {k: cand[k][keep] for k in (extra or ())}
     if intra:
-        d = y - x
-        means = diagonal_means(np.asarray(mask_rows), np.asarray(mask_cols), np.asarray(mask_vals), dpx, d, intra)
-        mvec = np.array([means[int(k)] for k in d])
-        with np.errstate(invalid="ignore"):
-            passing = cand["cval"][keep] > 2 * mvec
+        if "enriched" in cand:                                # decided on the device (mb200_enrich_candidates)
+            passing = cand["enriched"][keep]
+        else:
+            d = y - x
+            means = diagonal_means(np.asarray(mask_rows), np.asarray(mask_cols), np.asarray(mask_vals), dpx, d, intra)
+            mvec = np.array([means[int(k)] for k in d])
+            with np.errstate(invalid="ignore"):
+                passing = cand["cval"][keep] > 2 * mvec
         if passing.sum() == 0:
             return done([], emptied=True)
         x, y, o9, so9 = x[passing], y[passing], o9[passing], so9[passing]

@@ -343,7 +343,7 @@ def test_device_candidates_equal_host_selection(eng, octs, pt, st):
     recs = eng.records_batch()
     eng.select_candidates(pt, st)
     cands = eng.candidates_batch()
-    seen_keep = seen_drop = False
+    seen_keep = seen_drop = seen_pass = seen_fail = False
     for b in range(3):
         assert np.array_equal(eng.q_values(b), fdr_bh(recs[b]["p"]))
         ref = _host_candidates(n, dpx, masks[b], recs[b], pt, st)
@@ -353,7 +353,25 @@ def test_device_candidates_equal_host_selection(eng, octs, pt, st):
         seen_drop |= bool((~ref["keep"]).any())
         for k in ("rows", "cols", "q", "sigma", "keep", "cval", "o9", "so9"):
             assert np.array_equal(got[k], ref[k]), (b, k)
+        # enrichment filter (mustache.py:816-828) decided on the device: np.mean of the diagonal's non-zero entries bit for bit
+        kx, ky = ref["rows"][ref["keep"]], ref["cols"][ref["keep"]]
+        means = mm.postprocess.diagonal_means(*masks[b], dpx, ky - kx)
+        with np.errstate(invalid="ignore"):
+            passing = ref["cval"][ref["keep"]] > 2 * np.array([means[int(k)] for k in ky - kx])
+        assert np.array_equal(got["enriched"][got["keep"]], passing), b
+        assert not got["enriched"][~got["keep"]].any()
+        seen_pass |= bool(passing.any())
+        seen_fail |= bool((~passing).any())
     assert seen_keep and seen_drop                       # the sparsity filter both keeps and rejects on these tiles
+    assert seen_pass and seen_fail                       # and so does the enrichment filter
+    # a scratch pool of one diagonal forces one round per needed diagonal: same flags
+    os.environ["MB200_ENRICH_POOL_KB"] = "1"
+    try:
+        eng.select_candidates(pt, st)
+        again = eng.candidates_batch()
+    finally:
+        del os.environ["MB200_ENRICH_POOL_KB"]
+    assert all(np.array_equal(again[b]["enriched"], cands[b]["enriched"]) for b in range(3))
     # candidate capacity overflow: the fetch re-runs the selection with room for every record
     eng.select_candidates(pt, st, candidate_fraction=1e-9)
     small = eng.candidates_batch()

@@ -303,12 +303,20 @@ enrich_mean_kernel(const double* __restrict__ raw, int n, int wc, const int* __r
         double* out = scratch + (size_t)slot * n;
         const int rows = n - k;                                  // entries (i, i + k), i = 0 .. n - k - 1
         int m = 0;
-        for (int i0 = 0; i0 < rows; i0 += 32) {
-            const int i = i0 + lane;
-            const double v = i < rows ? col[(size_t)i * wc] : 0.0;
-            const unsigned nzb = __ballot_sync(0xffffffffu, v != 0.0);
-            if (v != 0.0) out[m + __popc(nzb & ((1u << lane) - 1u))] = v;
-            m += __popc(nzb);
+        constexpr int INFLIGHT = 8;                              // strided (one sector per element) loads in flight per lane
+        for (int i0 = 0; i0 < rows; i0 += 32 * INFLIGHT) {
+            double v[INFLIGHT];
+#pragma unroll
+            for (int q = 0; q < INFLIGHT; ++q) {
+                const int i = i0 + q * 32 + lane;
+                v[q] = i < rows ? col[(size_t)i * wc] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < INFLIGHT; ++q) {
+                const unsigned nzb = __ballot_sync(0xffffffffu, v[q] != 0.0);
+                if (v[q] != 0.0) out[m + __popc(nzb & ((1u << lane) - 1u))] = v[q];
+                m += __popc(nzb);
+            }
         }
         __syncwarp();
         double mu = 0.0;

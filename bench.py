@@ -69,12 +69,13 @@ def contact_bins(n, dpx):
 def fp64_instr_per_bin(octaves, dedupe=True):
     """FP64 instructions per contact-bin of the two separable passes: with the reference's arithmetic as it stands
     (scipy's folded taps, 3R+1 per output and pass), and as executed (the axis-0 pass shares the pair sums inside the
-    groups mb_engine.cu:plan_kv cuts: R*(2n+1)+n per group of n steps with largest radius R)."""
+    groups mb_engine.cu:plan_kv cuts: R*(2n+1)+n per group of n steps with largest radius R; groups of at most 5, or at
+    most 3 for chains that reach radius 24, which run the 64-register variant of the axis-0 kernel)."""
     from mustache_b200 import ladder
     prog = ladder.build_program(octaves, dedupe=dedupe)
     radii = sorted(s.radius for s in prog.steps)
     reference = sum(2 * (3 * r + 1) for r in radii)
-    gmax, n = 5, len(radii)
+    gmax, n = (3 if radii[-1] >= 24 else 5), len(radii)     # mb_kernels.cuh: KV_GSMALL / KV_GSMALL_RMIN / KV_GMAX
     best = [0] * (n + 1)
     for i in range(n - 1, -1, -1):
         best[i] = min(radii[i + c - 1] * (2 * c + 1) + c + best[i + c] for c in range(1, gmax + 1) if i + c <= n)

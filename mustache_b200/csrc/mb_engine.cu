@@ -296,6 +296,10 @@ int set_smem_limits(mb200_engine* e) {
         CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
         CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
         CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE, false, KV_GSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, false, KV_GSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_WIDE, true, KV_GSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
+        CU(e, cudaFuncSetAttribute(kv_kernel<KV_TH_NARROW, true, KV_GSMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kvb));
         e->kv_smem_set = kvb;
     }
     if (khb != e->kh_smem_set) {
@@ -354,12 +358,23 @@ int launch_pass(mb200_engine* e, int first_block, int nblk, MbGeom* dbg_geom, cu
         }
         return MB200_OK;
     }
+    const bool small_groups = kp.gmax <= KV_GSMALL;
     if (e->fast) {
-        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
-        else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        if (th == KV_TH_WIDE) {
+            if (small_groups) kv_kernel<KV_TH_WIDE, true, KV_GSMALL><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+            else kv_kernel<KV_TH_WIDE, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        } else {
+            if (small_groups) kv_kernel<KV_TH_NARROW, true, KV_GSMALL><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+            else kv_kernel<KV_TH_NARROW, true><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        }
     } else {
-        if (th == KV_TH_WIDE) kv_kernel<KV_TH_WIDE, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
-        else kv_kernel<KV_TH_NARROW, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        if (th == KV_TH_WIDE) {
+            if (small_groups) kv_kernel<KV_TH_WIDE, false, KV_GSMALL><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+            else kv_kernel<KV_TH_WIDE, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        } else {
+            if (small_groups) kv_kernel<KV_TH_NARROW, false, KV_GSMALL><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+            else kv_kernel<KV_TH_NARROW, false><<<gv, KV_THREADS, kvb, sq>>>(kp, g);
+        }
     }
     CU(e, cudaGetLastError());
     if (after_kv) CU(e, cudaEventRecord(after_kv, sq));
@@ -568,9 +583,10 @@ static int plan_kv(mb200_engine* e, const MbProgram& p, KvPlan& kp) {
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.st[a].radius < p.st[b].radius; });
     std::vector<long long> best(n + 1, 0);
     std::vector<int> take(n + 1, 1);
+    const int gmax = p.rmax >= KV_GSMALL_RMIN ? KV_GSMALL : KV_GMAX;
     for (int i = n - 1; i >= 0; --i) {
         best[i] = -1;
-        for (int c = 1; c <= KV_GMAX && i + c <= n; ++c) {
+        for (int c = 1; c <= gmax && i + c <= n; ++c) {
             const long long cost = (long long)p.st[order[i + c - 1]].radius * (2 * c + 1) + c + best[i + c];
             if (best[i] < 0 || cost < best[i]) {
                 best[i] = cost;
@@ -579,6 +595,7 @@ static int plan_kv(mb200_engine* e, const MbProgram& p, KvPlan& kp) {
         }
     }
     kp.rmax = p.rmax;
+    kp.gmax = gmax;
     int off = 0;
     for (int pos = 0; pos < n; pos += take[pos]) {
         const int cnt = take[pos];

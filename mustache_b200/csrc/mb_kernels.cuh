@@ -66,6 +66,12 @@ struct MbProgram {
 // for j beyond the slot's own radius.  Adding (pair sum) * 0 before a step's first real tap leaves its accumulator
 // unchanged, so the padded taps cost FP64 instructions but not exactness.
 #define KV_GMAX 5
+// Chains with large radii (the 4-octave ladder) are cut into groups of at most KV_GSMALL: 0.7 % more FP64 instructions than
+// groups of 5, but 12 instead of 20 accumulators -- the kernel fits 64 registers and three CTAs per SM (the 61 KB tile is
+// then the limit).  Measured on the 10k tile: axis-0 pass 5.67 -> 5.37 ms; on the 2-octave shapes the small groups are
+// slower (0.85 -> 0.97 ms on 24 x 2000^2), so those keep groups of 5 at two CTAs per SM.
+#define KV_GSMALL 3
+#define KV_GSMALL_RMIN 24   // chains whose largest radius reaches this use the small groups
 #define KV_MAX_GROUPS 32
 #define KV_MAX_TAPS_T 2048
 struct KvGroup {
@@ -77,7 +83,8 @@ struct KvGroup {
 struct KvPlan {
     int n_groups;
     int rmax;
-    int pad[2];
+    int gmax;           // largest group of this plan (KV_GSMALL or KV_GMAX): selects the kernel variant
+    int pad;
     KvGroup grp[KV_MAX_GROUPS];
     double tapsT[KV_MAX_TAPS_T];
 };
@@ -410,8 +417,8 @@ __device__ __forceinline__ void kv_group(const double* __restrict__ ctr, const d
     }
 }
 
-template <int KV_TH, bool FAST>
-__global__ void __launch_bounds__(KV_THREADS, 2)
+template <int KV_TH, bool FAST, int GM = KV_GMAX>
+__global__ void __launch_bounds__(KV_THREADS, GM <= KV_GSMALL ? 4 : 2)
 kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
     extern __shared__ double smem[];
     double* cs = smem + KV_GUARD * KV_TW;           // [(KV_TH + 2 rmax)][KV_TW]; the last window of a radius < 3 step
@@ -476,12 +483,20 @@ kv_kernel(const __grid_constant__ KvPlan plan, const MbGeom g) {
             const KvGroup& gr = plan.grp[gi];
             if (dmax_w < 2 - gr.rmax || dmin_w > g.dhi + 2 + gr.rmax) continue;     // warp-uniform: nobody reads these
             const double* tp = plan.tapsT + gr.tap_off;
-            switch (gr.n) {
-                case 1: kv_group<1, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 2: kv_group<2, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 3: kv_group<3, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                case 4: kv_group<4, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
-                default: kv_group<5, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+            if (GM <= KV_GSMALL) {
+                switch (gr.n) {
+                    case 1: kv_group<1, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    case 2: kv_group<2, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    default: kv_group<3, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                }
+            } else {
+                switch (gr.n) {
+                    case 1: kv_group<1, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    case 2: kv_group<2, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    case 3: kv_group<3, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    case 4: kv_group<4, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                    default: kv_group<5, FAST>(ctr, tp, gr.rmax, gr.step, vrow, step_stride, kstride, vmask); break;
+                }
             }
         }
     }

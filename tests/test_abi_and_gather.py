@@ -63,7 +63,7 @@ def test_cli_parsers_match_reference_defaults():
 
 def test_kv_plan_is_a_partition_with_the_optimal_cost():
     """The axis-0 kernel's grouping (host-only entry point, runs without a GPU): every step in exactly one group of at
-    most 5, groups ordered by radius, and the cost equals the dynamic programme bench.py restates for the roofline."""
+    most 5 (3 for chains that reach radius 24), groups ordered by radius, and the cost equals the dynamic programme bench.py restates for the roofline."""
     import bench
     from mustache_b200 import engine, ladder
     lib = engine.load_library()
@@ -75,7 +75,7 @@ def test_kv_plan_is_a_partition_with_the_optimal_cost():
         st = lib.mb200_kv_plan(len(radius), radius.ctypes.data_as(engine._i32p), grp.ctypes.data_as(engine._i32p), C.byref(cost))
         assert st == 0 and (grp >= 0).all()
         sizes = np.bincount(grp)
-        assert sizes.min() >= 1 and sizes.max() <= 5
+        assert sizes.min() >= 1 and sizes.max() <= (3 if radius.max() >= 24 else 5)   # KV_GSMALL for large-radius chains
         by_radius = [sorted(radius[grp == g]) for g in range(len(sizes))]
         assert all(a[-1] <= b[0] for a, b in zip(by_radius, by_radius[1:]))          # groups are contiguous in radius
         assert cost.value == sum(r[-1] * (2 * len(r) + 1) + len(r) for r in by_radius)

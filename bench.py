@@ -20,8 +20,11 @@ DoG, 3x3 maxima, extremum test, exponential-fit p-values, compact records) over 
            are independent; `wall_ms_per_step` is the host clock around the same region).
 `e2e`    : same metric through the public API with HOST buffers, the sequence the CLI runs: host -> device upload of every
            tile (dense pinned tile for config 2, block COO for the chromosome configs), all kernels, BH + `o < pt` + sparsity
-           filter on the device, device -> host read of the selected candidates, and for
-           N > 1 the gather of the per-block result rows on the rank that writes the TSV.
+           + enrichment filter on the device, device -> host read of the selected candidates, and for
+           N > 1 the gather of the per-block result rows on the rank that writes the TSV.  Measured twice: with one engine
+           handle (`single_engine_ms_per_step`: run, then post-processing and fetch, then the next run) and with two handles
+           used alternately (mb200_run_after; the reported `e2e`): the post-processing and fetch of batch k overlap the run
+           of batch k+1, timed from an empty pipeline to the last result on the host.
 `--impl reference` times the UNMODIFIED reference (baseline/_ref, mustache.py:697-778 up to the intercepted
 multipletests call) on all host cores over a bounded sample of the same workload; when baseline/_ref is absent, the
 oracle port on the same scipy kernels.
@@ -312,7 +315,7 @@ class Harness:
         return float(t.item())
 
 
-def measure(h, eng, cfg, name, steps, warmup, device_only=False):
+def measure(h, eng, cfg, name, steps, warmup, device_only=False, eng2=None):
     """Device-resident and end-to-end timing of one workload on this rank's engine.  Returns a dict of raw figures."""
     from mustache_b200 import blockrun, sharding
     rank, world = h.rank, h.world
@@ -379,21 +382,26 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
         return out
 
     # ---- end to end through the public API with host buffers ----
-    # Every step: host tiles -> device, all kernels, ONE packed records fetch, and for N > 1 the gather of the per-block
-    # result rows on rank 0.  The uploads of step k+1 are issued right after the run of step k (the engine double-buffers
-    # tiles on a second stream), which is how a caller with more than one batch uses the API.
+    # Every step: host tiles -> device, all kernels, BH + selection + filters on the device, ONE fetch of the selected
+    # candidates, and for N > 1 the gather of the per-block result rows on rank 0.  The uploads of the next batch are issued
+    # right after a run (the engine double-buffers tiles on a second stream), which is how a caller with more than one batch
+    # uses the API.
     dev = blockrun.collective_device(eng)
+    sel = (0.05 if nmaps == 2 else 0.1, 0.88)
+
+    def fetch(e):
+        # the CLI's path: BH + o < pt + sparsity + enrichment filter on the device, only the selected candidates (with the
+        # neighbourhoods the clustering and, for config 5, the differential selection read) come back
+        e.select_candidates(*sel)
+        recs = e.candidates_batch(pair=(nmaps == 2))
+        rows = np.array([[rank, b, r["n_found"], r["nz_count"]] for b, r in enumerate(recs)], dtype=np.float64).reshape(-1, 4)
+        got = sharding.gather_loops(rows, rank, world, dev) if world > 1 else rows
+        return recs, got
 
     def e2e_step():
         run()
         upload()
-        # the CLI's path: BH + o < pt + sparsity filter on the device, only the selected candidates (with the neighbourhoods
-        # the clustering and, for config 5, the differential selection read) come back
-        eng.select_candidates(0.05 if nmaps == 2 else 0.1, 0.88)
-        recs = eng.candidates_batch(pair=(nmaps == 2))
-        rows = np.array([[rank, b, r["n_found"], r["nz_count"]] for b, r in enumerate(recs)], dtype=np.float64).reshape(-1, 4)
-        got = sharding.gather_loops(rows, rank, world, dev) if world > 1 else rows
-        return recs, got
+        return fetch(eng)
 
     upload()
     for _ in range(max(1, warmup // 2)):
@@ -403,7 +411,70 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     for _ in range(steps):
         recs, got = e2e_step()
     h.barrier()
-    e2e_ms = h.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    e2e_single_ms = h.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    e2e_ms, e2e_mode = e2e_single_ms, "one engine: run, then post-processing and fetch, then the next run"
+
+    # Two engine handles on the GPU used alternately (mb200_run_after): the run of batch k+1 follows the run of batch k back
+    # to back while BH / selection / filters and the candidate fetch of batch k overlap it.  The timed region starts with an
+    # empty pipeline and ends with every result on the host: `steps` uploads, runs and fetches.
+    if eng2 is not None:
+        try:
+            eng2.set_octaves(cfg["octaves"], differential=(nmaps == 2))
+            eng2.configure(n, dpx, max(nblk, nmaps))
+            engines = [eng, eng2]
+
+            def upload_to(e):
+                if cfg["kind"] == "dense":
+                    for b, t in enumerate(tiles):
+                        e.upload_dense(b, t)
+                elif nblk:
+                    e.upload_coo_batch(0, offsets, *flat)
+
+            trace = [] if os.environ.get("BENCH_TRACE") else None
+
+            def pipelined(count):
+                out = None
+                for i in range(count + 1):
+                    e, o = engines[i % 2], engines[(i + 1) % 2]
+                    ta = time.perf_counter()
+                    if i < count:
+                        if i > 0:
+                            e.run_after(o)
+                        (e.run_differential if nmaps == 2 else e.run)()
+                        tb = time.perf_counter()
+                        upload_to(e)                       # tiles of the batch this engine runs next
+                    else:
+                        tb = ta
+                    tc = time.perf_counter()
+                    if i > 0:
+                        out = fetch(o)                     # results of step i - 1, next to the run of step i
+                    if trace is not None:
+                        td = time.perf_counter()
+                        trace.append((round((tb - ta) * 1e3, 3), round((tc - tb) * 1e3, 3), round((td - tc) * 1e3, 3),
+                                      round(o.timing()["total_ms"], 3) if i > 0 else None, round(o.post_ms(), 3) if i > 0 else None))
+                return out
+
+            for e in engines:
+                upload_to(e)
+            pipelined(max(2, warmup // 2))
+            for e in engines:
+                e.sync()
+            h.barrier()
+            t0 = time.perf_counter()
+            recs, got = pipelined(steps)
+            h.barrier()
+            e2e_ms = h.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+            e2e_mode = ("two engine handles used alternately (mb200_run_after): post-processing and fetch of batch k overlap "
+                        "the run of batch k+1; timed from an empty pipeline to the last result on the host")
+            eng2.sync()
+            if trace is not None:
+                sys.stderr.write("pipeline trace (run enqueue, upload enqueue, fetch, device run ms, post ms): %s\n" % trace[-(steps + 1):])
+        except Exception as err:                           # e.g. not enough memory for the second engine's scratch
+            e2e_mode += " (two-engine pipeline unavailable: %s)" % str(err)[:120]
+            eng.configure(n, dpx, max(nblk, nmaps))
+            upload()
+            run()
+            recs, got = fetch(eng)
     eng.sync()
     n_found = int(sum(r["n_found"] for r in recs))
     total_found = h.sum_over_ranks(n_found)
@@ -413,7 +484,8 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False):
     # block, row, col, flags; q, sigma, cval; o9, so9 (+ pair9, vself9, vother9 for the differential path); counters
     d2h = n_cand * (4 * 4 + 3 * 8 + (45 if nmaps == 2 else 18) * 8) + nblk * 16 + 8
     post_ms = eng.post_ms()
-    out.update(e2e_ms=e2e_ms, e2e_value=bins_all / (e2e_ms * 1e-3), h2d=int(h.sum_over_ranks(h2d)),
+    out.update(e2e_ms=e2e_ms, e2e_value=bins_all / (e2e_ms * 1e-3), e2e_single_ms=e2e_single_ms, e2e_mode=e2e_mode,
+               h2d=int(h.sum_over_ranks(h2d)),
                d2h=int(h.sum_over_ranks(d2h)), n_found=int(total_found), post_ms=post_ms,
                n_candidates=None if n_cand is None else int(h.sum_over_ranks(n_cand)))
     return out
@@ -503,6 +575,7 @@ def main():
     ap.add_argument("--fusion", type=int, default=0, help="mb200_set_fusion: 1 = axis-1 + scoring fused, 2 = axis-0 + axis-1 fused")
     ap.add_argument("--overlap", action="store_true", help="two half-batches on two streams (mb200_set_overlap)")
     ap.add_argument("--no-fast", action="store_true", help="skip the extra device-resident measurement in the opt-in FMA mode")
+    ap.add_argument("--single-engine", action="store_true", help="e2e with one engine handle only (no pipelining of the post-processing)")
     ap.add_argument("--device-only", action="store_true", help="profiling aid: only the device-resident steps (no e2e, no CPU leg)")
     args = ap.parse_args()
     if args.config == "norm":
@@ -556,7 +629,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()              # 200 ms period: started before the warm-up so that short timed regions are covered
-    m = measure(h, eng, cfg, args.config, args.steps, args.warmup, device_only=args.device_only)
+    eng2 = None if (args.device_only or args.single_engine) else ScaleSpaceEngine(local_rank)   # second handle for the e2e pipeline
+    m = measure(h, eng, cfg, args.config, args.steps, args.warmup, device_only=args.device_only, eng2=eng2)
     clocks = sampler.stop() if rank == 0 else None
     if args.device_only:
         if rank == 0:
@@ -570,11 +644,12 @@ def main():
         eng.set_arithmetic(False)
     c4 = None
     if not strong and not args.no_config4:
-        c4m = measure(h, eng, CONFIGS["4"], "4", max(3, args.steps), 3)
+        c4m = measure(h, eng, CONFIGS["4"], "4", max(3, args.steps), 3, eng2=eng2)
         c4 = {"workload": CONFIGS["4"]["workload"], "scaling": "strong", "n_gpus": world, "value": c4m["value"],
               "unit": "contact-bins/s", "ms_per_step": c4m["step_ms"], "blocks_on_rank0": c4m["blocks_rank"],
               "e2e": {"value": c4m["e2e_value"], "ms_per_step": c4m["e2e_ms"], "h2d_bytes_per_step": c4m["h2d"],
-                      "d2h_bytes_per_step": c4m["d2h"]}, "records_per_step": c4m["n_found"]}
+                      "d2h_bytes_per_step": c4m["d2h"], "single_engine_ms_per_step": c4m["e2e_single_ms"]},
+              "records_per_step": c4m["n_found"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -591,7 +666,8 @@ def main():
            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks,
            "e2e": {"value": m["e2e_value"], "unit": "contact-bins/s", "ms_per_step": m["e2e_ms"],
-                   "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+                   "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "mode": m["e2e_mode"],
+                   "single_engine_ms_per_step": m["e2e_single_ms"]},
            "gpu_launches": m["launches"], "records_per_step": m["n_found"], "candidates_per_step": m["n_candidates"],
            "post_ms_per_step": m["post_ms"], "phases_ms_per_step": m["phases"],
            "wall_ms_per_step": m["wall_step_ms"],

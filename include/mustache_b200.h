@@ -88,6 +88,11 @@ MB200_API int mb200_upload_band_host(mb200_engine* e, int block, const double* b
  * and p-value (:755-756).  Asynchronous on the engine's stream; mb200_sync / the fetch calls wait. */
 MB200_API int mb200_run(mb200_engine* e);
 MB200_API int mb200_sync(mb200_engine* e);
+/* Two engines on one GPU, used alternately for a stream of batches (the reference keeps several blocks in flight with its
+ * `-p` worker processes, mustache.py:926-934): everything enqueued on `e` from now on starts after the kernels `other` has
+ * enqueued so far.  With it, the run of batch k+1 on one engine follows the run of batch k on the other back to back while
+ * the post-processing and the result fetch of batch k (mb200_select_candidates ...) overlap it.  Same device required. */
+MB200_API int mb200_run_after(mb200_engine* e, mb200_engine* other);
 
 /* nz_count = np.sum(nz) (mustache.py:701; guards at :701 and :775 stay with the caller), n_found = sum(pAll != 2). */
 MB200_API int mb200_block_counts(mb200_engine* e, int block, int64_t* nz_count, int64_t* n_found);

@@ -79,6 +79,11 @@ struct mb200_engine {
                                      // batch overlaps the Gaussian passes of the other half)
     cudaStream_t stream2 = nullptr;  // second compute stream of the overlapped mode
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t post_stream = nullptr;   // high priority: BH / selection / filters / candidate fetch of a finished run; next to a
+                                          // run of ANOTHER engine (mb200_run_after) its small grids are not queued behind that
+                                          // run's large ones
+    cudaEvent_t ev_post_done = nullptr;   // last work queued on post_stream; the next run on `stream` waits for it
+    cudaEvent_t ev_chain = nullptr;  // mb200_run_after: marks what this engine has enqueued when another engine chains behind it
     int fusion = 0;                  // mb200_set_fusion: 1 = axis-1 + scoring fused (khs_kernel) whenever the chain fits, 0 = never
     int fast = 0;                    // mb200_set_arithmetic: 0 = the reference's multiply-then-add, 1 = fused multiply-add
     int pass_limit = 0;              // mb200_set_pass_limit: upper bound on blocks per pass (0 = as many as fit)
@@ -114,6 +119,7 @@ int ensure(mb200_engine* e, DevBuf& b, size_t bytes) {
     if (b.p) {
         CU(e, cudaStreamSynchronize(e->stream));
         if (e->stream2) CU(e, cudaStreamSynchronize(e->stream2));
+        if (e->post_stream) CU(e, cudaStreamSynchronize(e->post_stream));
         CU(e, cudaStreamSynchronize(e->up_stream));
         CU(e, cudaFree(b.p));
         b.p = nullptr;
@@ -494,8 +500,11 @@ int mb200_create(int device, mb200_engine** out) {
         cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->post_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_post_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_chain, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_up, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_run[1], cudaEventDisableTiming) != cudaSuccess ||
@@ -537,6 +546,9 @@ void mb200_destroy(mb200_engine* e) {
         if (e->ev_run[k]) cudaEventDestroy(e->ev_run[k]);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_chain) cudaEventDestroy(e->ev_chain);
+    if (e->ev_post_done) cudaEventDestroy(e->ev_post_done);
+    if (e->post_stream) { cudaStreamSynchronize(e->post_stream); cudaStreamDestroy(e->post_stream); }
     if (e->stream2) { cudaStreamSynchronize(e->stream2); cudaStreamDestroy(e->stream2); }
     if (e->up_stream) cudaStreamDestroy(e->up_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -718,6 +730,7 @@ int mb200_configure(mb200_engine* e, int n, int dpx, int intra, int nblocks, dou
     if (n <= 2 * e->prog.rmax + 1) return fail(e, MB200_ERR_ARG, "tile side %d too small for radius %d", n, e->prog.rmax);
     int st = use_device(e);
     if (st) return st;
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_post_done, 0));    // a post-processing still in flight reads the tile slots
     e->n = n;
     e->dpx = dpx;
     e->intra = intra;
@@ -946,6 +959,7 @@ int mb200_run(mb200_engine* e) {
     e->ran_diff = false;
     e->packed = false;
     e->post_done = false;
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_post_done, 0));    // the post-processing of the previous batch reads its records
     if ((st = adopt_uploads(e))) return st;
     // Passes: as many blocks as the scratch holds.  Overlapped mode: the scratch is split into two regions and the passes
     // alternate between two streams, so that the (issue-bound) scoring of one half of the batch runs while the (FP64 /
@@ -1010,6 +1024,16 @@ int mb200_run(mb200_engine* e) {
     return MB200_OK;
 }
 
+int mb200_run_after(mb200_engine* e, mb200_engine* other) {
+    if (!e || !other || e == other) return MB200_ERR_ARG;
+    if (e->device != other->device) return fail(e, MB200_ERR_ARG, "mb200_run_after needs both engines on one device");
+    int st = use_device(e);
+    if (st) return st;
+    CU(e, cudaEventRecord(other->ev_chain, other->stream));
+    CU(e, cudaStreamWaitEvent(e->stream, other->ev_chain, 0));
+    return MB200_OK;
+}
+
 int mb200_sync(mb200_engine* e) {
     if (!e) return MB200_ERR_ARG;
     int st = use_device(e);
@@ -1017,6 +1041,7 @@ int mb200_sync(mb200_engine* e) {
     CU(e, cudaStreamSynchronize(e->up_stream));
     CU(e, cudaStreamSynchronize(e->stream2));
     CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(e->post_stream));
     return MB200_OK;
 }
 
@@ -1184,7 +1209,7 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     if (st) return st;
     const int B = e->nblocks;
     const size_t slots = (size_t)B * e->rec_cap;
-    cudaStream_t sq = e->stream;
+    cudaStream_t sq = e->post_stream;                 // the run is complete once refresh_counts below has returned
     // one small device -> host read of the record counters: the sort and BH grids are sized by the fullest block, not by
     // the capacity, and an overflow or a non-finite tile is reported before any work is queued
     if ((st = refresh_counts(e))) return st;
@@ -1255,6 +1280,7 @@ int mb200_select_candidates(mb200_engine* e, double pt, double st_thr, double ca
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_post1, sq));
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));          // the candidate kernel reads the tile slot too
+    CU(e, cudaEventRecord(e->ev_post_done, sq));
     e->launches += 7;
     e->post_done = true;
     return MB200_OK;
@@ -1267,7 +1293,7 @@ int mb200_enrich_candidates(mb200_engine* e) {
     if (!e->post_done) return fail(e, MB200_ERR_ARG, "mb200_select_candidates has not been called for this batch");
     int st = use_device(e);
     if (st) return st;
-    cudaStream_t sq = e->stream;
+    cudaStream_t sq = e->post_stream;
     unsigned long long tot = 0;
     CU(e, cudaMemcpyAsync(&tot, e->cd_count.p, sizeof(tot), cudaMemcpyDeviceToHost, sq));
     CU(e, cudaStreamSynchronize(sq));
@@ -1309,6 +1335,7 @@ int mb200_enrich_candidates(mb200_engine* e) {
         enrich_next_round_kernel<<<gl, 256, 0, sq>>>(nlines, (int*)e->en_need.p);
     }
     CU(e, cudaEventRecord(e->ev_run[e->slot_run], sq));              // the mean kernel reads the tile slot
+    CU(e, cudaEventRecord(e->ev_post_done, sq));
     return MB200_OK;
 }
 
@@ -1326,30 +1353,30 @@ int mb200_fetch_candidates(mb200_engine* e, int64_t capacity, int32_t* block, in
             return fail(e, MB200_ERR_CAPACITY, "block %d produced %llu records, capacity %lld", b, e->h_rec[b], e->rec_cap);
     }
     unsigned long long tot = 0;
-    CU(e, cudaMemcpyAsync(&tot, e->cd_count.p, sizeof(tot), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaMemcpyAsync(&tot, e->cd_count.p, sizeof(tot), cudaMemcpyDeviceToHost, e->post_stream));
+    CU(e, cudaStreamSynchronize(e->post_stream));
     if (n_out) *n_out = (int64_t)tot;
     if ((long long)tot > e->cand_cap)
         return fail(e, MB200_ERR_CAPACITY, "%llu candidates, capacity %lld: raise candidate_fraction and call mb200_select_candidates again", tot, e->cand_cap);
     if (tot == 0 || capacity <= 0) return MB200_OK;
     if ((int64_t)tot > capacity) return fail(e, MB200_ERR_CAPACITY, "%llu candidates, caller capacity %lld", tot, (long long)capacity);
     const size_t m = (size_t)tot;
-    if (block) CU(e, cudaMemcpyAsync(block, e->cd_block.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (row) CU(e, cudaMemcpyAsync(row, e->cd_row.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (col) CU(e, cudaMemcpyAsync(col, e->cd_col.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (flags) CU(e, cudaMemcpyAsync(flags, e->cd_flags.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    if (q) CU(e, cudaMemcpyAsync(q, e->cd_q.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (sigma) CU(e, cudaMemcpyAsync(sigma, e->cd_sigma.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (cval) CU(e, cudaMemcpyAsync(cval, e->cd_cval.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (o9) CU(e, cudaMemcpyAsync(o9, e->cd_o9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (so9) CU(e, cudaMemcpyAsync(so9, e->cd_so9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (block) CU(e, cudaMemcpyAsync(block, e->cd_block.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->post_stream));
+    if (row) CU(e, cudaMemcpyAsync(row, e->cd_row.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->post_stream));
+    if (col) CU(e, cudaMemcpyAsync(col, e->cd_col.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->post_stream));
+    if (flags) CU(e, cudaMemcpyAsync(flags, e->cd_flags.p, m * sizeof(int), cudaMemcpyDeviceToHost, e->post_stream));
+    if (q) CU(e, cudaMemcpyAsync(q, e->cd_q.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+    if (sigma) CU(e, cudaMemcpyAsync(sigma, e->cd_sigma.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+    if (cval) CU(e, cudaMemcpyAsync(cval, e->cd_cval.p, m * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+    if (o9) CU(e, cudaMemcpyAsync(o9, e->cd_o9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+    if (so9) CU(e, cudaMemcpyAsync(so9, e->cd_so9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
     if (pair9 || vself9 || vother9) {
         if (!e->post_diff) return fail(e, MB200_ERR_ARG, "the batch was not run with mb200_run_differential");
-        if (pair9) CU(e, cudaMemcpyAsync(pair9, e->cd_pair9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        if (vself9) CU(e, cudaMemcpyAsync(vself9, e->cd_vs9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        if (vother9) CU(e, cudaMemcpyAsync(vother9, e->cd_vo9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (pair9) CU(e, cudaMemcpyAsync(pair9, e->cd_pair9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+        if (vself9) CU(e, cudaMemcpyAsync(vself9, e->cd_vs9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+        if (vother9) CU(e, cudaMemcpyAsync(vother9, e->cd_vo9.p, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
     }
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaStreamSynchronize(e->post_stream));
     return MB200_OK;
 }
 
@@ -1362,8 +1389,8 @@ int mb200_fetch_q(mb200_engine* e, int block, int64_t capacity, double* q, int64
     const int64_t m = std::min<int64_t>(nf, capacity);
     if (m <= 0) return MB200_OK;
     if (!q) return fail(e, MB200_ERR_ARG, "null output array");
-    CU(e, cudaMemcpyAsync(q, (double*)e->rec_q.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CU(e, cudaStreamSynchronize(e->stream));
+    CU(e, cudaMemcpyAsync(q, (double*)e->rec_q.p + (size_t)block * e->rec_cap, m * sizeof(double), cudaMemcpyDeviceToHost, e->post_stream));
+    CU(e, cudaStreamSynchronize(e->post_stream));
     return MB200_OK;
 }
 
@@ -1480,6 +1507,7 @@ int mb200_debug_level(mb200_engine* e, int block, int step, double* gauss_out, d
     const size_t bytes = (size_t)e->n * e->n * sizeof(double);
     if ((st = ensure(e, e->dbgG, bytes))) return st;
     if ((st = ensure(e, e->dbgL, bytes))) return st;
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_post_done, 0));
     if ((st = adopt_uploads(e))) return st;
     CU(e, cudaMemsetAsync(e->dbgG.p, 0, bytes, e->stream));
     CU(e, cudaMemsetAsync(e->dbgL.p, 0, bytes, e->stream));

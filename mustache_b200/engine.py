@@ -36,6 +36,7 @@ SIGNATURES = {
     "mb200_upload_band_host": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
     "mb200_run": (C.c_int, [_H]),
     "mb200_sync": (C.c_int, [_H]),
+    "mb200_run_after": (C.c_int, [_H, _H]),
     "mb200_block_counts": (C.c_int, [_H, C.c_int, _i64p, _i64p]),
     "mb200_fetch_records": (C.c_int, [_H, C.c_int, C.c_int64, _i32p, _i32p, _f64p, _i32p, _f64p, _i64p]),
     "mb200_batch_counts": (C.c_int, [_H, _i64p, _i64p]),
@@ -285,6 +286,11 @@ class ScaleSpaceEngine:
         self._chk(self.lib.mb200_run(self.h))
         if sync:
             self.sync()
+
+    def run_after(self, other):
+        """Everything enqueued on this engine from now on starts after what `other` (same GPU) has enqueued so far: two
+        engines used alternately keep the GPU on the runs while the post-processing of the previous batch overlaps."""
+        self._chk(self.lib.mb200_run_after(self.h, other.h))
 
     def run_differential(self):
         """Blocks 2k / 2k+1 = map 1 / map 2 of pair k: both maps scored + pPair of every record."""

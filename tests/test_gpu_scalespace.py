@@ -228,3 +228,68 @@ def test_unusual_ladders_match_oracle(eng, octaves):
     assert np.array_equal(rec["rows"], ref["rows"][found]) and np.array_equal(rec["cols"], ref["cols"][found])
     assert np.array_equal(rec["v"], ref["v"][found]) and np.array_equal(rec["sigma"], ref["scale"][found])
     assert np.abs(rec["p"] - ref["p"][found]).max() <= P_TOL
+
+
+def test_two_engines_alternating_give_the_single_engine_results(eng):
+    """mb200_run_after: two engine handles on one GPU used alternately for a stream of batches (the run of batch k+1 behind
+    the run of batch k, post-processing and fetch of batch k next to it) return exactly what one engine returns batch by
+    batch -- records, device-selected candidates and enrichment flags."""
+    from mustache_b200 import synth as gen
+    from mustache_b200.engine import ScaleSpaceEngine, EngineError
+    n, dpx, octs = 512, 200, [1.6, 3.2]
+    batches = [[gen.band_to_dense(gen.dense_band_tile(n, dpx, seed=70 + 3 * k + b, blob_seed=170 + 3 * k + b, nblobs=12,
+                                                     missing=0.3), n) for b in range(2)] for k in range(5)]
+
+    def keyed(r):
+        o = np.lexsort((r["cols"], r["rows"]))
+        return {k: np.asarray(v)[o] for k, v in r.items() if isinstance(v, np.ndarray)}
+
+    def same(a, b):
+        a, b = keyed(a), keyed(b)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+    eng.set_octaves(octs)
+    ref = []
+    for tiles in batches:
+        eng.configure(n, dpx, 2)
+        for b, t in enumerate(tiles):
+            eng.upload_dense(b, t)
+        eng.run()
+        eng.select_candidates(0.2, 0.88)
+        ref.append((eng.candidates_batch(), [eng.records(b) for b in range(2)]))
+    assert sum(len(c["rows"]) for cands, _ in ref for c in cands) > 0
+
+    other = ScaleSpaceEngine(eng.device)
+    try:
+        engines = [eng, other]
+        for e in engines:
+            e.set_octaves(octs)
+            e.configure(n, dpx, 2)
+        for k in range(2):                                   # first tiles of each engine
+            for b, t in enumerate(batches[k]):
+                engines[k].upload_dense(b, t)
+        got = []
+        for i in range(len(batches) + 1):
+            e, o = engines[i % 2], engines[(i + 1) % 2]
+            if i < len(batches):
+                if i > 0:
+                    e.run_after(o)
+                e.run()
+                if i + 2 < len(batches):                     # tiles of the batch this engine runs next
+                    for b, t in enumerate(batches[i + 2]):
+                        e.upload_dense(b, t)
+            if i > 0:
+                o.select_candidates(0.2, 0.88)
+                got.append((o.candidates_batch(), [o.records(b) for b in range(2)]))
+        assert len(got) == len(ref)
+        for (gc, gr), (rc, rr) in zip(got, ref):
+            for b in range(2):
+                same(gc[b], rc[b])
+                same(gr[b], rr[b])
+                assert gc[b]["n_found"] == rc[b]["n_found"] and gc[b]["nz_count"] == rc[b]["nz_count"]
+        with pytest.raises(EngineError):
+            eng.run_after(eng)
+    finally:
+        other.close() if hasattr(other, "close") else None

@@ -622,6 +622,34 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int n_steps = prog.n_steps;
+    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
+    // into its slot of the ring, after every warp released the boxes it overlaps.
+    const MbStage* stg = prog.stage;
+    int next_issue = 0, next_prefetch = 0;
+    auto issue_ready = [&](int p_now) {
+        if (KH_PREFETCH > 0) {                                  // boxes the ring cannot hold yet: into L2
+            while (next_prefetch < n_steps && next_prefetch <= p_now + KH_LOOKAHEAD + KH_PREFETCH) {
+                if (next_prefetch > p_now + KH_LOOKAHEAD && elect_one())
+                    tma_prefetch_box3d(&tm->v[next_prefetch], (js - prog.st[next_prefetch].radius - g.vlo) & ~1, i0,
+                                       next_prefetch * g.zstride + g.zoff + b);
+                ++next_prefetch;
+            }
+        }
+        while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
+            const int dep = stg[next_issue].dep;
+            if (dep >= p_now) break;                            // the overlapped box is still ahead of this warp
+            if (elect_one()) {
+                if (dep >= 0) mbar_wait(&empty[dep], 0);
+                const int s = next_issue;
+                const int R = prog.st[s].radius;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
+                // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
+                tma_load_box3d(vbuf + stg[next_issue].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.zstride + g.zoff + b, &full[s]);
+            }
+            ++next_issue;
+        }
+    };
+    if (!border && warp == 0) issue_ready(0);   // first boxes in flight before the store geometry below is set up
     // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
                             (js + warp * KH_K < g.n);
@@ -656,34 +684,6 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     // warp-uniform: no pixel of the chunk needs a mask (true for all but the tiles on the band / image edges)
     const bool interior = __all_sync(0xffffffffu, zmask == (1u << KH_K) - 1u && qmask == (1u << (KH_TR / 4)) - 1u);
 
-    // Producer side (one elected lane of warp 0): one TMA box copy per step -- the 32 x (TC + 2R + 2) axis-0 tile of step s
-    // into its slot of the ring, after every warp released the boxes it overlaps.
-    const MbStage* stg = prog.stage;
-    int next_issue = 0, next_prefetch = 0;
-    auto issue_ready = [&](int p_now) {
-        if (KH_PREFETCH > 0) {                                  // boxes the ring cannot hold yet: into L2
-            while (next_prefetch < n_steps && next_prefetch <= p_now + KH_LOOKAHEAD + KH_PREFETCH) {
-                if (next_prefetch > p_now + KH_LOOKAHEAD && elect_one())
-                    tma_prefetch_box3d(&tm->v[next_prefetch], (js - prog.st[next_prefetch].radius - g.vlo) & ~1, i0,
-                                       next_prefetch * g.zstride + g.zoff + b);
-                ++next_prefetch;
-            }
-        }
-        while (next_issue < n_steps && next_issue <= p_now + KH_LOOKAHEAD) {
-            const int dep = stg[next_issue].dep;
-            if (dep >= p_now) break;                            // the overlapped box is still ahead of this warp
-            if (elect_one()) {
-                if (dep >= 0) mbar_wait(&empty[dep], 0);
-                const int s = next_issue;
-                const int R = prog.st[s].radius;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
-                // x = column index of the first needed element in the skewed view, floored to even (16-byte aligned rows)
-                tma_load_box3d(vbuf + stg[next_issue].off, &tm->v[s], (js - R - g.vlo) & ~1, i0, s * g.zstride + g.zoff + b, &full[s]);
-            }
-            ++next_issue;
-        }
-    };
-    if (!border && warp == 0) issue_ready(0);
 
     double gA[KH_K], gB[KH_K];
 #pragma unroll
@@ -702,16 +702,27 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             __syncthreads();                                     // previous step's readers are done with the buffer
             const double* vin = g.V + ((size_t)s * g.zstride + g.zoff + b) * g.plane_v;
             const int wlen = KH_TC + 1 + 2 * R;
-            for (int r = warp; r < KH_TR; r += NW) {
-                const int ii = i0 + r;
-                for (int t = lane; t < wlen; t += 32) {
-                    double val = 0.0;
-                    if (ii < g.n) {
-                        const int jj = reflect_idx(js - R + t, g.n);
+            // one warp per tile row, four rows x two column groups (= eight independent loads per thread) in flight at a time
+            for (int t0 = lane; t0 < wlen; t0 += 64) {
+                double val[2][KH_TR / NW];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t0 + 32 * h;
+                    const int jj = reflect_idx(js - R + min(t, wlen - 1), g.n);
+#pragma unroll
+                    for (int q = 0; q < KH_TR / NW; ++q) {
+                        const int ii = i0 + warp + q * NW;
                         const int dd = jj - ii - g.vlo;
-                        if (dd >= 0 && dd < g.wv) val = vin[(size_t)ii * g.wv + dd];
+                        val[h][q] = (ii < g.n && dd >= 0 && dd < g.wv) ? vin[(size_t)ii * g.wv + dd] : 0.0;
                     }
-                    vst[r * bw + t] = val;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t0 + 32 * h;
+                    if (t < wlen) {
+#pragma unroll
+                        for (int q = 0; q < KH_TR / NW; ++q) vst[(warp + q * NW) * bw + t] = val[h][q];
+                    }
                 }
             }
             __syncthreads();

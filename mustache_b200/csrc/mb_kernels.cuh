@@ -860,16 +860,23 @@ ks_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     const int cl = (c0 == 0) ? 0 : -1;
     const int cr = KS_K;
 
-    if (threadIdx.x == 0) {
-        for (int d = 0; d < D; ++d) {
-            mbar_init(&full[d], 1);
-            mbar_init(&empty[d], NW);
-            stage_lvl[d] = d;
-        }
+    if (warp == 0) {
+        // steps that form a DoG, in chain order: one step per lane, ranks from a ballot (a serial loop of thread 0 here kept
+        // the other 255 threads of every CTA at the barrier below for ~4 % of the kernel's time)
         int nlev = 0;
-        for (int s = 0; s < prog.n_steps; ++s)
-            if (!(prog.st[s].flags & MB_FLAG_RESTART)) lvl_step[nlev++] = s;            // steps that form a DoG
-        n_levels_s = nlev;
+        for (int s0 = 0; s0 < prog.n_steps; s0 += 32) {
+            const int s = s0 + lane;
+            const bool forms = s < prog.n_steps && !(prog.st[s].flags & MB_FLAG_RESTART);
+            const unsigned m = __ballot_sync(0xffffffffu, forms);
+            if (forms) lvl_step[nlev + __popc(m & ((1u << lane) - 1u))] = s;
+            nlev += __popc(m);
+        }
+        if (lane < D) {
+            mbar_init(&full[lane], 1);
+            mbar_init(&empty[lane], NW);
+            stage_lvl[lane] = lane;
+        }
+        if (lane == 0) n_levels_s = nlev;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();

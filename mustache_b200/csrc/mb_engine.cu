@@ -564,15 +564,37 @@ static void plan_ring(const MbProgram& p, int cap, MbStage* stage, int fused_tc 
         const int w = fused_tc ? kf_box_width(p.st[s].radius, fused_tc) : kh_box_width(p.st[s].radius);
         return (KH_TR * w + 15) & ~15;
     };
+    // Boxes small enough for three to fit are packed one after the other, wrapping at the end of the ring.  Larger boxes
+    // alternate between the two ENDS of the ring: packed from the bottom, a growing box that wraps to offset 0 reaches into
+    // the box of the step before it, and its load can then only start when that step is over (every second step of the
+    // largest radii of the 4-octave chain was serialised with its own load that way: 8 % of the axis-1 kernel's samples
+    // sat in that one wait).  From the two ends, consecutive boxes overlap only if their sum exceeds the ring.
+    // (Each large box takes the end whose latest overlapped box is the older one; ties alternate.)
+    auto dep_at = [&](int s, int off, int size) {
+        int dep = -1;
+        for (int t = 0; t < s; ++t)
+            if (stage[t].off < off + size && off < stage[t].off + size_of(t)) dep = t;
+        return dep;
+    };
     int cur = 0;
+    bool top = true;
     for (int s = 0; s < p.n_steps; ++s) {
         const int size = size_of(s);
-        if (cur + size > cap) cur = 0;
-        stage[s].off = cur;
-        stage[s].dep = -1;
-        for (int t = 0; t < s; ++t)
-            if (stage[t].off < cur + size && cur < stage[t].off + size_of(t)) stage[s].dep = t;
-        cur += size;
+        int off;
+        if (3 * size > cap && size <= cap) {
+            const int off_top = (cap - size) & ~15;
+            const int dt = dep_at(s, off_top, size), db = dep_at(s, 0, size);
+            const bool use_top = dt != db ? dt < db : top;
+            off = use_top ? off_top : 0;
+            top = !use_top;
+            cur = off + size;
+        } else {
+            if (cur + size > cap) cur = 0;
+            off = cur;
+            cur += size;
+        }
+        stage[s].off = off;
+        stage[s].dep = dep_at(s, off, size);
     }
 }
 

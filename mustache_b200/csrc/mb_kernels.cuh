@@ -166,6 +166,14 @@ constexpr int KS_SC = KS_TC - 2;   // scored columns per CTA
 constexpr int KS_PITCH = KS_TC + 6;   // 70: box width of the staged DoG tile (tile + even start column + row stagger); with
                                       // 70 = 6 (mod 16) and the one-column stagger of rows 8-15 / 24-31 the 16 lanes (= rows) of a
                                       // half warp read 16 different 8-byte bank pairs
+// kh_kernel producer: 0 = warp 0 issues the boxes at the start of its steps and blocks until the boxes they overwrite are
+// released; 1 = every warp, at the start of each of its steps, issues whatever box has become free (non-blocking test of the
+// release barrier, claimed with a CAS on a shared counter): the warp that releases a box last is the one that sees it free
+// first, and nobody waits for somebody else's release.  Measured slower (axis-1 pass 7.66 -> 8.00 ms on the 10k tile, 1.38 ->
+// 1.47 ms on 24 x 2000^2): off
+#ifndef MB_KH_COOP
+#define MB_KH_COOP 0
+#endif
 #ifndef MB_KS_DEPTH
 #define MB_KS_DEPTH 6
 #endif
@@ -549,6 +557,17 @@ __device__ __forceinline__ bool mbar_arrive_is_last(uint64_t* bar) {
         "}" : "=r"(done) : "r"(smem_u32(bar)) : "memory");
     return done != 0;
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -615,10 +634,12 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
     // tiles whose +/- rmax column halo leaves the image need 'reflect' indexing: generic (slow) staging for those
     const bool border = (js - rmax < 0) || (js + KH_TC + 1 + rmax > g.n);
 
+    __shared__ int next_box;                                    // MB_KH_COOP: first box nobody has issued yet
     for (int t = threadIdx.x; t < prog.n_steps; t += KH_THREADS) {
         mbar_init(&full[t], 1);
         mbar_init(&empty[t], NW);
     }
+    if (threadIdx.x == 0) next_box = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int n_steps = prog.n_steps;
@@ -649,7 +670,27 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
             ++next_issue;
         }
     };
-    if (!border && warp == 0) issue_ready(0);   // first boxes in flight before the store geometry below is set up
+    // MB_KH_COOP: any warp, non-blocking
+    auto issue_free = [&](int p_now) {
+        for (int round = 0; round <= KH_LOOKAHEAD; ++round) {
+            const int nb = *(volatile int*)&next_box;
+            if (nb >= n_steps || nb > p_now + KH_LOOKAHEAD) break;
+            const int dep = stg[nb].dep;
+            if (dep >= 0 && !mbar_test(&empty[dep], 0)) break;               // the box it overwrites is still being read
+            if (elect_one()) {
+                if (atomicCAS(&next_box, nb, nb + 1) == nb) {
+                    const int R = prog.st[nb].radius;
+                    mbar_arrive_expect_tx(&full[nb], (uint32_t)(KH_TR * kh_box_width(R)) * 8u);
+                    tma_load_box3d(vbuf + stg[nb].off, &tm->v[nb], (js - R - g.vlo) & ~1, i0, nb * g.zstride + g.zoff + b, &full[nb]);
+                }
+            }
+            __syncwarp();
+        }
+    };
+    if (!border && warp == 0) {                 // first boxes in flight before the store geometry below is set up
+        if (MB_KH_COOP) issue_free(0);
+        else issue_ready(0);
+    }
     // any pixel of this warp's 32 x 9 chunk on a diagonal the detector reads (2 .. dhi+2)?
     const bool chunk_live = (js + warp * KH_K + KH_K - i0 >= 2) && (js + warp * KH_K - (i0 + KH_TR - 1) <= g.dhi + 2) &&
                             (js + warp * KH_K < g.n);
@@ -696,7 +737,8 @@ kh_kernel(const __grid_constant__ MbProgram prog, const MbTensorMaps* __restrict
         const int bw = kh_box_width(R);                          // row pitch of this step's staged box
         const int shift = border ? 0 : ((js - R - g.vlo) & 1);   // the box starts one column early when that is odd
         if (!border) {
-            if (warp == 0) issue_ready(s);
+            if (MB_KH_COOP) issue_free(s);
+            else if (warp == 0) issue_ready(s);
             mbar_wait(&full[s], 0);
         } else {
             __syncthreads();                                     // previous step's readers are done with the buffer

@@ -218,6 +218,12 @@ MB200_API int mb200_normalize_sparse(mb200_engine* e, const int32_t* x, const in
  * (steps of a group share the folded pair sums x[-j] + x[j], which do not depend on the Gaussian) and the FP64
  * instructions per output pixel the plan costs, sum over groups of R_group*(2n+1)+n.  Either output may be NULL. */
 MB200_API int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, int64_t* fp64_per_output);
+/* Host-only inspection of the axis-1 kernel's staging ring (no engine, no device): for every chain step the offset and size
+ * (in doubles) of its TMA box in the shared-memory ring and the latest earlier step whose box it overwrites (-1: none) --
+ * the load of step s can start once step dep[s] has been released by every warp; ring_doubles receives the capacity.
+ * Any output may be NULL. */
+MB200_API int mb200_kh_ring_plan(int n_steps, const int32_t* radius, int32_t* offset, int32_t* size, int32_t* dep,
+                                 int32_t* ring_doubles);
 
 /* Native reader of the text contact format, the parse half of read_pd() (mustache.py:254-263: get_sep, pd.read_csv(header=None),
  * dropna, the is_chr filter on both chromosome columns of a 5-column file).  Host only, multi-threaded over a memory map

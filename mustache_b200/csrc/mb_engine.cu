@@ -1751,6 +1751,27 @@ int mb200_kv_plan(int n_steps, const int32_t* radius, int32_t* group_of_step, in
     return MB200_OK;
 }
 
+int mb200_kh_ring_plan(int n_steps, const int32_t* radius, int32_t* offset, int32_t* size, int32_t* dep, int32_t* ring_doubles) {
+    if (!radius || n_steps < 1 || n_steps > MB_MAX_STEPS) return MB200_ERR_ARG;
+    static MbProgram p;                      // host-only helper, no engine: large structs stay off the stack
+    memset(&p, 0, sizeof(p));
+    p.n_steps = n_steps;
+    for (int s = 0; s < n_steps; ++s) {
+        if (radius[s] < 1) return MB200_ERR_ARG;
+        p.st[s].radius = radius[s];
+        p.rmax = std::max(p.rmax, (int)radius[s]);
+    }
+    if (kh_smem_bytes(p.rmax, 1) > 227 * 1024) return MB200_ERR_ARG;
+    plan_kh_ring(p);
+    for (int s = 0; s < n_steps; ++s) {
+        if (offset) offset[s] = p.stage[s].off;
+        if (size) size[s] = (KH_TR * kh_box_width(p.st[s].radius) + 15) & ~15;
+        if (dep) dep[s] = p.stage[s].dep;
+    }
+    if (ring_doubles) *ring_doubles = kh_ring_doubles(p.rmax);
+    return MB200_OK;
+}
+
 int mb200_contacts_open(const char* path, const char* chromosome, int threads, void** handle, int64_t* n_rows, int* n_cols,
                         int* value_is_int) {
     if (!path || !handle) return MB200_ERR_ARG;

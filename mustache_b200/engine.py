@@ -66,6 +66,7 @@ SIGNATURES = {
     "mb200_normalize_sparse": (C.c_int, [_H, _i32p, _i32p, _f64p, C.c_int64, C.c_int, C.c_int, _f64p, C.c_int,
                                          C.POINTER(C.c_int)]),
     "mb200_kv_plan": (C.c_int, [C.c_int, _i32p, _i32p, _i64p]),
+    "mb200_kh_ring_plan": (C.c_int, [C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "mb200_contacts_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), _i64p, C.POINTER(C.c_int),
                                       C.POINTER(C.c_int)]),
     "mb200_contacts_read": (C.c_int, [C.c_void_p, _i64p, _i64p, _f64p]),

@@ -83,3 +83,26 @@ def test_kv_plan_is_a_partition_with_the_optimal_cost():
         assert exec_instr == cost.value + int(sum(3 * r + 1 for r in radius))        # axis-0 plan + axis-1 pass
         assert cost.value < sum(3 * r + 1 for r in radius)                            # sharing always pays
     assert lib.mb200_kv_plan(0, None, None, None) != 0
+
+
+def test_kh_ring_plan_keeps_two_boxes_in_flight():
+    """The axis-1 kernel's staging ring (host-only entry point): boxes stay inside the ring on 128-byte boundaries, a box
+    only overlaps boxes of steps up to the one it declares as its dependency, and -- the point of placing large boxes at
+    alternating ends of the ring -- the box of step s never has to wait for step s - 1 (its load can overlap that step)."""
+    from mustache_b200 import engine, ladder
+    lib = engine.load_library()
+    for octs in ([1.6, 3.2], [1.6, 3.2, 6.4], [1.6, 3.2, 6.4, 12.8], [0.7, 1.4, 2.8, 5.6, 11.2], [2.3], [4.0, 9.0]):
+        radius = np.array([s.radius for s in ladder.build_program(octs).steps], np.int32)
+        n = len(radius)
+        off, size, dep = (np.zeros(n, np.int32) for _ in range(3))
+        cap = C.c_int32(0)
+        ptr = lambda a: a.ctypes.data_as(engine._i32p)
+        assert lib.mb200_kh_ring_plan(n, ptr(radius), ptr(off), ptr(size), ptr(dep), C.byref(cap)) == 0
+        assert (off % 16 == 0).all() and (off >= 0).all() and (off + size <= cap.value).all()
+        assert cap.value * 8 <= 112 * 1024
+        for s in range(n):
+            over = [t for t in range(s) if off[t] < off[s] + size[s] and off[s] < off[t] + size[t]]
+            assert dep[s] == (max(over) if over else -1)
+            if s >= 2:
+                assert dep[s] <= s - 2, (octs, s, int(radius[s]))        # double buffered at the very least
+    assert lib.mb200_kh_ring_plan(0, None, None, None, None, None) != 0

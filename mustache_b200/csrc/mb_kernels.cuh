@@ -191,7 +191,10 @@ __host__ __device__ inline int kh_box_width(int R) {
 }
 __host__ __device__ inline int kh_vbuf_pitch(int rmax) { return kh_box_width(rmax); }
 // staging ring of kh_kernel: half an SM's shared memory (two CTAs per SM), at least two of the widest boxes
-constexpr int KH_LOOKAHEAD = 4;        // at most this many steps ahead of the slowest warp (6: no measurable difference)
+#ifndef MB_KH_LOOKAHEAD
+#define MB_KH_LOOKAHEAD 4
+#endif
+constexpr int KH_LOOKAHEAD = MB_KH_LOOKAHEAD;        // at most this many steps ahead of the slowest warp (6: no measurable difference)
 #ifndef MB_KH_PREFETCH
 #define MB_KH_PREFETCH 0
 #endif

@@ -417,10 +417,17 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False, eng2=None):
     # Two engine handles on the GPU used alternately (mb200_run_after): the run of batch k+1 follows the run of batch k back
     # to back while BH / selection / filters and the candidate fetch of batch k overlap it.  The timed region starts with an
     # empty pipeline and ends with every result on the host: `steps` uploads, runs and fetches.
+    ready = 0
     if eng2 is not None:
-        try:
+        try:                                               # the second engine's scratch is allocated here
             eng2.set_octaves(cfg["octaves"], differential=(nmaps == 2))
             eng2.configure(n, dpx, max(nblk, nmaps))
+            ready = 1
+        except Exception as err:
+            e2e_mode += " (second engine unavailable: %s)" % str(err)[:120]
+    # every rank takes the same path (the fetches below contain a collective): all of them pipeline, or none does
+    if -h.max_over_ranks(-ready) > 0:
+        try:
             engines = [eng, eng2]
 
             def upload_to(e):
@@ -469,8 +476,10 @@ def measure(h, eng, cfg, name, steps, warmup, device_only=False, eng2=None):
             eng2.sync()
             if trace is not None:
                 sys.stderr.write("pipeline trace (run enqueue, upload enqueue, fetch, device run ms, post ms): %s\n" % trace[-(steps + 1):])
-        except Exception as err:                           # e.g. not enough memory for the second engine's scratch
-            e2e_mode += " (two-engine pipeline unavailable: %s)" % str(err)[:120]
+        except Exception as err:
+            if world > 1:                                  # the other ranks are inside the collectives of the pipeline
+                raise
+            e2e_mode += " (two-engine pipeline failed: %s)" % str(err)[:120]
             eng.configure(n, dpx, max(nblk, nmaps))
             upload()
             run()
